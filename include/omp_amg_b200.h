@@ -1,0 +1,97 @@
+/*
+ * omp_amg_b200.h -- C ABI of the B200 AMG hierarchy-construction engine.
+ *
+ * Drop-in boundary for the serial AMG setup path of nicooff/omp_amg (gslib's AMG coarse
+ * solver).  Plain pointers and sizes only.  Every entry point names the reference interface it
+ * replaces.  All functions return 0 on success and a negative code on failure;
+ * amgb_last_error() gives the message.  There is no CPU path: without a CUDA device
+ * amgb_init / amgb_setup fail with code -101.
+ *
+ * Data layout handed back by the accessors is the reference's struct csr_mat
+ * (amg_tools.h:5): row offsets, ascending column indices per row, fp64 values -- with int32
+ * indices instead of the reference's build-time "uint".
+ */
+#ifndef OMP_AMG_B200_H
+#define OMP_AMG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct amgb_hier amgb_hier;
+
+/* ---- runtime ---- */
+int amgb_device_count(void);
+int amgb_init(int device);                 /* device < 0: keep the current device */
+const char *amgb_last_error(void);
+const char *amgb_build_info(void);         /* "cuda sm_100a ..." or "host-emulation (tests)" */
+
+/* ---- setup: replaces amg_setup() (amg_setup.h:5, amg_setup.c:60) ----
+ * Input is the assembled matrix as COO triplets, 0-based, exactly what serial_amg.c:76-96
+ * builds from amgdmp_{i,j,p}.dat.  Zero values are dropped, empty rows/columns removed
+ * (build_csr, amg_setup.c:3612).  The hierarchy stays resident in HBM. */
+int amgb_setup(int64_t nnz, const int32_t *Ai, const int32_t *Aj, const double *Av,
+               amgb_hier **out);                                   /* HOST buffers */
+int amgb_setup_device(int64_t nnz, const int32_t *dAi, const int32_t *dAj, const double *dAv,
+                      amgb_hier **out);                            /* buffers already in HBM */
+/* reads amgdmp_i.dat, amgdmp_j.dat, amgdmp_p.dat from dir (serial_amg.c main) */
+int amgb_setup_from_dump(const char *dir, amgb_hier **out);
+void amgb_free(amgb_hier *h);
+
+/* ---- struct amg_setup_data accessors (amg_tools.h:29) ---- */
+int amgb_nlevels(const amgb_hier *h);      /* data->nlevels   */
+int amgb_nullspace(const amgb_hier *h);    /* data->nullspace */
+/* info[0]=n info[1]=nnz(A) info[2]=nf info[3]=nc info[4]=nnz(Af) info[5]=nnz(W) info[6]=nnz(AfP)
+   info[7]=coarsening rounds info[8]=Lanczos iterations info[9]=interpolation rounds */
+int amgb_level_info(const amgb_hier *h, int lvl, int64_t info[10]);
+/* par[0]=data->m[lvl] par[1]=data->rho[lvl] par[2],par[3]=Lanczos lambda_min, lambda_max */
+int amgb_level_params(const amgb_hier *h, int lvl, double par[4]);
+enum { AMGB_A = 0, AMGB_AF = 1, AMGB_W = 2, AMGB_AFP = 3 };   /* data->A/Af/W/AfP[lvl] */
+/* Copies one matrix to HOST buffers; pass NULL arrays to query rn/cn/nnz first. */
+int amgb_get_csr(const amgb_hier *h, int lvl, int which, int32_t *rn, int32_t *cn, int64_t *nnz,
+                 int32_t *row_off, int32_t *col, double *a);
+enum { AMGB_C = 0, AMGB_D = 1, AMGB_IDC = 2, AMGB_IDF = 3 };  /* data->C/D/idc/idf[lvl] */
+int amgb_get_vec(const amgb_hier *h, int lvl, int which, double *out);
+
+/* ---- replaces amg_export() (amg_setup.h:9, amg_setup.c:405) ----
+ * Writes amg.dat, amg_W.dat, amg_AfP.dat, amg_Aff.dat into dir in the reference's format
+ * (the files amg.c:813 read_data consumes). */
+int amgb_export(const amgb_hier *h, const char *dir);
+
+/* ---- V-cycle: replaces amg_exec()+crs_solve() (amg.c:114, amg.c:171), one process ---- */
+int amgb_solve(const amgb_hier *h, double *x, const double *b);                /* HOST vectors */
+int amgb_solve_device(const amgb_hier *h, double *dx, const double *db);      /* HBM vectors  */
+
+/* ---- measurement ----
+ * t[0]=total t[1]=build_csr t[2]=coarsen t[3]=smoother t[4]=lanczos t[5]=interpolation
+ * t[6]=galerkin (host seconds, stream synchronised at stage ends)
+ * t[7]=device seconds inside SpGEMM kernels  t[8]=their algorithmic bytes  t[9]=SpGEMM calls
+ * t[10]=kernel launches  t[11]=host syncs */
+int amgb_timing(const amgb_hier *h, double t[12]);
+
+/* ---- stage trace (debug): FNV-1a hashes of intermediate arrays, in stage order ---- */
+void amgb_trace_enable(int on);
+int amgb_trace_count(void);
+int amgb_trace_get(int i, char *tag, int taglen, uint64_t *hash, int64_t *bytes);
+
+/* ---- gslib coarse-solver slot: crs.h:12-22 ----
+ * Same names, argument meaning and order as the reference (with the crs_amg_ prefix gslib
+ * gives its AMG variant).  uint -> uint32_t, ulong -> uint64_t.  One process: comm must be
+ * NULL or describe np == 1.  id[i] == 0 marks a dof that is not solved for; repeated ids are
+ * the same dof (entries are summed, as gs_setup/assign_dofs do in amg.c:399). */
+struct comm;                       /* gslib's struct comm (comm.h); only np == 1 is accepted */
+struct crs_data;
+struct crs_data *crs_amg_setup(uint32_t n, const uint64_t *id, uint32_t nz, const uint32_t *Ai,
+                               const uint32_t *Aj, const double *A, uint32_t null_space,
+                               const struct comm *comm);
+void crs_amg_solve(double *x, struct crs_data *data, double *b);
+void crs_amg_stats(struct crs_data *data);
+void crs_amg_free(struct crs_data *data);
+amgb_hier *crs_amg_hierarchy(struct crs_data *data);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,233 @@
+"""ctypes binding of include/omp_amg_b200.h and the host-side mirror of the reference API.
+
+Reference interfaces mirrored here:
+  * ``amg_setup(n, Ai, Aj, Av, data)``      amg_setup.h:5   -> :func:`amg_setup`
+  * ``amg_export(data)``                    amg_setup.h:9   -> :meth:`Hierarchy.export`
+  * ``struct amg_setup_data`` fields        amg_tools.h:29  -> :class:`Hierarchy` accessors
+  * ``crs_setup / crs_solve / crs_stats / crs_free``  crs.h:14-22 -> functions of the same name
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+_LIB_PATH = os.path.join(_HERE, "libomp_amg_b200.so")
+
+A, AF, W, AFP = 0, 1, 2, 3
+VEC_C, VEC_D, VEC_IDC, VEC_IDF = 0, 1, 2, 3
+
+
+class AmgError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def _declare(L):
+    i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+    f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+    vp = C.c_void_p
+    L.amgb_last_error.restype = C.c_char_p
+    L.amgb_build_info.restype = C.c_char_p
+    L.amgb_init.argtypes = [C.c_int]
+    L.amgb_setup.argtypes = [C.c_int64, i32p, i32p, f64p, C.POINTER(vp)]
+    L.amgb_setup_device.argtypes = [C.c_int64, vp, vp, vp, C.POINTER(vp)]
+    L.amgb_setup_from_dump.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.amgb_free.argtypes = [vp]
+    L.amgb_free.restype = None
+    L.amgb_nlevels.argtypes = [vp]
+    L.amgb_nullspace.argtypes = [vp]
+    L.amgb_level_info.argtypes = [vp, C.c_int, C.POINTER(C.c_int64)]
+    L.amgb_level_params.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
+    L.amgb_get_csr.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                               C.POINTER(C.c_int64), vp, vp, vp]
+    L.amgb_get_vec.argtypes = [vp, C.c_int, C.c_int, f64p]
+    L.amgb_export.argtypes = [vp, C.c_char_p]
+    L.amgb_solve.argtypes = [vp, f64p, f64p]
+    L.amgb_solve_device.argtypes = [vp, vp, vp]
+    L.amgb_timing.argtypes = [vp, C.POINTER(C.c_double)]
+    L.amgb_trace_enable.argtypes = [C.c_int]
+    L.amgb_trace_enable.restype = None
+    L.amgb_trace_get.argtypes = [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]
+    u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+    u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+    L.crs_amg_setup.argtypes = [C.c_uint32, u64p, C.c_uint32, u32p, u32p, f64p, C.c_uint32, vp]
+    L.crs_amg_setup.restype = vp
+    L.crs_amg_solve.argtypes = [f64p, vp, f64p]
+    L.crs_amg_solve.restype = None
+    L.crs_amg_stats.argtypes = [vp]
+    L.crs_amg_stats.restype = None
+    L.crs_amg_free.argtypes = [vp]
+    L.crs_amg_free.restype = None
+    L.crs_amg_hierarchy.argtypes = [vp]
+    L.crs_amg_hierarchy.restype = vp
+    return L
+
+
+def lib(path=None):
+    """Load the CUDA library.  Raises if it has not been built: there is no fallback."""
+    global _LIB
+    if path is not None:
+        return _declare(C.CDLL(path))
+    if _LIB is None:
+        if not os.path.exists(_LIB_PATH):
+            raise AmgError("%s is missing: run `make -C omp_amg_b200/csrc` (or __graft_entry__.build()); "
+                           "omp_amg_b200 has no CPU implementation" % _LIB_PATH)
+        _LIB = _declare(C.CDLL(_LIB_PATH))
+    return _LIB
+
+
+def build_info(L=None):
+    return (L or lib()).amgb_build_info().decode()
+
+
+def device_count(L=None):
+    return (L or lib()).amgb_device_count()
+
+
+def _check(L, rc):
+    if rc != 0:
+        raise AmgError("omp_amg_b200 error %d: %s" % (rc, L.amgb_last_error().decode()))
+
+
+class Hierarchy:
+    """Handle to a hierarchy resident in HBM (the reference's ``struct amg_setup_data``)."""
+
+    def __init__(self, L, handle):
+        self._L = L
+        self._h = handle
+
+    # -- struct amg_setup_data --
+    @property
+    def nlevels(self):
+        return self._L.amgb_nlevels(self._h)
+
+    @property
+    def nullspace(self):
+        return self._L.amgb_nullspace(self._h)
+
+    def level_info(self, lvl):
+        info = (C.c_int64 * 10)()
+        _check(self._L, self._L.amgb_level_info(self._h, lvl, info))
+        keys = ("n", "nnz", "nf", "nc", "nnzf", "nnzw", "nnzfp", "coarsen_rounds", "lanczos_iters", "interp_rounds")
+        return dict(zip(keys, list(info)))
+
+    def level_params(self, lvl):
+        par = (C.c_double * 4)()
+        _check(self._L, self._L.amgb_level_params(self._h, lvl, par))
+        return {"m": par[0], "rho": par[1], "lambda_min": par[2], "lambda_max": par[3]}
+
+    def csr(self, lvl, which):
+        """(row_off, col, a, (rn, cn)) of data->A/Af/W/AfP[lvl], copied to host."""
+        rn, cn, nnz = C.c_int32(), C.c_int32(), C.c_int64()
+        _check(self._L, self._L.amgb_get_csr(self._h, lvl, which, C.byref(rn), C.byref(cn), C.byref(nnz),
+                                              None, None, None))
+        ro = np.zeros(rn.value + 1, np.int32)
+        col = np.zeros(max(nnz.value, 1), np.int32)
+        a = np.zeros(max(nnz.value, 1), np.float64)
+        _check(self._L, self._L.amgb_get_csr(self._h, lvl, which, None, None, None, ro.ctypes.data,
+                                              col.ctypes.data, a.ctypes.data))
+        return ro, col[:nnz.value], a[:nnz.value], (rn.value, cn.value)
+
+    def vec(self, lvl, which):
+        info = self.level_info(lvl)
+        ln = {VEC_C: info["n"], VEC_D: info["nf"], VEC_IDC: info["nc"], VEC_IDF: info["nf"]}[which]
+        out = np.zeros(max(ln, 1), np.float64)
+        _check(self._L, self._L.amgb_get_vec(self._h, lvl, which, out))
+        return out[:ln]
+
+    # -- amg_export --
+    def export(self, dirname):
+        _check(self._L, self._L.amgb_export(self._h, os.fsencode(dirname)))
+
+    # -- amg_exec + crs_solve projection --
+    def solve(self, b):
+        b = np.ascontiguousarray(b, np.float64)
+        x = np.zeros_like(b)
+        _check(self._L, self._L.amgb_solve(self._h, x, b))
+        return x
+
+    def solve_device(self, x_ptr, b_ptr):
+        _check(self._L, self._L.amgb_solve_device(self._h, x_ptr, b_ptr))
+
+    def timing(self):
+        t = (C.c_double * 12)()
+        _check(self._L, self._L.amgb_timing(self._h, t))
+        keys = ("total", "build_csr", "coarsen", "smoother", "lanczos", "interp", "galerkin",
+                "spgemm_device_s", "spgemm_bytes", "spgemm_calls", "launches", "syncs")
+        return dict(zip(keys, list(t)))
+
+    def free(self):
+        if self._h:
+            self._L.amgb_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def amg_setup(Ai, Aj, Av, L=None, device_ptrs=False, nnz=None):
+    """``amg_setup`` (amg_setup.c:60).  ``Ai, Aj`` 0-based int32, ``Av`` float64 host arrays; with
+    ``device_ptrs=True`` they are raw device addresses (ints) of arrays already in HBM."""
+    L = L or lib()
+    h = C.c_void_p()
+    if device_ptrs:
+        _check(L, L.amgb_setup_device(int(nnz), C.c_void_p(Ai), C.c_void_p(Aj), C.c_void_p(Av), C.byref(h)))
+    else:
+        Ai = np.ascontiguousarray(Ai, np.int32)
+        Aj = np.ascontiguousarray(Aj, np.int32)
+        Av = np.ascontiguousarray(Av, np.float64)
+        _check(L, L.amgb_setup(len(Av), Ai, Aj, Av, C.byref(h)))
+    return Hierarchy(L, h)
+
+
+def amg_setup_from_dump(dirname, L=None):
+    """The reference driver's input path (serial_amg.c:76-96): amgdmp_{i,j,p}.dat in ``dirname``."""
+    L = L or lib()
+    h = C.c_void_p()
+    _check(L, L.amgb_setup_from_dump(os.fsencode(dirname), C.byref(h)))
+    return Hierarchy(L, h)
+
+
+class _Crs:
+    def __init__(self, L, ptr, n):
+        self.L, self.ptr, self.n = L, ptr, n
+
+
+def crs_setup(n, id, nz, Ai, Aj, A, null_space, comm=None, L=None):
+    """``crs_setup`` (crs.h:14): same argument order and meaning as the reference."""
+    L = L or lib()
+    id = np.ascontiguousarray(id, np.uint64)
+    Ai = np.ascontiguousarray(Ai, np.uint32)
+    Aj = np.ascontiguousarray(Aj, np.uint32)
+    A = np.ascontiguousarray(A, np.float64)
+    p = L.crs_amg_setup(n, id, nz, Ai, Aj, A, null_space, comm)
+    if not p:
+        raise AmgError("crs_setup failed: %s" % L.amgb_last_error().decode())
+    return _Crs(L, p, n)
+
+
+def crs_solve(x, data, b):
+    """``crs_solve`` (crs.h:18): x and b are local vectors of length n."""
+    b = np.ascontiguousarray(b, np.float64)
+    assert x.dtype == np.float64 and x.flags.c_contiguous
+    data.L.crs_amg_solve(x, data.ptr, b)
+
+
+def crs_stats(data):
+    data.L.crs_amg_stats(data.ptr)
+
+
+def crs_free(data):
+    if data.ptr:
+        data.L.crs_amg_free(data.ptr)
+        data.ptr = None

@@ -1,0 +1,386 @@
+// capi.cu -- the C ABI declared in include/omp_amg_b200.h.
+#include "../../include/omp_amg_b200.h"
+#include "setup.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <string>
+
+using namespace amgb;
+
+struct amgb_hier { Hierarchy H; };
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define API_BEGIN try {
+#define API_END                                                                  \
+  }                                                                              \
+  catch (const amgb::Error &e) { return fail(e.code, e.what()); }                \
+  catch (const std::exception &e) { return fail(-1, e.what()); }                 \
+  catch (...) { return fail(-1, "unknown error"); }
+
+extern "C" {
+
+const char *amgb_last_error(void) { return g_err.c_str(); }
+
+const char *amgb_build_info(void) {
+#ifdef AMGB_EMU
+  return "host-emulation (tests only, not a product path)";
+#else
+  return "cuda sm_100a, fp64, fmad=false";
+#endif
+}
+
+int amgb_device_count(void) {
+#ifdef AMGB_EMU
+  return 0;
+#else
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+#endif
+}
+
+int amgb_init(int device) {
+  API_BEGIN
+  ctx_init(device);
+  return 0;
+  API_END
+}
+
+int amgb_setup_device(int64_t nnz, const int32_t *dAi, const int32_t *dAj, const double *dAv,
+                      amgb_hier **out) {
+  API_BEGIN
+  if (!out) return fail(-2, "null output pointer");
+  *out = nullptr;
+  ctx_init(-1);
+  if (nnz <= 0) return fail(-2, "empty matrix");
+  amgb_hier *h = new amgb_hier();
+  try { setup(nnz, dAi, dAj, dAv, h->H); }
+  catch (...) { delete h; throw; }
+  *out = h;
+  return 0;
+  API_END
+}
+
+int amgb_setup(int64_t nnz, const int32_t *Ai, const int32_t *Aj, const double *Av, amgb_hier **out) {
+  API_BEGIN
+  if (!out) return fail(-2, "null output pointer");
+  *out = nullptr;
+  ctx_init(-1);
+  if (nnz <= 0 || !Ai || !Aj || !Av) return fail(-2, "empty matrix");
+  Buf<int> dAi(nnz), dAj(nnz);
+  Buf<double> dAv(nnz);
+  dAi.upload(Ai, nnz); dAj.upload(Aj, nnz); dAv.upload(Av, nnz);
+  return amgb_setup_device(nnz, dAi.p, dAj.p, dAv.p, out);
+  API_END
+}
+
+static int read_dump_file(const std::string &path, std::vector<double> &v) {
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f) return -1;
+  fseek(f, 0, SEEK_END);
+  long n = ftell(f) / (long)sizeof(double);
+  fseek(f, 0, SEEK_SET);
+  v.resize((size_t)n);
+  size_t got = fread(v.data(), sizeof(double), (size_t)n, f);
+  fclose(f);
+  if ((long)got != n || n < 1) return -2;
+  if (std::fabs(v[0] - 3.14159) > 1e-6) {   // endianness marker (serial_amg.c:59)
+    for (double &x : v) { unsigned char *b = (unsigned char *)&x; std::reverse(b, b + 8); }
+    if (std::fabs(v[0] - 3.14159) > 1e-6) return -3;
+  }
+  return 0;
+}
+
+int amgb_setup_from_dump(const char *dir, amgb_hier **out) {
+  API_BEGIN
+  std::vector<double> vi, vj, vp;
+  std::string d(dir ? dir : ".");
+  if (read_dump_file(d + "/amgdmp_i.dat", vi) || read_dump_file(d + "/amgdmp_j.dat", vj) ||
+      read_dump_file(d + "/amgdmp_p.dat", vp))
+    return fail(-20, "cannot read amgdmp_{i,j,p}.dat in " + d);
+  if (vi.size() != vj.size() || vi.size() != vp.size()) return fail(-21, "amgdmp files differ in length");
+  const size_t n = vi.size() - 1;
+  std::vector<int32_t> Ai(n), Aj(n);
+  for (size_t k = 0; k < n; k++) { Ai[k] = (int32_t)vi[k + 1] - 1; Aj[k] = (int32_t)vj[k + 1] - 1; }
+  return amgb_setup((int64_t)n, Ai.data(), Aj.data(), vp.data() + 1, out);
+  API_END
+}
+
+void amgb_free(amgb_hier *h) { delete h; }
+
+int amgb_nlevels(const amgb_hier *h) { return h ? (int)h->H.lv.size() : 0; }
+int amgb_nullspace(const amgb_hier *h) { return h ? h->H.nullspace : 0; }
+
+int amgb_level_info(const amgb_hier *h, int l, int64_t info[10]) {
+  if (!h || l < 0 || l >= (int)h->H.lv.size()) return fail(-2, "level out of range");
+  const Level &L = h->H.lv[(size_t)l];
+  info[0] = L.n; info[1] = L.A.nnz; info[2] = L.nf; info[3] = L.nc; info[4] = L.Af.nnz;
+  info[5] = L.W.nnz; info[6] = L.AfP.nnz; info[7] = L.coarsen_rounds; info[8] = L.lanczos_k;
+  info[9] = L.interp_rounds;
+  return 0;
+}
+int amgb_level_params(const amgb_hier *h, int l, double par[4]) {
+  if (!h || l < 0 || l >= (int)h->H.lv.size()) return fail(-2, "level out of range");
+  const Level &L = h->H.lv[(size_t)l];
+  par[0] = L.m; par[1] = L.rho; par[2] = L.lmin; par[3] = L.lmax;
+  return 0;
+}
+
+static const Csr *pick(const amgb_hier *h, int l, int which) {
+  if (!h || l < 0 || l >= (int)h->H.lv.size()) return nullptr;
+  const Level &L = h->H.lv[(size_t)l];
+  const bool last = (l == (int)h->H.lv.size() - 1);
+  switch (which) {
+    case AMGB_A: return &L.A;
+    case AMGB_AF: return last ? nullptr : &L.Af;
+    case AMGB_W: return last ? nullptr : &L.W;
+    case AMGB_AFP: return last ? nullptr : &L.AfP;
+  }
+  return nullptr;
+}
+
+int amgb_get_csr(const amgb_hier *h, int l, int which, int32_t *rn, int32_t *cn, int64_t *nnz,
+                 int32_t *ro, int32_t *col, double *a) {
+  API_BEGIN
+  const Csr *M = pick(h, l, which);
+  if (!M) return fail(-2, "no such matrix");
+  if (rn) *rn = M->rn;
+  if (cn) *cn = M->cn;
+  if (nnz) *nnz = M->nnz;
+  if (ro) d2h(ro, M->ro.p, sizeof(int) * (size_t)(M->rn + 1));
+  if (col && M->nnz) d2h(col, M->col.p, sizeof(int) * (size_t)M->nnz);
+  if (a && M->nnz) d2h(a, M->a.p, sizeof(double) * (size_t)M->nnz);
+  return 0;
+  API_END
+}
+
+int amgb_get_vec(const amgb_hier *h, int l, int which, double *out) {
+  API_BEGIN
+  if (!h || l < 0 || l >= (int)h->H.lv.size() - 1) return fail(-2, "level out of range");
+  const Level &L = h->H.lv[(size_t)l];
+  switch (which) {
+    case AMGB_C: d2h(out, L.C.p, sizeof(double) * (size_t)L.n); return 0;
+    case AMGB_D: d2h(out, L.D.p, sizeof(double) * (size_t)L.nf); return 0;
+    case AMGB_IDC: { std::vector<int> v = L.idc.download(); for (int i = 0; i < L.nc; i++) out[i] = v[(size_t)i]; return 0; }
+    case AMGB_IDF: { std::vector<int> v = L.idf.download(); for (int i = 0; i < L.nf; i++) out[i] = v[(size_t)i]; return 0; }
+  }
+  return fail(-2, "no such vector");
+  API_END
+}
+
+// ---- amg_export (amg_setup.c:405), savemats (:483), savevec (:550) ----
+namespace {
+struct HostCsr { int rn = 0, cn = 0; std::vector<int> ro, col; std::vector<double> a; };
+HostCsr fetch(const Csr &M) {
+  HostCsr h;
+  h.rn = M.rn; h.cn = M.cn;
+  h.ro = M.ro.download(); h.ro.resize((size_t)M.rn + 1);
+  h.col = M.col.download(); h.col.resize((size_t)M.nnz);
+  h.a = M.a.download(); h.a.resize((size_t)M.nnz);
+  return h;
+}
+int save_mats(std::vector<int> &len, int n, int nl, const std::vector<int> &lvl,
+              const std::vector<HostCsr> &mats, const std::vector<std::vector<int>> &ids,
+              const std::string &path) {
+  const double magic = 3.14159;
+  FILE *f = fopen(path.c_str(), "wb");
+  if (!f) return -1;
+  fwrite(&magic, sizeof(double), 1, f);
+  std::vector<int> row((size_t)nl, 0);
+  std::vector<double> buf;
+  for (int i = 0; i < n; i++) {
+    const int l = lvl[(size_t)i] - 1;
+    if (l >= nl) { len[(size_t)i] = 0; continue; }
+    const HostCsr &M = mats[(size_t)l];
+    const int j = row[(size_t)l]++;
+    const int kb = M.ro[(size_t)j], ke = M.ro[(size_t)j + 1];
+    buf.clear();
+    for (int k = kb; k < ke; k++) { buf.push_back((double)ids[(size_t)l][(size_t)M.col[(size_t)k]]); buf.push_back(M.a[(size_t)k]); }
+    len[(size_t)i] = ke - kb;
+    if (!buf.empty()) fwrite(buf.data(), sizeof(double), buf.size(), f);
+  }
+  fclose(f);
+  return 0;
+}
+}  // namespace
+
+int amgb_export(const amgb_hier *h, const char *dir) {
+  API_BEGIN
+  if (!h) return fail(-2, "null hierarchy");
+  const Hierarchy &H = h->H;
+  const int nl = (int)H.lv.size(), n = H.lv[0].n;
+  if (nl < 2) return fail(-2, "single-level hierarchy has nothing to export");
+  std::vector<int> lvl((size_t)n, 1);
+  std::vector<double> dvec((size_t)n, 0.0);
+  std::vector<std::vector<int>> idc((size_t)nl - 1), idf((size_t)nl - 1);
+  std::vector<HostCsr> W, P, F;
+  for (int i = 0; i < nl - 1; i++) {
+    const Level &L = H.lv[(size_t)i];
+    idc[(size_t)i] = L.idc.download(); idc[(size_t)i].resize((size_t)L.nc);
+    idf[(size_t)i] = L.idf.download(); idf[(size_t)i].resize((size_t)L.nf);
+    std::vector<double> D = L.D.download();
+    for (int j = 0; j < L.nc; j++) lvl[(size_t)idc[(size_t)i][(size_t)j] - 1] += 1;
+    for (int j = 0; j < L.nf; j++) dvec[(size_t)idf[(size_t)i][(size_t)j] - 1] = D[(size_t)j];
+    W.push_back(fetch(L.W)); P.push_back(fetch(L.AfP)); F.push_back(fetch(L.Af));
+  }
+  const int k = idc[(size_t)nl - 2][0] - 1;
+  dvec[(size_t)k] = H.nullspace ? 0. : 1. / H.lv[(size_t)nl - 1].A.a.get(0);
+  std::vector<int> Wl((size_t)n), Pl((size_t)n), Fl((size_t)n);
+  const std::string d(dir ? dir : ".");
+  if (save_mats(Wl, n, nl - 1, lvl, W, idc, d + "/amg_W.dat") ||
+      save_mats(Pl, n, nl - 1, lvl, P, idc, d + "/amg_AfP.dat") ||
+      save_mats(Fl, n, nl - 1, lvl, F, idf, d + "/amg_Aff.dat"))
+    return fail(-22, "cannot write amg_*.dat in " + d);
+  FILE *f = fopen((d + "/amg.dat").c_str(), "wb");
+  if (!f) return fail(-22, "cannot write amg.dat in " + d);
+  const double magic = 3.14159, stamp = 2.01;
+  double t;
+  fwrite(&magic, sizeof(double), 1, f);
+  fwrite(&stamp, sizeof(double), 1, f);
+  t = nl; fwrite(&t, sizeof(double), 1, f);
+  for (int i = 0; i < nl - 1; i++) { t = H.lv[(size_t)i].m; fwrite(&t, sizeof(double), 1, f); }
+  for (int i = 0; i < nl - 1; i++) { t = H.lv[(size_t)i].rho; fwrite(&t, sizeof(double), 1, f); }
+  t = n; fwrite(&t, sizeof(double), 1, f);
+  for (int i = 0; i < n; i++) {
+    const double rec[6] = {(double)(i + 1), (double)lvl[(size_t)i], (double)Wl[(size_t)i], (double)Pl[(size_t)i],
+                           (double)Fl[(size_t)i], dvec[(size_t)i]};
+    fwrite(rec, sizeof(double), 6, f);
+  }
+  fclose(f);
+  return 0;
+  API_END
+}
+
+int amgb_solve_device(const amgb_hier *h, double *dx, const double *db) {
+  API_BEGIN
+  if (!h) return fail(-2, "null hierarchy");
+  vcycle_solve(h->H, dx, db);
+  stream_sync();
+  return 0;
+  API_END
+}
+int amgb_solve(const amgb_hier *h, double *x, const double *b) {
+  API_BEGIN
+  if (!h) return fail(-2, "null hierarchy");
+  const int n = h->H.n0;
+  Buf<double> dx(n), db(n);
+  db.upload(b, n);
+  vcycle_solve(h->H, dx.p, db.p);
+  d2h(x, dx.p, sizeof(double) * (size_t)n);
+  return 0;
+  API_END
+}
+
+int amgb_timing(const amgb_hier *h, double t[12]) {
+  if (!h) return fail(-2, "null hierarchy");
+  const StageTimes &s = h->H.t;
+  t[0] = s.total; t[1] = s.build; t[2] = s.coarsen; t[3] = s.smoother; t[4] = s.lanczos;
+  t[5] = s.interp; t[6] = s.galerkin; t[7] = s.spgemm; t[8] = (double)s.spgemm_bytes;
+  t[9] = (double)s.spgemm_calls; t[10] = (double)h->H.launches; t[11] = (double)h->H.syncs;
+  return 0;
+}
+
+void amgb_trace_enable(int on) { ctx().trace_on = on != 0; ctx().trace.clear(); }
+int amgb_trace_count(void) { return (int)ctx().trace.size(); }
+int amgb_trace_get(int i, char *tag, int taglen, uint64_t *hash, int64_t *bytes) {
+  if (i < 0 || i >= (int)ctx().trace.size()) return -1;
+  const TraceRec &r = ctx().trace[(size_t)i];
+  snprintf(tag, (size_t)taglen, "%s", r.tag.c_str());
+  *hash = r.hash; *bytes = r.bytes;
+  return 0;
+}
+
+// ---- gslib coarse-solver slot (crs.h:12-22), one process ----
+struct crs_data {
+  amgb_hier *h = nullptr;
+  uint32_t n = 0, un = 0, null_space = 0;
+  std::vector<int32_t> umap;     // local dof -> unique dof, -1 for id 0
+  std::vector<double> ub, ux;
+  int64_t solves = 0;
+  double solve_seconds = 0;
+};
+
+struct comm_np1 { void *c; uint32_t id, np; };   // leading fields of gslib's struct comm (comm.h)
+
+struct crs_data *crs_amg_setup(uint32_t n, const uint64_t *id, uint32_t nz, const uint32_t *Ai,
+                               const uint32_t *Aj, const double *A, uint32_t null_space,
+                               const struct comm *comm) {
+  try {
+    if (comm && ((const comm_np1 *)comm)->np != 1) { g_err = "crs_amg_setup: only np == 1 is supported by this build"; return nullptr; }
+    // assign_dofs (amg_tools.c:30): unique non-zero ids, sorted
+    std::vector<uint64_t> uid;
+    for (uint32_t i = 0; i < n; i++) if (id[i]) uid.push_back(id[i]);
+    std::sort(uid.begin(), uid.end());
+    uid.erase(std::unique(uid.begin(), uid.end()), uid.end());
+    crs_data *d = new crs_data();
+    d->n = n; d->un = (uint32_t)uid.size(); d->null_space = null_space;
+    d->umap.assign(n, -1);
+    for (uint32_t i = 0; i < n; i++)
+      if (id[i]) d->umap[i] = (int32_t)(std::lower_bound(uid.begin(), uid.end(), id[i]) - uid.begin());
+    // assemble: entries of the same (row,col) are summed in input order (mat_condense, amg_tools.c:57)
+    struct E { int32_t i, j; double v; };
+    std::vector<E> e;
+    e.reserve(nz);
+    for (uint32_t k = 0; k < nz; k++) {
+      const int32_t i = d->umap[Ai[k]], j = d->umap[Aj[k]];
+      if (i < 0 || j < 0 || std::fabs(A[k]) == 0) continue;     // amg.c:1065
+      e.push_back(E{i, j, A[k]});
+    }
+    std::stable_sort(e.begin(), e.end(), [](const E &a, const E &b) { return a.i != b.i ? a.i < b.i : a.j < b.j; });
+    std::vector<int32_t> ci, cj;
+    std::vector<double> cv;
+    for (size_t k = 0; k < e.size(); k++) {
+      if (!ci.empty() && ci.back() == e[k].i && cj.back() == e[k].j) cv.back() += e[k].v;
+      else { ci.push_back(e[k].i); cj.push_back(e[k].j); cv.push_back(e[k].v); }
+    }
+    if (amgb_setup((int64_t)cv.size(), ci.data(), cj.data(), cv.data(), &d->h) != 0) { delete d; return nullptr; }
+    if ((uint32_t)d->h->H.n0 != d->un) {
+      g_err = "crs_amg_setup: some dofs have an empty matrix row";
+      amgb_free(d->h); delete d; return nullptr;
+    }
+    d->ub.assign(d->un, 0.0); d->ux.assign(d->un, 0.0);
+    return d;
+  } catch (const std::exception &ex) { g_err = ex.what(); return nullptr; }
+}
+
+void crs_amg_solve(double *x, struct crs_data *d, double *b) {
+  if (!d) return;
+  std::fill(d->ub.begin(), d->ub.end(), 0.0);
+  for (uint32_t i = 0; i < d->n; i++) if (d->umap[i] >= 0) d->ub[(size_t)d->umap[i]] += b[i];
+  if (amgb_solve(d->h, d->ux.data(), d->ub.data()) != 0) {
+    fprintf(stderr, "crs_amg_solve: %s\n", g_err.c_str());
+    return;
+  }
+  // the hierarchy projects the mean out when it detected a singular operator; crs_solve does
+  // so when the caller asked for it (amg.c:181)
+  if (d->null_space && !d->h->H.nullspace) {
+    double s = 0;
+    for (double v : d->ux) s += v;
+    const double avg = s / (double)d->un;
+    for (double &v : d->ux) v -= avg;
+  }
+  for (uint32_t i = 0; i < d->n; i++) x[i] = d->umap[i] >= 0 ? d->ux[(size_t)d->umap[i]] : 0.0;
+  d->solves++;
+}
+
+void crs_amg_stats(struct crs_data *d) {
+  if (!d) return;
+  double t[12];
+  amgb_timing(d->h, t);
+  printf("AMG stats:\n  levels=%d rows=%u setup=%0.3e s (coarsen %0.3e, lanczos %0.3e, interp %0.3e, galerkin %0.3e)\n"
+         "  kernel launches=%.0f  V-cycles=%lld\n",
+         amgb_nlevels(d->h), d->un, t[0], t[2], t[4], t[5], t[6], t[10], (long long)d->solves);
+}
+
+void crs_amg_free(struct crs_data *d) {
+  if (!d) return;
+  amgb_free(d->h);
+  delete d;
+}
+
+amgb_hier *crs_amg_hierarchy(struct crs_data *d) { return d ? d->h : nullptr; }
+
+}  // extern "C"

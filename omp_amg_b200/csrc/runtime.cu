@@ -1,0 +1,322 @@
+// runtime.cu -- context, stream-ordered memory, prefix scans, deterministic reductions.
+#include "common.cuh"
+
+namespace amgb {
+
+static Context g_ctx;
+Context &ctx() { return g_ctx; }
+
+#ifndef AMGB_EMU
+// =======================================================================================
+// CUDA build
+// =======================================================================================
+static bool g_inited = false;
+void ctx_init(int device) {
+  if (g_inited) return;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    throw Error(-101, "omp_amg_b200: no CUDA device available (this library has no CPU path)");
+  if (device >= 0) CUDA_CHECK(cudaSetDevice(device));
+  int dev = 0;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+  g_ctx.sm_count = prop.multiProcessorCount;
+  CUDA_CHECK(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+  cudaMemPool_t pool;
+  CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
+  unsigned long long thr = ~0ULL;   // keep freed blocks cached in the pool
+  CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  g_inited = true;
+}
+void *dev_alloc(size_t bytes) {
+  void *p = nullptr;
+  CUDA_CHECK(cudaMallocAsync(&p, bytes ? bytes : 8, g_ctx.stream));
+  return p;
+}
+void dev_free(void *p) { if (p) cudaFreeAsync(p, g_ctx.stream); }
+void dev_memset(void *p, int v, size_t bytes) { if (bytes) CUDA_CHECK(cudaMemsetAsync(p, v, bytes, g_ctx.stream)); }
+void h2d(void *dst, const void *src, size_t bytes) {
+  if (bytes) CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_ctx.stream));
+}
+void d2h(void *dst, const void *src, size_t bytes) {
+  if (bytes) CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_ctx.stream));
+  stream_sync();
+}
+void d2d(void *dst, const void *src, size_t bytes) {
+  if (bytes) CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g_ctx.stream));
+}
+void stream_sync() { CUDA_CHECK(cudaStreamSynchronize(g_ctx.stream)); g_ctx.syncs++; }
+
+// ---- exclusive scan: 1024 items per block, block sums scanned recursively ----
+template <class T>
+__global__ void __launch_bounds__(256) k_scan_block(const T *in, T *out, T *bsum, i64 n) {
+  __shared__ T warp_tot[8];
+  const i64 base = (i64)blockIdx.x * 1024 + threadIdx.x * 4;
+  T v[4], s = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { v[k] = (base + k < n) ? in[base + k] : (T)0; s += v[k]; }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  T incl = s;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    T t = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += t;
+  }
+  if (lane == 31) warp_tot[w] = incl;
+  __syncthreads();
+  T woff = 0;
+  for (int k = 0; k < w; k++) woff += warp_tot[k];
+  T excl = woff + incl - s;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { if (base + k < n) out[base + k] = excl; excl += v[k]; }
+  if (threadIdx.x == 255 && bsum) bsum[blockIdx.x] = woff + incl;
+}
+template <class T>
+__global__ void __launch_bounds__(256) k_scan_add(T *out, const T *boff, i64 n) {
+  i64 i = (i64)blockIdx.x * 1024 + threadIdx.x;
+  T o = boff[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < 4; k++, i += 256) if (i < n) out[i] += o;
+}
+template <class T>
+static void scan_rec(const T *in, T *out, i64 n) {     // out[0..n) exclusive; out[n] untouched
+  if (n <= 0) return;
+  i64 nb = (n + 1023) / 1024;
+  if (nb == 1) {
+    k_scan_block<T><<<1, 256, 0, g_ctx.stream>>>(in, out, (T *)nullptr, n);
+    g_ctx.launches++;
+    return;
+  }
+  Buf<T> bsum(nb), boff(nb);
+  k_scan_block<T><<<(unsigned)nb, 256, 0, g_ctx.stream>>>(in, out, bsum.p, n);
+  g_ctx.launches++;
+  scan_rec<T>(bsum.p, boff.p, nb);
+  k_scan_add<T><<<(unsigned)nb, 256, 0, g_ctx.stream>>>(out, boff.p, n);
+  g_ctx.launches++;
+}
+template <class T>
+__global__ void k_scan_last(const T *in, T *out, i64 n) { out[n] = out[n - 1] + in[n - 1]; }
+template <class T>
+static T scan_total(const T *in, T *out, i64 n) {
+  if (n <= 0) { T z = 0; h2d(out, &z, sizeof(T)); stream_sync(); return 0; }
+  scan_rec<T>(in, out, n);
+  k_scan_last<T><<<1, 1, 0, g_ctx.stream>>>(in, out, n);
+  g_ctx.launches++;
+  T tot;
+  d2h(&tot, out + n, sizeof(T));
+  return tot;
+}
+i64 exclusive_scan(const int *in, int *out, i64 n) { return (i64)scan_total<int>(in, out, n); }
+i64 exclusive_scan64(const i64 *in, i64 *out, i64 n) { return scan_total<i64>(in, out, n); }
+
+// ---- deterministic tree sum ----
+__device__ __forceinline__ double chunk_tree(double x) {
+  __shared__ double wsum[8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) x = __dadd_rn(x, __shfl_down_sync(0xffffffffu, x, off));
+  if (lane == 0) wsum[w] = x;
+  __syncthreads();
+  double y = 0.0;
+  if (w == 0) {
+    y = (lane < 8) ? wsum[lane] : 0.0;
+#pragma unroll
+    for (int off = 4; off >= 1; off >>= 1) y = __dadd_rn(y, __shfl_down_sync(0xffffffffu, y, off));
+  }
+  return y;   // valid in thread 0
+}
+__global__ void __launch_bounds__(256) k_tree_sum(const double *v, i64 n, double *out) {
+  const i64 base = (i64)blockIdx.x * 1024 + threadIdx.x;
+  double x = (base < n) ? v[base] : 0.0;
+  x = __dadd_rn(x, (base + 256 < n) ? v[base + 256] : 0.0);
+  x = __dadd_rn(x, (base + 512 < n) ? v[base + 512] : 0.0);
+  x = __dadd_rn(x, (base + 768 < n) ? v[base + 768] : 0.0);
+  double r = chunk_tree(x);
+  if (threadIdx.x == 0) out[blockIdx.x] = r;
+}
+__global__ void __launch_bounds__(256) k_tree_dot(const double *a, const double *b, i64 n, double *out) {
+  const i64 base = (i64)blockIdx.x * 1024 + threadIdx.x;
+  double x = (base < n) ? __dmul_rn(a[base], b[base]) : 0.0;
+  x = __dadd_rn(x, (base + 256 < n) ? __dmul_rn(a[base + 256], b[base + 256]) : 0.0);
+  x = __dadd_rn(x, (base + 512 < n) ? __dmul_rn(a[base + 512], b[base + 512]) : 0.0);
+  x = __dadd_rn(x, (base + 768 < n) ? __dmul_rn(a[base + 768], b[base + 768]) : 0.0);
+  double r = chunk_tree(x);
+  if (threadIdx.x == 0) out[blockIdx.x] = r;
+}
+static double tree_finish(Buf<double> &part, i64 nc) {
+  while (nc > 1) {
+    i64 nc2 = (nc + 1023) / 1024;
+    Buf<double> nxt(nc2);
+    k_tree_sum<<<(unsigned)nc2, 256, 0, g_ctx.stream>>>(part.p, nc, nxt.p);
+    g_ctx.launches++;
+    part = std::move(nxt);
+    nc = nc2;
+  }
+  return part.get(0);
+}
+double tree_sum(const double *v, i64 n) {
+  if (n <= 0) return 0.0;
+  i64 nc = (n + 1023) / 1024;
+  Buf<double> part(nc);
+  k_tree_sum<<<(unsigned)nc, 256, 0, g_ctx.stream>>>(v, n, part.p);
+  g_ctx.launches++;
+  return tree_finish(part, nc);
+}
+double tree_dot(const double *a, const double *b, i64 n) {
+  if (n <= 0) return 0.0;
+  i64 nc = (n + 1023) / 1024;
+  Buf<double> part(nc);
+  k_tree_dot<<<(unsigned)nc, 256, 0, g_ctx.stream>>>(a, b, n, part.p);
+  g_ctx.launches++;
+  return tree_finish(part, nc);
+}
+
+// ---- max with first index ----
+struct MaxIdx { double v; i64 i; };
+__device__ __forceinline__ MaxIdx better(MaxIdx a, MaxIdx b) {
+  if (b.i < 0) return a;
+  if (a.i < 0) return b;
+  if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+  return a;
+}
+__global__ void __launch_bounds__(256) k_max_first(const double *v, const i64 *idx_in, i64 n, double *ov, i64 *oi) {
+  __shared__ double sv[8];
+  __shared__ i64 si[8];
+  MaxIdx m{0.0, -1};
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+    MaxIdx c{v[i], idx_in ? idx_in[i] : i};
+    m = better(m, c);
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    MaxIdx o{__shfl_down_sync(0xffffffffu, m.v, off), __shfl_down_sync(0xffffffffu, m.i, off)};
+    m = better(m, o);
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { sv[w] = m.v; si[w] = m.i; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; k++) m = better(m, MaxIdx{sv[k], si[k]});
+    ov[blockIdx.x] = m.v; oi[blockIdx.x] = m.i;
+  }
+}
+void max_first(const double *v, i64 n, double *val, i64 *idx) {
+  if (n <= 0) throw Error(-3, "max_first on an empty vector");
+  i64 nb = (n + 255) / 256;
+  if (nb > 1024) nb = 1024;
+  Buf<double> pv(nb), fv(1);
+  Buf<i64> pi(nb), fi(1);
+  k_max_first<<<(unsigned)nb, 256, 0, g_ctx.stream>>>(v, nullptr, n, pv.p, pi.p);
+  k_max_first<<<1, 256, 0, g_ctx.stream>>>(pv.p, pi.p, nb, fv.p, fi.p);
+  g_ctx.launches += 2;
+  struct { double v; i64 i; } out;
+  d2h(&out.v, fv.p, sizeof(double));
+  d2h(&out.i, fi.p, sizeof(i64));
+  *val = out.v;
+  if (idx) *idx = out.i;
+}
+
+__global__ void __launch_bounds__(256) k_count_nonzero(const double *v, i64 n, unsigned long long *out) {
+  unsigned long long c = 0;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+    c += (v[i] != 0.0);
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) c += __shfl_down_sync(0xffffffffu, c, off);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+i64 count_nonzero(const double *v, i64 n) {
+  if (n <= 0) return 0;
+  Buf<unsigned long long> c(1);
+  c.zero();
+  i64 nb = (n + 255) / 256;
+  if (nb > 1184) nb = 1184;
+  k_count_nonzero<<<(unsigned)nb, 256, 0, g_ctx.stream>>>(v, n, c.p);
+  g_ctx.launches++;
+  return (i64)c.get(0);
+}
+
+#else
+// =======================================================================================
+// host emulation build (tests only)
+// =======================================================================================
+void ctx_init(int) {}
+void *dev_alloc(size_t bytes) { void *p = malloc(bytes ? bytes : 8); if (!p) throw Error(-2, "out of memory"); return p; }
+void dev_free(void *p) { free(p); }
+void dev_memset(void *p, int v, size_t bytes) { memset(p, v, bytes); }
+void h2d(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); }
+void d2h(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); g_ctx.syncs++; }
+void d2d(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); }
+void stream_sync() { g_ctx.syncs++; }
+
+i64 exclusive_scan(const int *in, int *out, i64 n) {
+  int s = 0;
+  for (i64 i = 0; i < n; i++) { int v = in[i]; out[i] = s; s += v; }
+  out[n] = s;
+  return s;
+}
+i64 exclusive_scan64(const i64 *in, i64 *out, i64 n) {
+  i64 s = 0;
+  for (i64 i = 0; i < n; i++) { i64 v = in[i]; out[i] = s; s += v; }
+  out[n] = s;
+  return s;
+}
+static double chunk_tree_host(const double *v, i64 m, const double *b) {
+  double s[256];
+  for (int t = 0; t < 256; t++) {
+    double x = 0.0;
+    for (int k = 0; k < 4; k++) {
+      i64 i = t + 256 * k;
+      double p = (i < m) ? (b ? v[i] * b[i] : v[i]) : 0.0;
+      x = (k == 0) ? p : x + p;
+    }
+    s[t] = x;
+  }
+  double w[8];
+  for (int k = 0; k < 8; k++) {
+    double *x = s + 32 * k;
+    for (int off = 16; off >= 1; off >>= 1) for (int l = 0; l < off; l++) x[l] = x[l] + x[l + off];
+    w[k] = x[0];
+  }
+  for (int off = 4; off >= 1; off >>= 1) for (int l = 0; l < off; l++) w[l] = w[l] + w[l + off];
+  return w[0];
+}
+static double tree_host(const double *v, const double *b, i64 n) {
+  if (n <= 0) return 0.0;
+  i64 nc = (n + 1023) / 1024;
+  std::vector<double> part((size_t)nc);
+  for (i64 c = 0; c < nc; c++) {
+    i64 m = n - c * 1024; if (m > 1024) m = 1024;
+    part[(size_t)c] = chunk_tree_host(v + c * 1024, m, b ? b + c * 1024 : nullptr);
+  }
+  if (nc == 1) return part[0];
+  return tree_host(part.data(), nullptr, nc);
+}
+double tree_sum(const double *v, i64 n) { return tree_host(v, nullptr, n); }
+double tree_dot(const double *a, const double *b, i64 n) { return tree_host(a, b, n); }
+void max_first(const double *v, i64 n, double *val, i64 *idx) {
+  if (n <= 0) throw Error(-3, "max_first on an empty vector");
+  double m = v[0]; i64 k = 0;
+  for (i64 i = 1; i < n; i++) if (v[i] > m) { m = v[i]; k = i; }
+  *val = m; if (idx) *idx = k;
+}
+i64 count_nonzero(const double *v, i64 n) { i64 c = 0; for (i64 i = 0; i < n; i++) c += (v[i] != 0.0); return c; }
+#endif
+
+// ---- trace ----
+static uint64_t fnv1a(const void *p, size_t n) {
+  const unsigned char *b = (const unsigned char *)p;
+  uint64_t h = 1469598103934665603ULL;
+  for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ULL; }
+  return h;
+}
+void trace_dev(const char *tag, const void *dptr, size_t bytes) {
+  Context &c = ctx();
+  if (!c.trace_on) return;
+  std::vector<unsigned char> h(bytes ? bytes : 1);
+  if (bytes) d2h(h.data(), dptr, bytes);
+  c.trace.push_back(TraceRec{c.trace_prefix + tag, fnv1a(h.data(), bytes), (i64)bytes});
+}
+
+}  // namespace amgb

@@ -1,0 +1,834 @@
+// setup.cu -- coarsening, smoother estimate, interpolation and Galerkin product on the GPU.
+// Host code only orchestrates: every matrix- or vector-sized operation is a kernel.
+// All citations are amg_setup.c lines of the reference unless another file is named.
+#include "setup.cuh"
+#include <chrono>
+
+namespace amgb {
+
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// =======================================================================================
+// coarsen (:2737) with mat_max (:3535)
+// =======================================================================================
+// y[k] = max over rows i that hold k as a strong neighbour (|S_ik| >= tol*max_row_i, f[k]!=0)
+// of x[i].  The maximum is order-free, so rows scatter with an atomic max on ordered keys.
+void mat_max(double *y, const Csr &S, const double *f, const double *x, double tol,
+             Buf<unsigned long long> &keys) {
+  const int *ro = S.ro.p, *col = S.col.p;
+  const double *a = S.a.p;
+  unsigned long long *kp = keys.p;
+  const unsigned long long lowest = dbl_key(-DBL_MAX);
+  parallel_for(S.cn, [=] DEV(i64 i) { kp[i] = lowest; });
+  parallel_for(S.rn, [=] DEV(i64 i) {
+    const double xj = x[i];
+    double amax = 0;
+    for (int j = ro[i]; j < ro[i + 1]; j++)
+      if (f[col[j]] != 0 && fabs(a[j]) > amax) amax = fabs(a[j]);
+    amax = amax * tol;
+    const unsigned long long kx = dbl_key(xj);
+    for (int j = ro[i]; j < ro[i + 1]; j++) {
+      const int k = col[j];
+      if (f[k] == 0 || fabs(a[j]) < amax) continue;
+      atomic_max_u64(&kp[k], kx);
+    }
+  });
+  parallel_for(S.cn, [=] DEV(i64 i) { y[i] = key_dbl(kp[i]); });
+}
+
+int coarsen(double *vc, const Csr &A, double ctol) {
+  const int n = A.cn;
+  int rounds = 0;
+  Buf<double> D(n);
+  diag_of(D.p, A);
+  { double *d = D.p; parallel_for(n, [=] DEV(i64 i) { double s = sqrt(d[i]); d[i] = 1. / s; }); }
+  Csr S = A.clone();
+  scale_rows(S, D.p);
+  scale_cols(S, D.p);
+  { double *a = S.a.p; parallel_for(S.nnz, [=] DEV(i64 e) { a[e] = fabs(a[e]); }); }
+  diag_of(D.p, S);
+  sub_diag(S, D.p);
+  trace_csr("coarsen.S", S);
+
+  Buf<double> vf(n), g(n), w1(n), w2(n), tmp(n), w(n), mask(n), m(n);
+  Buf<unsigned long long> keys(n);
+  fill(vc, n, 0.);
+  fill(vf.p, n, 1.);
+  double *vfp = vf.p, *gp = g.p, *w1p = w1.p, *w2p = w2.p, *tp = tmp.p, *wp = w.p, *mk = mask.p, *mp = m.p;
+  const double ctol2 = ctol * ctol;
+  for (;;) {
+    rounds++;
+    spmv(gp, 0, vfp, 1., S, vfp);
+    parallel_for(n, [=] DEV(i64 i) { gp[i] = gp[i] * vfp[i]; });
+    spmv(w1p, 0, gp, 1., S, gp);
+    parallel_for(n, [=] DEV(i64 i) { w1p[i] = w1p[i] * vfp[i]; });
+    spmv(w2p, 0, w1p, 1., S, w1p);
+    parallel_for(n, [=] DEV(i64 i) { w2p[i] = w2p[i] * vfp[i]; });
+    spmv(tp, 0, w2p, 1., S, w2p);
+    parallel_for(n, [=] DEV(i64 i) {
+      const double w2v = tp[i] * vfp[i];
+      w2p[i] = w2v;
+      const double inv = 1. / w1p[i];
+      double wv = inv * w2v;
+      if (w1p[i] == 0) wv = 0.;
+      wp[i] = wv;
+    });
+    double w1m, wm;
+    i64 mi;
+    max_first(w1p, n, &w1m, &mi);
+    max_first(wp, n, &wm, nullptr);
+    const double b = (w1m < wm) ? sqrt(w1m) : sqrt(wm);
+    if (b <= ctol) {
+      if (count_nonzero(vc, n) == 0) parallel_for(1, [=] DEV(i64) { vc[mi] = 1.; });
+      break;
+    }
+    parallel_for(n, [=] DEV(i64 i) {
+      const double mv = (wp[i] > ctol2) ? 1. : 0.;
+      mk[i] = mv;
+      tp[i] = gp[i] * mv;
+    });
+    mat_max(mp, S, vfp, tp, 0.1, keys);
+    parallel_for(n, [=] DEV(i64 i) {
+      const double d = gp[i] - mp[i];
+      const double mv = (mk[i] != 0. && d >= 0.) ? 1. : 0.;
+      mk[i] = mv;
+      tp[i] = mv * ((double)i + 1.0);
+    });
+    mat_max(mp, S, vfp, tp, 0.1, keys);
+    parallel_for(n, [=] DEV(i64 i) {
+      const double d = ((double)i + 1.0) - mp[i];
+      const double mv = (mk[i] != 0. && d > 0.) ? 1. : 0.;
+      if (mv != 0.) vc[i] = 1.;
+      vfp[i] = ((vfp[i] == 0.) != (mv == 0.)) ? 1. : 0.;
+    });
+    if (ctx().trace_on) {
+      char t[64];
+      snprintf(t, sizeof t, "coarsen.vc.r%d", rounds);
+      trace_dev(t, vc, sizeof(double) * (size_t)n);
+    }
+    if (rounds > 10000) throw Error(-7, "coarsen: no convergence");
+  }
+  return rounds;
+}
+
+// =======================================================================================
+// pcg (:2242)
+// =======================================================================================
+int pcg(double *x, const Csr &A, double *r, const double *M, double tol, const double *b) {
+  const int n = A.rn;
+  Buf<double> p(n), z(n), w(n), t(n);
+  double *pp = p.p, *zp = z.p, *wp = w.p, *tp = t.p;
+  parallel_for(n, [=] DEV(i64 i) { x[i] = 0.; pp[i] = 0.; zp[i] = M[i] * r[i]; tp[i] = M[i] * b[i]; });
+  double rho = tree_dot(r, zp, n);
+  const double rho_0 = tree_dot(tp, b, n);
+  const double rho_stop = tol * tol * rho_0;
+  const int nmax = n <= 100 ? n : 100;
+  int k = 0;
+  double rho_old = 1;
+  while (nmax > 0 && rho > rho_stop && k < nmax) {
+    k++;
+    const double beta = rho / rho_old;
+    parallel_for(n, [=] DEV(i64 i) { const double pb = pp[i] * beta; pp[i] = pb + zp[i]; });
+    spmv(wp, 0, nullptr, 1, A, pp);
+    double alpha = tree_dot(pp, wp, n);
+    alpha = rho / alpha;
+    parallel_for(n, [=] DEV(i64 i) {
+      const double pa = pp[i] * alpha;
+      x[i] = x[i] + pa;
+      const double wa = wp[i] * alpha;
+      const double rn = r[i] - wa;
+      r[i] = rn;
+      zp[i] = M[i] * rn;
+    });
+    rho_old = rho;
+    rho = tree_dot(r, zp, n);
+  }
+  return k;
+}
+
+// =======================================================================================
+// lanczos (:2435); tdeig on the host (k x k, k <= 299)
+// =======================================================================================
+int lanczos(double *lambda, const Csr &A, hostmath::GlibcRand &rng, int *iters) {
+  const int rn = A.rn, kmax = 299;
+  std::vector<double> hr((size_t)rn);
+  for (int i = 0; i < rn; i++) hr[(size_t)i] = rng.uniform();
+  Buf<double> r(rn), qk(rn), qkm1(rn), Aqk(rn);
+  r.upload(hr.data(), rn);
+  trace_dev("lanczos.r0", r.p, sizeof(double) * (size_t)rn);
+  double *l = lambda;
+  double y[300], d[301], v[300];
+  double beta = tree_norm2(r.p, rn);
+  double beta2 = beta * beta;
+  beta = sqrt(beta2);
+  int k = 0;
+  double change = 0.0;
+  {
+    Buf<double> e = A.a.clone();
+    const int *ro = A.ro.p, *col = A.col.p;
+    double *ep = e.p;
+    parallel_for(rn, [=] DEV(i64 i) {
+      for (int j = ro[i]; j < ro[i + 1]; j++) if (col[j] == i) { ep[j] = ep[j] - 1.; break; }
+    });
+    double fro = tree_norm2(e.p, A.nnz);
+    const double fro2 = fro * fro;
+    fro = sqrt(fro2);
+    if (fro < 1e-11) { l[0] = 1; l[1] = 1; y[0] = 0; y[1] = 0; k = 2; change = 0.0; }
+    else change = 1.0;
+  }
+  if (rn == 1) { const double a00 = A.a.get(0); l[0] = a00; l[1] = a00; y[0] = 0; y[1] = 0; k = 2; change = 0.0; }
+  qk.zero();
+  double *rp = r.p, *qp = qk.p, *qmp = qkm1.p, *Ap = Aqk.p;
+  while (k < kmax && (change > 1e-5 || y[0] > 1e-3 || y[k - 1] > 1e-3)) {
+    k++;
+    const double ib = 1. / beta;
+    parallel_for(rn, [=] DEV(i64 i) { qmp[i] = qp[i]; qp[i] = rp[i] * ib; });
+    spmv(Ap, 0, nullptr, 1, A, qp);
+    const double alpha = tree_dot(qp, Ap, rn);
+    const double bt = beta;
+    parallel_for(rn, [=] DEV(i64 i) {
+      const double aq = qp[i] * alpha, bq = qmp[i] * bt;
+      const double t = Ap[i] - aq;
+      rp[i] = t - bq;
+    });
+    if (k == 1) { l[0] = alpha; y[0] = 1; }
+    else {
+      const double l0 = l[0], lkm2 = l[k - 2];
+      d[0] = 0;
+      for (int i = 1; i < k; i++) d[i] = l[i - 1];
+      d[k] = 0;
+      v[0] = alpha;
+      for (int i = 1; i < k; i++) v[i] = beta * y[i - 1];
+      hostmath::tdeig(l, y, d, v, k - 1);
+      change = fabs(l0 - l[0]) + fabs(lkm2 - l[k - 1]);
+    }
+    beta = tree_norm2(rp, rn);
+    beta2 = beta * beta;
+    beta = sqrt(beta2);
+    if (beta == 0) break;
+  }
+  if (iters) *iters = k;
+  int n = 0;
+  for (int i = 0; i < k; i++) if (y[i] < 0.01) lambda[n++] = l[i];
+  return n;
+}
+
+// =======================================================================================
+// local energy-minimising solves: interp (:2053) and interp_lmop (:1589)
+// =======================================================================================
+// sp_restrict_sorted (:2180)
+HD inline void restrict_sorted(double *y, int Rn, const int *Ri, int xn, const int *xi, const double *x) {
+  int p = 0;
+  for (int k = 0; k < Rn; k++) {
+    while (p < xn && xi[p] < Ri[k]) p++;
+    y[k] = (p < xn && xi[p] == Ri[k]) ? x[p] : 0.0;
+  }
+}
+// mv_utt (:2122)
+HD inline void tri_t_mv(double *y, int n, const double *U, const double *x) {
+  for (int i = 0; i < n; i++) {
+    double v = 0;
+    const double *u = U + (size_t)i * (i + 1) / 2;
+    for (int j = 0; j <= i; j++) v = v + u[j] * x[j];
+    y[i] = v;
+  }
+}
+// mv_ut (:2138)
+HD inline void tri_mv(double *y, int n, const double *U, const double *x) {
+  for (int j = 0; j < n; j++) {
+    y[j] = 0;
+    const double *u = U + (size_t)j * (j + 1) / 2;
+    for (int i = 0; i <= j; i++) y[i] = y[i] + u[i] * x[j];
+  }
+}
+// A-orthogonalisation of the support Qj (:2081-2099); optional QQt accumulation (:1637)
+HD inline void build_Q(double *Q, double *sqv1, double *sqv2, double *QQt, int nz, const int *Qj,
+                       const int *aro, const int *acol, const double *aa) {
+  double *qk = Q;
+  if (QQt) for (int k = 0; k < nz * nz; k++) QQt[k] = 0;
+  for (int k = 0; k < nz; k++, qk += k) {
+    const int s = Qj[k];
+    restrict_sorted(sqv1, k + 1, Qj, aro[s + 1] - aro[s], acol + aro[s], aa + aro[s]);
+    tri_t_mv(sqv2, k, Q, sqv1);
+    tri_mv(qk, k, Q, sqv2);
+    double alpha = sqv1[k];
+    for (int m = 0; m < k; m++) alpha = alpha - sqv1[m] * qk[m];
+    alpha = -1.0 / sqrt(alpha);
+    for (int m = 0; m < k; m++) qk[m] = qk[m] * alpha;
+    qk[k] = -alpha;
+    if (QQt)
+      for (int m = 0; m <= k; m++) {
+        const double qkm = qk[m];
+        for (int j = 0; j <= k; j++) QQt[m * nz + j] = QQt[m * nz + j] + qkm * qk[j];
+      }
+  }
+}
+
+// scratch layout per coarse column: sqv1[nz] sqv2[nz] Q[nz(nz+1)/2]
+void column_scratch_offsets(const Csr &Wt, Buf<i64> &off, i64 *total) {
+  Buf<i64> sz(Wt.rn + 1);
+  off.alloc(Wt.rn + 1);
+  const int *ro = Wt.ro.p;
+  i64 *s = sz.p;
+  parallel_for(Wt.rn, [=] DEV(i64 i) { i64 nz = ro[i + 1] - ro[i]; s[i] = 2 * nz + nz * (nz + 1) / 2; });
+  *total = exclusive_scan64(sz.p, off.p, Wt.rn);
+}
+
+// interp (:2053): overwrite the values of Wt (one row per coarse point) with
+// Q Q^t R (B e_i + u_i lambda)
+void interp(Csr &Wt, const Csr &At, const Csr &Bt, const double *u, const double *lambda) {
+  Buf<i64> off;
+  i64 total;
+  column_scratch_offsets(Wt, off, &total);
+  Buf<double> scratch(total);
+  const int *wro = Wt.ro.p, *wcol = Wt.col.p, *aro = At.ro.p, *acol = At.col.p, *bro = Bt.ro.p, *bcol = Bt.col.p;
+  const double *aa = At.a.p, *ba = Bt.a.p;
+  double *wa = Wt.a.p, *sc = scratch.p;
+  const i64 *offp = off.p;
+  parallel_for(Wt.rn, [=] DEV(i64 i) {
+    const int wir = wro[i], nz = wro[i + 1] - wir;
+    if (nz == 0) return;
+    const int *Qj = wcol + wir;
+    double *sqv1 = sc + offp[i], *sqv2 = sqv1 + nz, *Q = sqv2 + nz;
+    build_Q(Q, sqv1, sqv2, nullptr, nz, Qj, aro, acol, aa);
+    restrict_sorted(sqv1, nz, Qj, bro[i + 1] - bro[i], bcol + bro[i], ba + bro[i]);
+    for (int k = 0; k < nz; k++) sqv1[k] = sqv1[k] + u[i] * lambda[Qj[k]];
+    tri_t_mv(sqv2, nz, Q, sqv1);
+    tri_mv(wa + wir, nz, Q, sqv2);
+  });
+}
+
+// interp_lmop (:1589): S = sum over coarse points i of u_i * Q_i Q_i^t scattered into the
+// pattern of S.  Phase 1 forms every Q_i Q_i^t; phase 2 lets every row of S collect its
+// contributions in ascending i, which is the order the reference's loop produces.  A target
+// that is absent from the pattern of S is skipped (the reference's sp_add :1665 does not check
+// and writes to a wrong entry there; see DESIGN.md "sp_add").
+void interp_lmop(Csr &S, const Csr &At, const double *u, const Csr &Wskt, const Csr &Wsk,
+                 const int *tpos) {
+  Buf<i64> off, qsz(Wskt.rn + 1), qoff(Wskt.rn + 1);
+  i64 total;
+  column_scratch_offsets(Wskt, off, &total);
+  const int *tro = Wskt.ro.p, *tcol = Wskt.col.p, *aro = At.ro.p, *acol = At.col.p;
+  const double *aa = At.a.p;
+  { i64 *q = qsz.p; parallel_for(Wskt.rn, [=] DEV(i64 i) { i64 nz = tro[i + 1] - tro[i]; q[i] = nz * nz; }); }
+  const i64 qtotal = exclusive_scan64(qsz.p, qoff.p, Wskt.rn);
+  Buf<double> scratch(total), QQ(qtotal);
+  double *sc = scratch.p, *qq = QQ.p;
+  const i64 *offp = off.p, *qo = qoff.p;
+  parallel_for(Wskt.rn, [=] DEV(i64 i) {
+    const int b = tro[i], nz = tro[i + 1] - b;
+    if (nz == 0) return;
+    double *sqv1 = sc + offp[i], *sqv2 = sqv1 + nz, *Q = sqv2 + nz;
+    build_Q(Q, sqv1, sqv2, qq + qo[i], nz, tcol + b, aro, acol, aa);
+  });
+  const int *sro = S.ro.p, *scol = S.col.p, *kro = Wsk.ro.p, *kcol = Wsk.col.p;
+  double *sa = S.a.p;
+  parallel_for(S.rn, [=] DEV(i64 j) {
+    const int yb = sro[j], yn = sro[j + 1] - yb;
+    for (int q = 0; q < yn; q++) sa[yb + q] = 0.0;
+    if (yn == 0) return;
+    for (int e = kro[j]; e < kro[j + 1]; e++) {
+      const int i = kcol[e];
+      const int b = tro[i], nz = tro[i + 1] - b, k = tpos[e] - b;
+      const double ui = u[i];
+      const double *x = qq + qo[i] + (i64)k * nz;
+      const int *xi = tcol + b;
+      int p = 0;
+      for (int kk = 0; kk < nz; kk++) {
+        while (p < yn && scol[yb + p] < xi[kk]) p++;
+        if (p < yn && scol[yb + p] == xi[kk]) { sa[yb + p] = sa[yb + p] + ui * x[kk]; p++; }
+      }
+    }
+  });
+}
+
+// min_skel (:2198)
+Csr min_skel(const Csr &R) {
+  Csr W(R.rn, R.cn, R.rn);
+  const int *ro = R.ro.p, *col = R.col.p;
+  const double *a = R.a.p;
+  int *wro = W.ro.p, *wcol = W.col.p;
+  double *wa = W.a.p;
+  const int rn = R.rn;
+  parallel_for(rn, [=] DEV(i64 i) {
+    double ymax = -DBL_MAX;
+    int j = 0;
+    for (int k = ro[i]; k < ro[i + 1]; k++) if (a[k] > ymax) { ymax = a[k]; j = col[k]; }
+    wa[i] = (ymax > 0.0) ? 1.0 : 0.0;
+    wcol[i] = j;
+    wro[i] = (int)i;
+    if (i == rn - 1) wro[rn] = rn;
+  });
+  if (rn == 0) W.ro.zero();
+  return W;
+}
+
+// solve_constraint (:1499)
+void solve_constraint(double *lam, const Csr &Wsk, const Csr &Wskt, const int *tpos, const Csr &Af,
+                      const Csr &W0, const double *alpha, const double *u, const double *v, double tol) {
+  const int nf = Wsk.rn, nc = Wsk.cn;
+  Buf<double> au2(nc);
+  { double *p = au2.p; parallel_for(nc, [=] DEV(i64 i) { const double uu = u[i] * u[i]; p[i] = uu * alpha[i]; }); }
+  Csr S = spgemm(Wsk, Wskt);
+  interp_lmop(S, Af, au2.p, Wskt, Wsk, tpos);
+  trace_csr("sc.S", S);
+  Buf<double> resid(nf), d(nf), keep(nf);
+  spmv(resid.p, 1.0, v, -1.0, W0, u);
+  diag_of(d.p, S);
+  double *dp = d.p, *kp = keep.p, *rp = resid.p;
+  parallel_for(nf, [=] DEV(i64 i) { kp[i] = (dp[i] != 0.) ? 1. : 0.; });
+  const i64 nk = count_nonzero(kp, nf);
+  if (nk == nf) {
+    Buf<double> q(nf), x(nf);
+    spmv(q.p, 1., rp, -1., S, lam);
+    parallel_for(nf, [=] DEV(i64 i) { dp[i] = 1. / dp[i]; });
+    pcg(x.p, S, q.p, dp, tol, rp);
+    double *xp = x.p;
+    parallel_for(nf, [=] DEV(i64 i) { lam[i] = lam[i] + xp[i]; });
+    return;
+  }
+  // some rows of S are empty: solve on the kept rows only (:1532-1574)
+  Csr S2 = sub_mat(S, kp, kp);
+  Buf<int> kflag(nf + 1), pos(nf + 1);
+  int *kf = kflag.p;
+  parallel_for(nf, [=] DEV(i64 i) { kf[i] = (kp[i] != 0.) ? 1 : 0; if (kp[i] == 0.) lam[i] = 0.; });
+  exclusive_scan(kflag.p, pos.p, nf);
+  Buf<double> rc(nk), dc(nk), lc(nk), q(nk), x(nk);
+  const int *ps = pos.p;
+  double *rcp = rc.p, *dcp = dc.p, *lcp = lc.p, *xp = x.p;
+  parallel_for(nf, [=] DEV(i64 i) {
+    if (!kf[i]) return;
+    rcp[ps[i]] = rp[i]; dcp[ps[i]] = dp[i]; lcp[ps[i]] = lam[i];
+  });
+  spmv(q.p, 1., rcp, -1., S2, lcp);
+  parallel_for(nk, [=] DEV(i64 i) { dcp[i] = 1. / dcp[i]; });
+  pcg(xp, S2, q.p, dcp, tol, rcp);
+  parallel_for(nf, [=] DEV(i64 i) { if (kf[i]) lam[i] = lam[i] + xp[ps[i]]; });
+}
+
+// solve_weights (:1437).  W and W0 share the pattern of W_skel; their values come back from the
+// transposed solves through the transpose position map, which equals transposing them again.
+void solve_weights(Csr &W, Csr &W0, double *lam, const Csr &Wsk, const Csr &Af, const Csr &Armt,
+                   const double *alpha, const double *u, const double *v, double tol) {
+  const int nf = Af.rn, nc = Wsk.cn;
+  Buf<double> au(nc), zeros(nf);
+  { double *p = au.p; parallel_for(nc, [=] DEV(i64 i) { p[i] = alpha[i] * u[i]; }); }
+  zeros.zero();
+  Buf<int> tpos;
+  Csr Wskt = transpose(Wsk, &tpos);
+  Csr W0t = Wskt.clone();
+  interp(W0t, Af, Armt, au.p, zeros.p);
+  W0 = Wsk.clone();
+  const int *tp = tpos.p;
+  { double *dst = W0.a.p; const double *src = W0t.a.p; parallel_for(Wsk.nnz, [=] DEV(i64 e) { dst[e] = src[tp[e]]; }); }
+  solve_constraint(lam, Wsk, Wskt, tp, Af, W0, alpha, u, v, tol);
+  trace_dev("sw.lam", lam, sizeof(double) * (size_t)nf);
+  interp(Wskt, Af, Armt, au.p, lam);
+  W = Wsk.clone();
+  { double *dst = W.a.p; const double *src = Wskt.a.p; parallel_for(Wsk.nnz, [=] DEV(i64 e) { dst[e] = src[tp[e]]; }); }
+}
+
+// find_support (:1260).  Entries leave R one per bad column and round; here they are zeroed and
+// flagged dead instead of compacting R and its transpose every round (a zero adds nothing to any
+// of the sums involved, so all vectors are bit-identical).
+Csr find_support(const Csr &R, double goal) {
+  const int nf = R.rn, nc = R.cn;
+  Buf<int> tpos;
+  Csr Rt = transpose(R, &tpos);
+  Buf<int> src(R.nnz), skel(R.nnz), alive_t(R.nnz);
+  Buf<double> rv = R.a.clone();
+  skel.zero();
+  fill_int(alive_t.p, R.nnz, 1);
+  { int *s = src.p; const int *tp = tpos.p; parallel_for(R.nnz, [=] DEV(i64 e) { s[tp[e]] = (int)e; }); }
+  Buf<double> rs(nf), tmp(nf), onec(nc), w(nc), w2(nc), v(nc);
+  fill(onec.p, nc, 1.);
+  double theta = 0.5;
+  double *rvp = rv.p, *rtv = Rt.a.p, *rsp = rs.p, *wp = w.p, *w2p = w2.p, *vp = v.p;
+  const int *tro = Rt.ro.p, *tcol = Rt.col.p, *srcp = src.p;
+  int *skp = skel.p, *alp = alive_t.p;
+  int guard = 0;
+  for (;;) {
+    spmv_vals(rsp, 0., nullptr, 1., R, rvp, onec.p);
+    spmv_vals(wp, 0., nullptr, 1., Rt, rtv, rsp);
+    spmv_vals(tmp.p, 0., nullptr, 1., R, rvp, wp);
+    spmv_vals(w2p, 0., nullptr, 1., Rt, rtv, tmp.p);
+    parallel_for(nc, [=] DEV(i64 i) { double q = w2p[i] / wp[i]; if (wp[i] == 0.) q = 0.; vp[i] = q; });
+    double mv;
+    max_first(vp, nc, &mv, nullptr);
+    if (mv < goal) break;
+    if (nf <= 1) break;   // the reference writes row index 1 here and never terminates
+    while (mv <= (1 + theta) * goal) theta = theta / 2.;
+    const double thr = (1 + theta) * goal;
+    parallel_for(nc, [=] DEV(i64 c) {
+      double sum = 0.0;
+      for (int p = tro[c]; p < tro[c + 1]; p++) sum = sum + rtv[p];
+      if (!(wp[c] > thr && sum != 0.)) return;
+      double maxx = -DBL_MAX;
+      int arg = -1;
+      for (int p = tro[c]; p < tro[c + 1]; p++) {
+        if (!alp[p]) continue;
+        const double x = rtv[p] * rsp[tcol[p]];
+        if (x > maxx) { maxx = x; arg = p; }
+      }
+      if (arg < 0) return;
+      alp[arg] = 0; rtv[arg] = 0.0;
+      rvp[srcp[arg]] = 0.0; skp[srcp[arg]] = 1;
+    });
+    if (++guard > 100000) throw Error(-8, "find_support: no convergence");
+  }
+  // Skel = sparse(skel_i, skel_j, 1): the flagged entries, in place
+  Buf<int> cnt(nf + 1);
+  const int *ro = R.ro.p, *col = R.col.p;
+  { int *c = cnt.p; parallel_for(nf, [=] DEV(i64 i) { int k = 0; for (int j = ro[i]; j < ro[i + 1]; j++) k += skp[j]; c[i] = k; }); }
+  Buf<int> mro(nf + 1);
+  const i64 nnz = exclusive_scan(cnt.p, mro.p, nf);
+  Csr M(nf, nc, nnz);
+  M.ro = std::move(mro);
+  const int *mr = M.ro.p;
+  int *mcol = M.col.p;
+  double *ma = M.a.p;
+  parallel_for(nf, [=] DEV(i64 i) {
+    int p = mr[i];
+    for (int j = ro[i]; j < ro[i + 1]; j++) if (skp[j]) { mcol[p] = col[j]; ma[p] = 1.; p++; }
+  });
+  return M;
+}
+
+// expand_support (:907)
+Csr expand_support(const Csr &Wsk, const Csr &R, const Csr &R0, double gamma) {
+  const int nf = Wsk.rn, nc = Wsk.cn;
+  Csr M = find_support(R, gamma);
+  trace_csr("es.M", M);
+  Csr ns = mpm(1., M, 1., Wsk);
+  Buf<double> badrow(nf);
+  double *br = badrow.p;
+  const int *nro = ns.ro.p;
+  double *na = ns.a.p;
+  parallel_for(nf, [=] DEV(i64 i) {
+    double b = 0.;
+    for (int j = nro[i]; j < nro[i + 1]; j++) if (na[j] == 2.) { b = 1.; break; }
+    br[i] = b;
+  });
+  const i64 nbad = count_nonzero(br, nf);
+  if (nbad == 0) {
+    parallel_for(ns.nnz, [=] DEV(i64 e) { if (na[e] == 2.) na[e] = 1.; });
+    return ns;
+  }
+  // X = R0 - R0.*W_skel, then per bad row: |X| sorted descending (stable), shortest prefix whose
+  // running sum is not below half of the row sum (:965-1114 without the dense rank matrices)
+  Csr R0W = mxmpoint(R0, Wsk);
+  Csr X = mpm(1., R0, -1., R0W);
+  Buf<int> take(nf + 1);
+  const int *xro = X.ro.p;
+  int *xcol = X.col.p, *tk = take.p;
+  double *xa = X.a.p;
+  parallel_for(nf, [=] DEV(i64 i) {
+    if (br[i] == 0.) { tk[i] = 0; return; }
+    const int b = xro[i], len = xro[i + 1] - b;
+    int *c = xcol + b;
+    double *v = xa + b;
+    for (int k = 0; k < len; k++) v[k] = fabs(v[k]);
+    for (int a = 1; a < len; a++) {          // stable insertion sort, descending by value
+      const double tv = v[a]; const int tc = c[a];
+      int j = a - 1;
+      while (j >= 0 && v[j] < tv) { v[j + 1] = v[j]; c[j + 1] = c[j]; j--; }
+      v[j + 1] = tv; c[j + 1] = tc;
+    }
+    double tot = 0.0;
+    for (int k = 0; k < len; k++) if (v[k] != 0.) tot = tot + v[k];
+    const double half = tot * 0.5;
+    int below = 0;
+    double cs = 0.0;
+    for (int k = 0; k < len; k++) {
+      if (v[k] != 0.) cs = cs + v[k];
+      const double s = (half != 0.) ? (1. * cs + (-1.) * half) : (1. * cs);
+      if (s < 0.) below++;
+    }
+    int t = below + 1;
+    if (t > len) t = len;
+    for (int a = 1; a < t; a++) {            // the chosen columns, ascending
+      const int tc = c[a];
+      int j = a - 1;
+      while (j >= 0 && c[j] > tc) { c[j + 1] = c[j]; j--; }
+      c[j + 1] = tc;
+    }
+    tk[i] = t;
+  });
+  Buf<int> nro2(nf + 1);
+  const i64 nn = exclusive_scan(take.p, nro2.p, nf);
+  Csr N(nf, nc, nn);
+  N.ro = std::move(nro2);
+  const int *nr = N.ro.p;
+  int *ncol = N.col.p;
+  double *nva = N.a.p;
+  parallel_for(nf, [=] DEV(i64 i) {
+    const int b = xro[i];
+    int p = nr[i];
+    for (int k = 0; k < tk[i]; k++) { ncol[p] = xcol[b + k]; nva[p] = 1.; p++; }
+  });
+  Csr out = mpm(1., ns, 1., N);
+  { double *oa = out.a.p; parallel_for(out.nnz, [=] DEV(i64 e) { if (oa[e] != 0.) oa[e] = 1.; }); }
+  return out;
+}
+
+// interpolation (:598)
+Csr interpolation(const Csr &Af, const Csr &Ac, const Csr &Ar, double gamma2, double tol, int *rounds_out) {
+  const int nf = Af.rn, nc = Ac.cn;
+  Buf<double> Df(nf), Dfsqrti(nf), uc(nc), tmp(nf), v(nf), b(nf), Dc(nc), Dcinv(nc);
+  diag_of(Df.p, Af);
+  double *dfp = Df.p, *dfi = Dfsqrti.p;
+  parallel_for(nf, [=] DEV(i64 i) { dfi[i] = 1. / dfp[i]; });
+  fill(uc.p, nc, 1.);
+  spmv(tmp.p, 0, nullptr, -1, Ar, uc.p);
+  fill(b.p, nf, 1.0);
+  pcg(v.p, Af, tmp.p, Df.p, 1e-16, b.p);
+  trace_dev("ip.v", v.p, sizeof(double) * (size_t)nf);
+  diag_of(Dc.p, Ac);
+  double *dcp = Dc.p, *dci = Dcinv.p;
+  parallel_for(nc, [=] DEV(i64 i) { dci[i] = 1. / dcp[i]; });
+  Csr Wsk;
+  {
+    Csr ArD = Ar.clone();
+    double *a = ArD.a.p;
+    parallel_for(ArD.nnz, [=] DEV(i64 e) { a[e] = a[e] * a[e]; });
+    scale_rows(ArD, dfi);
+    scale_cols(ArD, dci);
+    Wsk = min_skel(ArD);
+  }
+  Buf<double> lam(nf), alpha(nc), Dcsqrti(nc), w1(nc), w2(nc), ones(nc), r(nc);
+  lam.zero();
+  d2d(alpha.p, Dc.p, sizeof(double) * (size_t)nc);
+  parallel_for(nf, [=] DEV(i64 i) { dfi[i] = sqrt(dfi[i]); });
+  fill(ones.p, nc, 1.0);
+  Csr Armt = transpose(Ar);
+  { double *a = Armt.a.p; parallel_for(Armt.nnz, [=] DEV(i64 e) { a[e] = a[e] * -1.0; }); }
+  double *dsq = Dcsqrti.p, *w1p = w1.p, *w2p = w2.p, *rp = r.p, *alp = alpha.p;
+  Csr W;
+  int rounds = 0;
+  const std::string pfx_save = ctx().trace_prefix;
+  for (;;) {
+    rounds++;
+    if (rounds > 100) throw Error(-9, "interpolation did not converge in 100 rounds (the reference would not terminate)");
+    if (ctx().trace_on) ctx().trace_prefix = pfx_save + "r" + std::to_string(rounds) + ".";
+    trace_csr("ip.Wsk", Wsk);
+    Csr Wt, W0;
+    solve_weights(Wt, W0, lam.p, Wsk, Af, Armt, alp, uc.p, v.p, tol);
+    trace_csr("ip.W0", W0);
+    trace_csr("ip.Wtmp", Wt);
+    Csr R0, R;
+    { Csr AfW = spgemm(Af, W0); R0 = mpm(1., AfW, 1., Ar); }
+    { Csr AfW = spgemm(Af, Wt); R = mpm(1., AfW, 1., Ar); }
+    {
+      Csr Arr = mpm(1.0, R, 1.0, Ar);
+      Csr ArW = mxmpoint(Wt, Arr);
+      col_sums(dsq, ArW);
+    }
+    parallel_for(nc, [=] DEV(i64 i) { double t = dsq[i] + dcp[i]; t = 1. / t; dsq[i] = sqrt(t); });
+    scale_rows(R, dfi);
+    { double *a = R.a.p; parallel_for(R.nnz, [=] DEV(i64 e) { a[e] = fabs(a[e]); }); }
+    scale_cols(R, dsq);
+    scale_rows(R0, dfi);
+    { double *a = R0.a.p; parallel_for(R0.nnz, [=] DEV(i64 e) { a[e] = fabs(a[e]); }); }
+    scale_cols(R0, dsq);
+    trace_csr("ip.R", R);
+    trace_csr("ip.R0", R0);
+    {
+      Csr Rt = transpose(R);
+      spmv(tmp.p, 0., nullptr, 1., R, ones.p);
+      spmv(w1p, 0., nullptr, 1., Rt, tmp.p);
+      spmv(tmp.p, 0., nullptr, 1., R, w1p);
+      spmv(w2p, 0., nullptr, 1., Rt, tmp.p);
+    }
+    parallel_for(nc, [=] DEV(i64 i) {
+      double q = w2p[i] / w1p[i];
+      if (w1p[i] == 0) q = 0.;
+      rp[i] = (q > gamma2) ? 1. : 0.;
+    });
+    const i64 nbig = count_nonzero(rp, nc);
+    double w1m;
+    max_first(w1p, nc, &w1m, nullptr);
+    if (nbig == 0 || w1m <= gamma2) {
+      Csr W0b;
+      solve_weights(W, W0b, lam.p, Wsk, Af, Armt, alp, uc.p, v.p, 1e-16);
+      Buf<double> wuc(nf);
+      spmv(wuc.p, 0., nullptr, 1., W, uc.p);
+      // the reference rescales only entries whose column index equals the row index (:821-837)
+      const int *wro = W.ro.p, *wcol = W.col.p;
+      double *wa = W.a.p, *wu = wuc.p, *vp = v.p;
+      parallel_for(nf, [=] DEV(i64 i) {
+        if (wu[i] == 0.) return;
+        for (int j = wro[i]; j < wro[i + 1]; j++)
+          if ((int)i == wcol[j]) { const double s = vp[i] / wu[i]; wa[j] = s * wa[j]; }
+      });
+      break;
+    }
+    parallel_for(nc, [=] DEV(i64 i) { const double x = w2p[i] > 1e-6 ? w2p[i] : 1e-6; alp[i] = dcp[i] / x; });
+    Wsk = expand_support(Wsk, R, R0, gamma2);
+  }
+  ctx().trace_prefix = pfx_save;
+  if (rounds_out) *rounds_out = rounds;
+  return W;
+}
+
+// =======================================================================================
+// amg_setup (:60)
+// =======================================================================================
+// build_csr (:3612): assemble, then drop empty rows and the same-numbered columns
+static Csr build_csr(i64 n, const int *Ai, const int *Aj, const double *Av) {
+  Buf<double> mx(2);
+  // dimensions: 1 + largest index among the non-zero entries
+  Buf<int> dims(2);
+  dims.zero();
+  int *dp = dims.p;
+  parallel_for(n, [=] DEV(i64 e) {
+    if (Av[e] == 0.) return;
+#ifdef __CUDA_ARCH__
+    atomicMax(&dp[0], Ai[e] + 1); atomicMax(&dp[1], Aj[e] + 1);
+#else
+    if (Ai[e] + 1 > dp[0]) dp[0] = Ai[e] + 1;
+    if (Aj[e] + 1 > dp[1]) dp[1] = Aj[e] + 1;
+#endif
+  });
+  std::vector<int> hd = dims.download();
+  int rn = hd[0] > hd[1] ? hd[0] : hd[1];
+  Csr T = coo_to_csr(n, Ai, Aj, Av, rn, rn);
+  Buf<double> keep(rn);
+  const int *ro = T.ro.p;
+  double *kp = keep.p;
+  parallel_for(rn, [=] DEV(i64 i) { kp[i] = (ro[i + 1] - ro[i] == 0) ? 0. : 1.; });
+  if (count_nonzero(kp, rn) == rn) return T;
+  return sub_mat(T, kp, kp);
+}
+
+void setup(i64 nnz, const int *dAi, const int *dAj, const double *dAv, Hierarchy &H) {
+  Context &c = ctx();
+  const i64 launches0 = c.launches, syncs0 = c.syncs;
+  const double t_begin = now_s();
+  double t0 = t_begin;
+  auto lap = [&](double &acc) { stream_sync(); const double t = now_s(); acc += t - t0; t0 = t; };
+  Csr A = build_csr(nnz, dAi, dAj, dAv);
+  lap(H.t.build);
+  const double tol = 0.5, ctol = 0.7, itol = 1e-4;
+  const double gamma2 = 1. - sqrt(1. - tol);
+  hostmath::GlibcRand rng(1);
+  H.lv.clear();
+  H.n0 = A.rn;
+  H.nullspace = 0;
+  Buf<int> idl(A.rn);
+  { int *p = idl.p; parallel_for(A.rn, [=] DEV(i64 i) { p[i] = (int)i + 1; }); }
+  for (int level = 0;; level++) {
+    if (level >= 128) throw Error(-10, "more than 128 levels");
+    H.lv.emplace_back();
+    Level &L = H.lv.back();
+    const int rn = A.rn;
+    L.n = rn;
+    if (c.trace_on) c.trace_prefix = "L" + std::to_string(level) + ".";
+    trace_csr("A", A);
+    if (rn <= 1) {
+      H.nullspace = (rn == 1 && A.nnz > 0 && A.a.get(0) < 1e-9) ? 1 : 0;
+      L.A = std::move(A);
+      break;
+    }
+    // ---- coarsen (:174-186)
+    L.C.alloc(rn);
+    Buf<double> vf(rn);
+    L.coarsen_rounds = coarsen(L.C.p, A, ctol);
+    const double *vc = L.C.p;
+    { double *f = vf.p; parallel_for(rn, [=] DEV(i64 i) { f[i] = (vc[i] == 0.) ? 1. : 0.; }); }
+    trace_dev("vc", vc, sizeof(double) * (size_t)rn);
+    lap(H.t.coarsen);
+
+    // ---- diagonal smoother (:188-228)
+    L.Af = sub_mat(A, vf.p, vf.p);
+    const int nf = L.Af.rn;
+    L.nf = nf;
+    L.D.alloc(nf);
+    {
+      const int *ro = L.Af.ro.p, *col = L.Af.col.p;
+      const double *a = L.Af.a.p;
+      double *D = L.D.p;
+      parallel_for(nf, [=] DEV(i64 i) {
+        double s = 0, dg = 0.;
+        bool found = false;
+        for (int j = ro[i]; j < ro[i + 1]; j++) {
+          s = s + a[j] * a[j];
+          if (!found && col[j] == i) { dg = a[j]; found = true; }
+        }
+        const double inv = 1. / s;
+        D[i] = dg * inv;
+      });
+    }
+    lap(H.t.smoother);
+    if (nf >= 2) {   // (:232-285)
+      Buf<double> Dh(nf);
+      double *dh = Dh.p, *D = L.D.p;
+      parallel_for(nf, [=] DEV(i64 i) { dh[i] = sqrt(D[i]); });
+      Csr DAD = L.Af.clone();
+      scale_rows(DAD, dh);
+      scale_cols(DAD, dh);
+      double lambda[300];
+      const int k = lanczos(lambda, DAD, rng, &L.lanczos_k);
+      if (k < 1) throw Error(-11, "lanczos returned no eigenvalue estimate");
+      const double a = lambda[0], b = lambda[k - 1];
+      const double sc = 2. / (a + b);
+      parallel_for(nf, [=] DEV(i64 i) { D[i] = D[i] * sc; });
+      L.rho = (b - a) / (b + a);
+      L.lmin = a; L.lmax = b;
+      double m, cc;
+      hostmath::chebsim(&m, &cc, L.rho, gamma2);
+      L.m = m;
+    } else { L.rho = 0; L.m = 1; }
+    trace_dev("D", L.D.p, sizeof(double) * (size_t)nf);
+    lap(H.t.lanczos);
+
+    // ---- interpolation (:302-334)
+    Csr Afc = sub_mat(A, vf.p, vc);
+    Csr Ac = sub_mat(A, vc, vc);
+    const int nc = Ac.rn;
+    L.nc = nc;
+    {
+      Buf<int> cflag(rn + 1), fflag(rn + 1);
+      L.cpos.alloc(rn + 1); L.fpos.alloc(rn + 1);
+      int *cf = cflag.p, *ff = fflag.p;
+      parallel_for(rn, [=] DEV(i64 i) { cf[i] = (vc[i] == 1.) ? 1 : 0; ff[i] = (vc[i] == 1.) ? 0 : 1; });
+      exclusive_scan(cflag.p, L.cpos.p, rn);
+      exclusive_scan(fflag.p, L.fpos.p, rn);
+      L.idc.alloc(nc); L.idf.alloc(nf);
+      const int *cp = L.cpos.p, *fp = L.fpos.p, *il = idl.p;
+      int *ic = L.idc.p, *jf = L.idf.p;
+      parallel_for(rn, [=] DEV(i64 i) { if (cf[i]) ic[cp[i]] = il[i]; else jf[fp[i]] = il[i]; });
+    }
+    L.W = interpolation(L.Af, Ac, Afc, gamma2, itol, &L.interp_rounds);
+    trace_csr("W", L.W);
+    lap(H.t.interp);
+
+    // ---- Galerkin product (:336-372): AfP = Af*W + Afc;  A = W'*AfP + Acf*W + Ac
+    {
+      Csr AfW = spgemm(L.Af, L.W);
+      L.AfP = mpm(1., AfW, 1., Afc);
+    }
+    trace_csr("AfP", L.AfP);
+    L.Wt = transpose(L.W);
+    Csr An;
+    {
+      Csr WtAfP = spgemm(L.Wt, L.AfP);
+      Csr Acf = transpose(Afc);
+      Csr AcfW = spgemm(Acf, L.W);
+      Csr Atmp = mpm(1., WtAfP, 1., AcfW);
+      An = mpm(1., Atmp, 1, Ac);
+    }
+    idl = L.idc.clone();
+    L.A = std::move(A);
+    A = std::move(An);
+    lap(H.t.galerkin);
+  }
+  c.trace_prefix.clear();
+  stream_sync();
+  H.t.total = now_s() - t_begin;
+  H.launches = c.launches - launches0;
+  H.syncs = c.syncs - syncs0;
+}
+
+}  // namespace amgb

@@ -1,0 +1,48 @@
+// setup.cuh -- the AMG hierarchy in HBM and the stages that build it.
+#pragma once
+#include "sparse.cuh"
+#include "hostmath.h"
+
+namespace amgb {
+
+// One level of struct amg_setup_data (amg_tools.h:29), resident in HBM.
+struct Level {
+  Csr A;              // data->A[l]
+  Csr Af, W, AfP;     // data->Af[l], data->W[l], data->AfP[l]   (absent on the last level)
+  Csr Wt;             // W^t, kept for the restriction b_{l+1} += W^t b_l of the V-cycle
+  Buf<double> C;      // data->C[l]: 1.0 where the dof stays on the coarse level
+  Buf<double> D;      // data->D[l]: diagonal smoother of the F block
+  Buf<int> idc, idf;  // data->idc[l], data->idf[l] (1-based ids of the finest level)
+  Buf<int> fpos, cpos;  // position of every dof among the F (resp. C) dofs of its level
+  int n = 0, nf = 0, nc = 0;
+  double m = 0, rho = 0, lmin = 0, lmax = 0;
+  int coarsen_rounds = 0, lanczos_k = 0, interp_rounds = 0;
+};
+
+struct StageTimes {    // host wall-clock with a stream sync at stage ends, seconds
+  double build = 0, coarsen = 0, smoother = 0, lanczos = 0, interp = 0, galerkin = 0, total = 0;
+  double spgemm = 0;   // device time (CUDA events) inside the SpGEMM kernels
+  i64 spgemm_bytes = 0;  // algorithmic bytes moved by those kernels
+  i64 spgemm_calls = 0;
+};
+
+struct Hierarchy {
+  std::vector<Level> lv;
+  int nullspace = 0;
+  int n0 = 0;
+  StageTimes t;
+  i64 launches = 0, syncs = 0;
+};
+
+// stages (each cites amg_setup.c)
+int coarsen(double *vc, const Csr &A, double ctol);                                   // :2737
+int lanczos(double *lambda, const Csr &A, hostmath::GlibcRand &rng, int *iters);      // :2435
+int pcg(double *x, const Csr &A, double *r, const double *M, double tol, const double *b);  // :2242
+Csr interpolation(const Csr &Af, const Csr &Ac, const Csr &Ar, double gamma2, double tol,
+                  int *rounds);                                                        // :598
+void setup(i64 nnz, const int *dAi, const int *dAj, const double *dAv, Hierarchy &H);  // :60
+
+// V-cycle (amg.c:114 amg_exec + amg.c:171 crs_solve), device vectors of length n0
+void vcycle_solve(const Hierarchy &H, double *x, const double *b);
+
+}  // namespace amgb

@@ -1,0 +1,67 @@
+// solve.cu -- the V-cycle of amg.c:114 (amg_exec) and the projection of amg.c:171 (crs_solve)
+// on the hierarchy in HBM.  amg.c keeps all levels' F rows in one vector; here every level has
+// its own numbering, which is the same arithmetic up to the column order inside rows of W/AfP.
+#include "setup.cuh"
+
+namespace amgb {
+
+void vcycle_level(const Hierarchy &H, int l, double *x, const double *b) {
+  const Level &L = H.lv[(size_t)l];
+  if (l == (int)H.lv.size() - 1) {
+    const double *a = L.A.a.p;
+    const int ns = H.nullspace;
+    const bool has = L.A.nnz > 0;
+    parallel_for(1, [=] DEV(i64) { const double d = (ns || !has) ? 0. : 1. / a[0]; x[0] = d * b[0]; });
+    return;
+  }
+  const int n = L.n, nf = L.nf, nc = L.nc;
+  Buf<double> bf(nf), bc(nc), xc(nc), xf(nf), t(nc), c1(nf), c2(nf), r(nf);
+  const double *Cf = L.C.p;
+  const int *fpos = L.fpos.p, *cpos = L.cpos.p;
+  double *bfp = bf.p, *bcp = bc.p, *xcp = xc.p, *xfp = xf.p, *tp = t.p;
+  parallel_for(n, [=] DEV(i64 i) { if (Cf[i] != 0.) bcp[cpos[i]] = b[i]; else bfp[fpos[i]] = b[i]; });
+  // b_{l+1} += W^t b_l
+  spmv(tp, 0, nullptr, 1, L.Wt, bfp);
+  parallel_for(nc, [=] DEV(i64 i) { bcp[i] = 1 * bcp[i] + 1 * tp[i]; });
+  vcycle_level(H, l + 1, xcp, bcp);
+  // x_l = W x_{l+1};  b_l -= AfP x_{l+1}
+  spmv(xfp, 0, bfp, 1, L.W, xcp);
+  spmv(bfp, 1, bfp, -1, L.AfP, xcp);
+  const double *d = L.D.p;
+  double *c = c1.p, *co = c2.p, *rp = r.p;
+  const unsigned m = (unsigned)L.m;
+  double alpha = 0, beta = 0, gamma = 0;
+  parallel_for(nf, [=] DEV(i64 i) { c[i] = d[i] * bfp[i]; });
+  if (m > 1) {
+    alpha = L.rho / 2; alpha *= alpha;
+    gamma = 2 * alpha / (1 - 2 * alpha); beta = 1 + gamma;
+    spmv(rp, 1, bfp, -1, L.Af, c);
+    { double *s = c; c = co; co = s; }
+    { double *cc = c, *cco = co; const double bt = beta;
+      parallel_for(nf, [=] DEV(i64 i) { cc[i] = bt * (cco[i] + d[i] * rp[i]); }); }
+  }
+  for (unsigned ci = 3; ci <= m; ci++) {
+    gamma = alpha * beta; gamma = gamma / (1 - gamma); beta = 1 + gamma;
+    spmv(rp, 1, bfp, -1, L.Af, c);
+    { double *s = c; c = co; co = s; }
+    { double *cc = c, *cco = co; const double bt = beta, gm = gamma;
+      parallel_for(nf, [=] DEV(i64 i) { cc[i] = bt * (cco[i] + d[i] * rp[i]) - gm * cc[i]; }); }
+  }
+  { double *cc = c;
+    parallel_for(n, [=] DEV(i64 i) {
+      if (Cf[i] != 0.) x[i] = xcp[cpos[i]];
+      else { const int f = fpos[i]; x[i] = xfp[f] + cc[f]; }
+    }); }
+}
+
+void vcycle_solve(const Hierarchy &H, double *x, const double *b) {
+  const int n = H.n0;
+  vcycle_level(H, 0, x, b);
+  if (H.nullspace) {
+    const double s = tree_sum(x, n);
+    const double avg = (1 / (double)n) * s;
+    parallel_for(n, [=] DEV(i64 i) { x[i] = x[i] - avg; });
+  }
+}
+
+}  // namespace amgb

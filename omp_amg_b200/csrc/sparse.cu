@@ -1,0 +1,364 @@
+// sparse.cu -- sparse primitives (first generation: one logical thread per row; the hot ones
+// have warp-cooperative replacements in spgemm.cu / spmv kernels below).
+#include "sparse.cuh"
+
+namespace amgb {
+
+void fill(double *p, i64 n, double v) { parallel_for(n, [=] DEV(i64 i) { p[i] = v; }); }
+void fill_int(int *p, i64 n, int v) { parallel_for(n, [=] DEV(i64 i) { p[i] = v; }); }
+
+void trace_csr(const char *tag, const Csr &A) {
+  if (!ctx().trace_on) return;
+  std::string t(tag);
+  trace_dev((t + ".ro").c_str(), A.ro.p, sizeof(int) * (size_t)(A.rn + 1));
+  trace_dev((t + ".col").c_str(), A.col.p, sizeof(int) * (size_t)A.nnz);
+  trace_dev((t + ".a").c_str(), A.a.p, sizeof(double) * (size_t)A.nnz);
+}
+
+// ---------------------------------------------------------------------------------------
+// SpMV: row sums strictly left to right, separate multiply and add (amg_tools.c:71)
+// ---------------------------------------------------------------------------------------
+void spmv_vals(double *z, double alpha, const double *y, double beta, const Csr &M, const double *vals,
+               const double *x) {
+  const int *ro = M.ro.p, *col = M.col.p;
+  const bool plain = (alpha == 0. || y == nullptr);
+  parallel_for(M.rn, [=] DEV(i64 i) {
+    double t = 0;
+    for (int j = ro[i]; j < ro[i + 1]; j++) t = t + vals[j] * x[col[j]];
+    if (plain) z[i] = beta * t;
+    else z[i] = alpha * y[i] + beta * t;
+  });
+}
+void spmv(double *z, double alpha, const double *y, double beta, const Csr &M, const double *x) {
+  spmv_vals(z, alpha, y, beta, M, M.a.p, x);
+}
+
+// ---------------------------------------------------------------------------------------
+// row-local insertion sort by column (keys unique inside a row)
+// ---------------------------------------------------------------------------------------
+template <class V>
+static HD inline void row_sort(int *key, V *val, int n) {
+  for (int i = 1; i < n; i++) {
+    int k = key[i]; V v = val[i];
+    int j = i - 1;
+    while (j >= 0 && key[j] > k) { key[j + 1] = key[j]; val[j + 1] = val[j]; j--; }
+    key[j + 1] = k; val[j + 1] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// transpose (:2000): A^t rows list the source rows in ascending order
+// ---------------------------------------------------------------------------------------
+Csr transpose(const Csr &A, Buf<int> *tpos_out) {
+  Csr T(A.cn, A.rn, A.nnz);
+  Buf<int> cnt(A.cn + 1);
+  cnt.zero();
+  const int *ro = A.ro.p, *col = A.col.p;
+  const double *a = A.a.p;
+  int *cntp = cnt.p;
+  parallel_for(A.nnz, [=] DEV(i64 e) { atomic_add(&cntp[col[e]], 1); });
+  exclusive_scan(cnt.p, T.ro.p, A.cn);
+  Buf<int> cursor(A.cn), src(A.nnz);
+  d2d(cursor.p, T.ro.p, sizeof(int) * (size_t)A.cn);
+  int *cur = cursor.p, *tcol = T.col.p, *srcp = src.p;
+  parallel_for(A.rn, [=] DEV(i64 i) {
+    for (int e = ro[i]; e < ro[i + 1]; e++) {
+      int p = atomic_add(&cur[col[e]], 1);
+      tcol[p] = (int)i; srcp[p] = e;
+    }
+  });
+  const int *tro = T.ro.p;
+  double *ta = T.a.p;
+  parallel_for(A.cn, [=] DEV(i64 c) {
+    int b = tro[c], n = tro[c + 1] - b;
+    row_sort<int>(tcol + b, srcp + b, n);
+    for (int k = 0; k < n; k++) ta[b + k] = a[srcp[b + k]];
+  });
+  if (tpos_out) {
+    tpos_out->alloc(A.nnz);
+    int *tp = tpos_out->p;
+    parallel_for(A.nnz, [=] DEV(i64 p) { tp[srcp[p]] = (int)p; });
+  }
+  return T;
+}
+
+// ---------------------------------------------------------------------------------------
+// sub_mat (:3058)
+// ---------------------------------------------------------------------------------------
+Csr sub_mat(const Csr &A, const double *vr, const double *vc) {
+  const int rn = A.rn, cn = A.cn;
+  const int *ro = A.ro.p, *col = A.col.p;
+  const double *a = A.a.p;
+  Buf<int> rflag(rn + 1), rmap(rn + 1), cflag(cn + 1), cmap(cn + 1);
+  int *rf = rflag.p, *cf = cflag.p;
+  parallel_for(rn, [=] DEV(i64 i) { rf[i] = (vr == nullptr || vr[i] != 0) ? 1 : 0; });
+  parallel_for(cn, [=] DEV(i64 i) { cf[i] = (vc == nullptr || vc[i] != 0) ? 1 : 0; });
+  int subrn = (int)exclusive_scan(rflag.p, rmap.p, rn);
+  int subcn = (int)exclusive_scan(cflag.p, cmap.p, cn);
+  Buf<int> cnt(subrn + 1);
+  int *cntp = cnt.p;
+  const int *rm = rmap.p, *cm = cmap.p;
+  parallel_for(rn, [=] DEV(i64 i) {
+    if (!rf[i]) return;
+    int c = 0;
+    for (int j = ro[i]; j < ro[i + 1]; j++) c += cf[col[j]];
+    cntp[rm[i]] = c;
+  });
+  Buf<int> sro(subrn + 1);
+  i64 nnz = exclusive_scan(cnt.p, sro.p, subrn);
+  Csr S(subrn, subcn, nnz);
+  S.ro = std::move(sro);
+  const int *sr = S.ro.p;
+  int *scol = S.col.p;
+  double *sa = S.a.p;
+  parallel_for(rn, [=] DEV(i64 i) {
+    if (!rf[i]) return;
+    int p = sr[rm[i]];
+    for (int j = ro[i]; j < ro[i + 1]; j++)
+      if (cf[col[j]]) { scol[p] = cm[col[j]]; sa[p] = a[j]; p++; }
+  });
+  return S;
+}
+
+// ---------------------------------------------------------------------------------------
+// mpm (:1684): X = alpha*A + beta*B
+// ---------------------------------------------------------------------------------------
+Csr mpm(double alpha, const Csr &A, double beta, const Csr &B) {
+  if (A.rn != B.rn || A.cn != B.cn) throw Error(-4, "mpm: dimension mismatch");
+  const int rn = A.rn;
+  const int *aro = A.ro.p, *acol = A.col.p, *bro = B.ro.p, *bcol = B.col.p;
+  const double *aa = A.a.p, *ba = B.a.p;
+  Buf<int> cnt(rn + 1);
+  int *cntp = cnt.p;
+  parallel_for(rn, [=] DEV(i64 i) {
+    int ja = aro[i], ea = aro[i + 1], jb = bro[i], eb = bro[i + 1], c = 0;
+    while (ja < ea || jb < eb) {
+      if (ja < ea && jb < eb && acol[ja] == bcol[jb]) {
+        double s = alpha * aa[ja] + beta * ba[jb];
+        if (s != 0.) c++;
+        ja++; jb++;
+      } else if (jb == eb || (ja < ea && acol[ja] < bcol[jb])) { c++; ja++; }
+      else { c++; jb++; }
+    }
+    cntp[i] = c;
+  });
+  Buf<int> xro(rn + 1);
+  i64 nnz = exclusive_scan(cnt.p, xro.p, rn);
+  Csr X(rn, A.cn, nnz);
+  X.ro = std::move(xro);
+  const int *xr = X.ro.p;
+  int *xcol = X.col.p;
+  double *xa = X.a.p;
+  parallel_for(rn, [=] DEV(i64 i) {
+    int ja = aro[i], ea = aro[i + 1], jb = bro[i], eb = bro[i + 1], p = xr[i];
+    while (ja < ea || jb < eb) {
+      if (ja < ea && jb < eb && acol[ja] == bcol[jb]) {
+        double s = alpha * aa[ja] + beta * ba[jb];
+        if (s != 0.) { xcol[p] = acol[ja]; xa[p] = s; p++; }
+        ja++; jb++;
+      } else if (jb == eb || (ja < ea && acol[ja] < bcol[jb])) {
+        xcol[p] = acol[ja]; xa[p] = alpha * aa[ja]; p++; ja++;
+      } else {
+        xcol[p] = bcol[jb]; xa[p] = beta * ba[jb]; p++; jb++;
+      }
+    }
+  });
+  return X;
+}
+
+// ---------------------------------------------------------------------------------------
+// mxmpoint (:1807): X = A.*B on the intersection pattern (zeros kept)
+// ---------------------------------------------------------------------------------------
+Csr mxmpoint(const Csr &A, const Csr &B) {
+  if (A.rn != B.rn || A.cn != B.cn) throw Error(-4, "mxmpoint: dimension mismatch");
+  const int rn = A.rn;
+  const int *aro = A.ro.p, *acol = A.col.p, *bro = B.ro.p, *bcol = B.col.p;
+  const double *aa = A.a.p, *ba = B.a.p;
+  Buf<int> cnt(rn + 1);
+  int *cntp = cnt.p;
+  parallel_for(rn, [=] DEV(i64 i) {
+    int ja = aro[i], ea = aro[i + 1], jb = bro[i], eb = bro[i + 1], c = 0;
+    while (ja < ea && jb < eb) {
+      if (acol[ja] == bcol[jb]) { c++; ja++; jb++; }
+      else if (acol[ja] < bcol[jb]) ja++;
+      else jb++;
+    }
+    cntp[i] = c;
+  });
+  Buf<int> xro(rn + 1);
+  i64 nnz = exclusive_scan(cnt.p, xro.p, rn);
+  Csr X(rn, A.cn, nnz);
+  X.ro = std::move(xro);
+  const int *xr = X.ro.p;
+  int *xcol = X.col.p;
+  double *xa = X.a.p;
+  parallel_for(rn, [=] DEV(i64 i) {
+    int ja = aro[i], ea = aro[i + 1], jb = bro[i], eb = bro[i + 1], p = xr[i];
+    while (ja < ea && jb < eb) {
+      if (acol[ja] == bcol[jb]) { xcol[p] = acol[ja]; xa[p] = aa[ja] * ba[jb]; p++; ja++; jb++; }
+      else if (acol[ja] < bcol[jb]) ja++;
+      else jb++;
+    }
+  });
+  return X;
+}
+
+// ---------------------------------------------------------------------------------------
+// build_csr_dim (:3656)
+// ---------------------------------------------------------------------------------------
+Csr coo_to_csr(i64 n, const int *Ai, const int *Aj, const double *Av, int rn, int cn) {
+  Buf<int> cnt(rn + 1);
+  cnt.zero();
+  int *cntp = cnt.p;
+  Buf<int> bad(1);
+  bad.zero();
+  int *badp = bad.p;
+  parallel_for(n, [=] DEV(i64 e) {
+    if (Av[e] == 0.) return;
+    if (Ai[e] < 0 || Ai[e] >= rn || Aj[e] < 0 || Aj[e] >= cn) { *badp = 1; return; }
+    atomic_add(&cntp[Ai[e]], 1);
+  });
+  Buf<int> xro(rn + 1);
+  i64 nnz = exclusive_scan(cnt.p, xro.p, rn);
+  if (bad.get(0)) throw Error(-5, "COO index out of range");
+  Csr X(rn, cn, nnz);
+  X.ro = std::move(xro);
+  Buf<int> cursor(rn + 1);
+  d2d(cursor.p, X.ro.p, sizeof(int) * (size_t)(rn + 1));
+  int *cur = cursor.p, *xcol = X.col.p;
+  double *xa = X.a.p;
+  parallel_for(n, [=] DEV(i64 e) {
+    if (Av[e] == 0.) return;
+    int p = atomic_add(&cur[Ai[e]], 1);
+    xcol[p] = Aj[e]; xa[p] = Av[e];
+  });
+  const int *xr = X.ro.p;
+  parallel_for(rn, [=] DEV(i64 i) {
+    int b = xr[i], m = xr[i + 1] - b;
+    row_sort<double>(xcol + b, xa + b, m);
+    for (int k = 1; k < m; k++) if (xcol[b + k] == xcol[b + k - 1]) *badp = 2;
+  });
+  if (bad.get(0) == 2) throw Error(-6, "duplicate (row,col) entries: assemble the matrix first");
+  return X;
+}
+
+// ---------------------------------------------------------------------------------------
+// diagonal helpers
+// ---------------------------------------------------------------------------------------
+void diag_of(double *D, const Csr &A) {
+  const int *ro = A.ro.p, *col = A.col.p;
+  const double *a = A.a.p;
+  parallel_for(A.rn, [=] DEV(i64 i) {
+    double d = 0.;
+    for (int j = ro[i]; j < ro[i + 1]; j++) if (col[j] == i) { d = a[j]; break; }
+    D[i] = d;
+  });
+}
+void scale_rows(Csr &A, const double *D) {
+  const int *ro = A.ro.p;
+  double *a = A.a.p;
+  parallel_for(A.rn, [=] DEV(i64 i) { for (int j = ro[i]; j < ro[i + 1]; j++) a[j] = a[j] * D[i]; });
+}
+void scale_cols(Csr &A, const double *D) {
+  const int *col = A.col.p;
+  double *a = A.a.p;
+  parallel_for(A.nnz, [=] DEV(i64 e) { a[e] = a[e] * D[col[e]]; });
+}
+void sub_diag(Csr &A, const double *D) {
+  const int *ro = A.ro.p, *col = A.col.p;
+  double *a = A.a.p;
+  parallel_for(A.rn, [=] DEV(i64 i) {
+    for (int j = ro[i]; j < ro[i + 1]; j++) if (col[j] == i) { a[j] = a[j] - D[i]; break; }
+  });
+}
+void col_sums(double *s, const Csr &A) {
+  Csr T = transpose(A);
+  const int *ro = T.ro.p;
+  const double *a = T.a.p;
+  parallel_for(T.rn, [=] DEV(i64 c) {
+    double t = 0.0;
+    for (int j = ro[c]; j < ro[c + 1]; j++) t = t + a[j];
+    s[c] = t;
+  });
+}
+int max_row_len(const Csr &A) {
+  if (A.rn == 0) return 0;
+  Buf<double> len(A.rn);
+  const int *ro = A.ro.p;
+  double *lp = len.p;
+  parallel_for(A.rn, [=] DEV(i64 i) { lp[i] = (double)(ro[i + 1] - ro[i]); });
+  double m; i64 idx;
+  max_first(len.p, A.rn, &m, &idx);
+  return (int)m;
+}
+
+// ---------------------------------------------------------------------------------------
+// SpGEMM, generation 1 (reference semantics of mxm :1894): one logical thread per row, an
+// open-addressing table per row in HBM.  Every X[i][c] is accumulated over k ascending.
+// ---------------------------------------------------------------------------------------
+Csr spgemm_rowhash(const Csr &A, const Csr &B) {
+  if (A.cn != B.rn) throw Error(-4, "spgemm: dimension mismatch");
+  const int rn = A.rn;
+  const int *aro = A.ro.p, *acol = A.col.p, *bro = B.ro.p, *bcol = B.col.p;
+  const double *aa = A.a.p, *ba = B.a.p;
+  Buf<i64> hsz(rn + 1), hoff(rn + 1);
+  i64 *hszp = hsz.p;
+  parallel_for(rn, [=] DEV(i64 i) {
+    i64 ub = 0;
+    for (int ja = aro[i]; ja < aro[i + 1]; ja++) ub += bro[acol[ja] + 1] - bro[acol[ja]];
+    i64 sz = 0;
+    if (ub > 0) { sz = 4; while (sz < 2 * ub) sz <<= 1; }
+    hszp[i] = sz;
+  });
+  i64 total = exclusive_scan64(hsz.p, hoff.p, rn);
+  Buf<int> keys(total), cnt(rn + 1), rowlen(rn + 1);
+  Buf<double> vals(total);
+  dev_memset(keys.p, 0xFF, sizeof(int) * (size_t)total);
+  int *kp = keys.p, *cntp = cnt.p, *rl = rowlen.p;
+  double *vp = vals.p;
+  const i64 *ho = hoff.p;
+  parallel_for(rn, [=] DEV(i64 i) {
+    const i64 base = ho[i], sz = ho[i + 1] - base;
+    if (sz == 0) { cntp[i] = 0; rl[i] = 0; return; }
+    int *K = kp + base;
+    double *V = vp + base;
+    const unsigned mask = (unsigned)(sz - 1);
+    for (int ja = aro[i]; ja < aro[i + 1]; ja++) {
+      const int k = acol[ja];
+      const double av = aa[ja];
+      for (int jb = bro[k]; jb < bro[k + 1]; jb++) {
+        const int c = bcol[jb];
+        unsigned h = ((unsigned)c * 2654435761u) & mask;
+        while (K[h] != -1 && K[h] != c) h = (h + 1) & mask;
+        if (K[h] == -1) { K[h] = c; V[h] = 0.0; }
+        V[h] = V[h] + ba[jb] * av;
+      }
+    }
+    int m = 0;
+    for (i64 h = 0; h < sz; h++) if (K[h] != -1) { K[m] = K[h]; V[m] = V[h]; m++; }
+    row_sort<double>(K, V, m);
+    int nz = 0;
+    for (int q = 0; q < m; q++) nz += (V[q] != 0.0);
+    rl[i] = m; cntp[i] = nz;
+  });
+  Buf<int> xro(rn + 1);
+  i64 nnz = exclusive_scan(cnt.p, xro.p, rn);
+  Csr X(rn, B.cn, nnz);
+  X.ro = std::move(xro);
+  const int *xr = X.ro.p;
+  int *xcol = X.col.p;
+  double *xa = X.a.p;
+  parallel_for(rn, [=] DEV(i64 i) {
+    const i64 base = ho[i];
+    int p = xr[i];
+    for (int q = 0; q < rl[i]; q++)
+      if (vp[base + q] != 0.0) { xcol[p] = kp[base + q]; xa[p] = vp[base + q]; p++; }
+  });
+  return X;
+}
+
+#ifdef AMGB_EMU
+Csr spgemm(const Csr &A, const Csr &B) { return spgemm_rowhash(A, B); }
+#endif
+
+}  // namespace amgb

@@ -1,0 +1,60 @@
+// sparse.cuh -- device CSR matrices and the sparse primitives of the setup path.
+// Every primitive cites the reference routine whose result it reproduces bit for bit
+// (file amg_setup.c unless stated).
+#pragma once
+#include "common.cuh"
+
+namespace amgb {
+
+// CSR in HBM: ro[rn+1] (int32), col[nnz] (int32, ascending inside a row), a[nnz] (fp64).
+// struct csr_mat, amg_tools.h:5.
+struct Csr {
+  int rn = 0, cn = 0;
+  i64 nnz = 0;
+  Buf<int> ro, col;
+  Buf<double> a;
+  Csr() {}
+  Csr(int rn_, int cn_, i64 nnz_) : rn(rn_), cn(cn_), nnz(nnz_), ro(rn_ + 1), col(nnz_), a(nnz_) {}
+  Csr(Csr &&) = default;
+  Csr &operator=(Csr &&) = default;
+  Csr clone() const {                                   // copy_csr :3463
+    Csr B;
+    B.rn = rn; B.cn = cn; B.nnz = nnz;
+    B.ro = ro.clone(); B.col = col.clone(); B.a = a.clone();
+    return B;
+  }
+};
+
+// apply_M (amg_tools.c:71): z = alpha*y + beta*(M x); y may be null (then z = beta*(M x))
+void spmv(double *z, double alpha, const double *y, double beta, const Csr &M, const double *x);
+// values-only variant: same pattern as M, other value array
+void spmv_vals(double *z, double alpha, const double *y, double beta, const Csr &M, const double *vals,
+               const double *x);
+
+// transpose :2000.  If tpos != null it receives, for every entry e of A, its position in A^t.
+Csr transpose(const Csr &A, Buf<int> *tpos = nullptr);
+// sub_mat :3058; a null flag array means "keep all"
+Csr sub_mat(const Csr &A, const double *vr, const double *vc);
+// mpm :1684
+Csr mpm(double alpha, const Csr &A, double beta, const Csr &B);
+// mxmpoint :1807
+Csr mxmpoint(const Csr &A, const Csr &B);
+// mxm :1894 as X = A*B (row-wise, every X[i][c] accumulated over k ascending, exact zeros dropped)
+Csr spgemm(const Csr &A, const Csr &B);
+// build_csr_dim :3656 from device COO arrays (zeros dropped, sorted by row then column)
+Csr coo_to_csr(i64 n, const int *Ai, const int *Aj, const double *Av, int rn, int cn);
+
+void diag_of(double *D, const Csr &A);            // diag :3363
+void scale_rows(Csr &A, const double *D);         // diagcsr_op dmult :3426
+void scale_cols(Csr &A, const double *D);         // diagcsr_op multd :3436
+void sub_diag(Csr &A, const double *D);           // diagcsr_op dminus :3412
+void col_sums(double *s, const Csr &A);           // sum(.,.,1) :1193
+int max_row_len(const Csr &A);
+
+void trace_csr(const char *tag, const Csr &A);
+
+// element-wise helpers
+void fill(double *p, i64 n, double v);
+void fill_int(int *p, i64 n, int v);
+
+}  // namespace amgb
