@@ -65,6 +65,8 @@ struct Context {
 };
 Context &ctx();
 void ctx_init(int device);
+// checks the launch; with AMGB_DEBUG_SYNC=1 also synchronises so that faults are attributed
+void post_launch(const char *what);
 
 // ---------------------------------------------------------------------------------------
 // device buffers (stream-ordered pool allocations)
@@ -127,6 +129,7 @@ inline void parallel_for(i64 n, F f) {
   if (blocks > cap) blocks = cap;
   k_parallel_for<<<(unsigned)blocks, 256, 0, c.stream>>>(n, f);
   c.launches++;
+  post_launch("parallel_for");
 }
 #else
 template <class F>
@@ -150,6 +153,13 @@ HD inline unsigned long long atomic_max_u64(unsigned long long *p, unsigned long
   return atomicMax(p, v);
 #else
   unsigned long long o = *p; if (v > o) *p = v; return o;
+#endif
+}
+HD inline int atomic_max_i32(int *p, int v) {
+#ifdef __CUDA_ARCH__
+  return atomicMax(p, v);
+#else
+  int o = *p; if (v > o) *p = v; return o;
 #endif
 }
 HD inline int atomic_min_i32(int *p, int v) {

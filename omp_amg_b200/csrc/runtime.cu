@@ -11,12 +11,20 @@ Context &ctx() { return g_ctx; }
 // CUDA build
 // =======================================================================================
 static bool g_inited = false;
+static int g_debug_sync = -1;
+void post_launch(const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && g_debug_sync > 0) e = cudaStreamSynchronize(g_ctx.stream);
+  if (e != cudaSuccess)
+    throw Error(-100, std::string("CUDA kernel '") + what + "' failed: " + cudaGetErrorString(e));
+}
 void ctx_init(int device) {
   if (g_inited) return;
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
     throw Error(-101, "omp_amg_b200: no CUDA device available (this library has no CPU path)");
+  if (g_debug_sync < 0) { const char *e = getenv("AMGB_DEBUG_SYNC"); g_debug_sync = (e && *e && *e != '0') ? 1 : 0; }
   if (device >= 0) CUDA_CHECK(cudaSetDevice(device));
   int dev = 0;
   CUDA_CHECK(cudaGetDevice(&dev));
@@ -86,15 +94,15 @@ static void scan_rec(const T *in, T *out, i64 n) {     // out[0..n) exclusive; o
   i64 nb = (n + 1023) / 1024;
   if (nb == 1) {
     k_scan_block<T><<<1, 256, 0, g_ctx.stream>>>(in, out, (T *)nullptr, n);
-    g_ctx.launches++;
+    g_ctx.launches++; post_launch(__func__);
     return;
   }
   Buf<T> bsum(nb), boff(nb);
   k_scan_block<T><<<(unsigned)nb, 256, 0, g_ctx.stream>>>(in, out, bsum.p, n);
-  g_ctx.launches++;
+  g_ctx.launches++; post_launch(__func__);
   scan_rec<T>(bsum.p, boff.p, nb);
   k_scan_add<T><<<(unsigned)nb, 256, 0, g_ctx.stream>>>(out, boff.p, n);
-  g_ctx.launches++;
+  g_ctx.launches++; post_launch(__func__);
 }
 template <class T>
 __global__ void k_scan_last(const T *in, T *out, i64 n) { out[n] = out[n - 1] + in[n - 1]; }
@@ -103,7 +111,7 @@ static T scan_total(const T *in, T *out, i64 n) {
   if (n <= 0) { T z = 0; h2d(out, &z, sizeof(T)); stream_sync(); return 0; }
   scan_rec<T>(in, out, n);
   k_scan_last<T><<<1, 1, 0, g_ctx.stream>>>(in, out, n);
-  g_ctx.launches++;
+  g_ctx.launches++; post_launch(__func__);
   T tot;
   d2h(&tot, out + n, sizeof(T));
   return tot;
@@ -150,7 +158,7 @@ static double tree_finish(Buf<double> &part, i64 nc) {
     i64 nc2 = (nc + 1023) / 1024;
     Buf<double> nxt(nc2);
     k_tree_sum<<<(unsigned)nc2, 256, 0, g_ctx.stream>>>(part.p, nc, nxt.p);
-    g_ctx.launches++;
+    g_ctx.launches++; post_launch(__func__);
     part = std::move(nxt);
     nc = nc2;
   }
@@ -161,7 +169,7 @@ double tree_sum(const double *v, i64 n) {
   i64 nc = (n + 1023) / 1024;
   Buf<double> part(nc);
   k_tree_sum<<<(unsigned)nc, 256, 0, g_ctx.stream>>>(v, n, part.p);
-  g_ctx.launches++;
+  g_ctx.launches++; post_launch(__func__);
   return tree_finish(part, nc);
 }
 double tree_dot(const double *a, const double *b, i64 n) {
@@ -169,7 +177,7 @@ double tree_dot(const double *a, const double *b, i64 n) {
   i64 nc = (n + 1023) / 1024;
   Buf<double> part(nc);
   k_tree_dot<<<(unsigned)nc, 256, 0, g_ctx.stream>>>(a, b, n, part.p);
-  g_ctx.launches++;
+  g_ctx.launches++; post_launch(__func__);
   return tree_finish(part, nc);
 }
 
@@ -210,7 +218,7 @@ void max_first(const double *v, i64 n, double *val, i64 *idx) {
   Buf<i64> pi(nb), fi(1);
   k_max_first<<<(unsigned)nb, 256, 0, g_ctx.stream>>>(v, nullptr, n, pv.p, pi.p);
   k_max_first<<<1, 256, 0, g_ctx.stream>>>(pv.p, pi.p, nb, fv.p, fi.p);
-  g_ctx.launches += 2;
+  g_ctx.launches += 2; post_launch(__func__);
   struct { double v; i64 i; } out;
   d2h(&out.v, fv.p, sizeof(double));
   d2h(&out.i, fi.p, sizeof(i64));
@@ -233,7 +241,7 @@ i64 count_nonzero(const double *v, i64 n) {
   i64 nb = (n + 255) / 256;
   if (nb > 1184) nb = 1184;
   k_count_nonzero<<<(unsigned)nb, 256, 0, g_ctx.stream>>>(v, n, c.p);
-  g_ctx.launches++;
+  g_ctx.launches++; post_launch(__func__);
   return (i64)c.get(0);
 }
 
@@ -242,6 +250,7 @@ i64 count_nonzero(const double *v, i64 n) {
 // host emulation build (tests only)
 // =======================================================================================
 void ctx_init(int) {}
+void post_launch(const char *) {}
 void *dev_alloc(size_t bytes) { void *p = malloc(bytes ? bytes : 8); if (!p) throw Error(-2, "out of memory"); return p; }
 void dev_free(void *p) { free(p); }
 void dev_memset(void *p, int v, size_t bytes) { memset(p, v, bytes); }

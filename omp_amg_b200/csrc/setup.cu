@@ -676,20 +676,17 @@ Csr interpolation(const Csr &Af, const Csr &Ac, const Csr &Ar, double gamma2, do
 // amg_setup (:60)
 // =======================================================================================
 // build_csr (:3612): assemble, then drop empty rows and the same-numbered columns
-static Csr build_csr(i64 n, const int *Ai, const int *Aj, const double *Av) {
-  Buf<double> mx(2);
+Csr build_csr(i64 n, const int *Ai, const int *Aj, const double *Av) {
   // dimensions: 1 + largest index among the non-zero entries
   Buf<int> dims(2);
   dims.zero();
   int *dp = dims.p;
   parallel_for(n, [=] DEV(i64 e) {
     if (Av[e] == 0.) return;
-#ifdef __CUDA_ARCH__
-    atomicMax(&dp[0], Ai[e] + 1); atomicMax(&dp[1], Aj[e] + 1);
-#else
-    if (Ai[e] + 1 > dp[0]) dp[0] = Ai[e] + 1;
-    if (Aj[e] + 1 > dp[1]) dp[1] = Aj[e] + 1;
-#endif
+    // (no __CUDA_ARCH__ test inside an extended lambda: it would change the capture order
+    // between the host and device passes and with it the kernel's mangled name)
+    atomic_max_i32(&dp[0], Ai[e] + 1);
+    atomic_max_i32(&dp[1], Aj[e] + 1);
   });
   std::vector<int> hd = dims.download();
   int rn = hd[0] > hd[1] ? hd[0] : hd[1];

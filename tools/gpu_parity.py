@@ -13,8 +13,18 @@ def main():
     cases = sys.argv[1:] or ["dump:0", "poisson7:6", "poisson7:12", "poisson27:7", "sem_hex:8", "aniso7:10", "poisson7:20"]
     nbad = 0
     for c in cases:
+        timeonly = c.startswith("t:")
+        if timeonly: c = c[2:]
         name, n = c.split(":"); n = int(n)
         mat = M.read_amgdmp(os.path.join(ROOT, "tests", "golden")) if name == "dump" else M.by_name(name, n)
+        if timeonly:
+            for rep in range(2):
+                t = time.time(); Hp2 = api.amg_setup(*mat, L=L); dt = time.time() - t
+                tm = Hp2.timing()
+                print(c, "levels", [Hp2.level_info(l)["n"] for l in range(Hp2.nlevels)], flush=True)
+                print("   time-only %.4fs" % dt, {k: (round(v, 5) if isinstance(v, float) else v) for k, v in tm.items()}, flush=True)
+                Hp2.free()
+            continue
         h = O.setup_raw(*mat, orc.TREE, trace=True); Ho = O.fetch(h); to = O.trace(); O.free(h)
         L.amgb_trace_enable(1)
         t = time.time(); Hp = api.amg_setup(*mat, L=L); dt = time.time() - t
