@@ -1,0 +1,425 @@
+// localsolve.cu -- cooperative kernels for the local A-orthogonalisation (see localsolve.cuh).
+//
+// Arithmetic contract (what makes the results bit-identical to the reference): every sum is
+// formed in the reference's order -- mv_utt rows left to right, mv_ut columns in ascending j
+// starting from 0, the alpha recurrence in ascending m, QQ^t in ascending k -- with separate
+// multiply and add (the library is compiled with --fmad=false).  Parallelism is only ever over
+// independent outputs, never inside one sum.
+#include "localsolve.cuh"
+
+#ifndef AMGB_EMU
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+#endif
+
+namespace amgb {
+
+static HD inline i64 tri(i64 k) { return k * (k + 1) / 2; }
+
+// value of the sorted sparse row (xi, x, xn) at index t, 0 if absent (sp_restrict_sorted :2180)
+static HD inline double row_at(const int *xi, const double *x, int xn, int t) {
+  int lo = 0, hi = xn;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (xi[mid] < t) lo = mid + 1; else hi = mid; }
+  return (lo < xn && xi[lo] == t) ? x[lo] : 0.0;
+}
+static HD inline int pos_of(const int *xi, int xn, int t) {
+  int lo = 0, hi = xn;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (xi[mid] < t) lo = mid + 1; else hi = mid; }
+  return (lo < xn && xi[lo] == t) ? lo : -1;
+}
+
+void q_offsets(QStore &qs, const Csr &Wt) {
+  Buf<i64> sz(Wt.rn + 1), len(1);
+  qs.qoff.alloc(Wt.rn + 1);
+  const int *ro = Wt.ro.p;
+  i64 *s = sz.p;
+  parallel_for(Wt.rn, [=] DEV(i64 i) { const i64 nz = ro[i + 1] - ro[i]; s[i] = nz * (nz + 1) / 2; });
+  qs.total = exclusive_scan64(sz.p, qs.qoff.p, Wt.rn);
+  qs.maxnz = max_row_len(Wt);
+  qs.Q.alloc(qs.total);
+}
+void qq_offsets(QQStore &qq, const Csr &Wt) {
+  Buf<i64> sz(Wt.rn + 1);
+  qq.qqoff.alloc(Wt.rn + 1);
+  const int *ro = Wt.ro.p;
+  i64 *s = sz.p;
+  parallel_for(Wt.rn, [=] DEV(i64 i) { const i64 nz = ro[i + 1] - ro[i]; s[i] = nz * nz; });
+  const i64 total = exclusive_scan64(sz.p, qq.qqoff.p, Wt.rn);
+  qq.QQ.alloc(total);
+}
+
+#ifdef AMGB_EMU
+// =======================================================================================
+// host emulation: straight restatement, one logical thread per column / row
+// =======================================================================================
+void build_q_store(QStore &qs, const Csr &Wt, const Csr &At) {
+  q_offsets(qs, Wt);
+  Buf<double> scratch((i64)2 * (qs.maxnz + 1));
+  const int *wro = Wt.ro.p, *wcol = Wt.col.p, *aro = At.ro.p, *acol = At.col.p;
+  const double *aa = At.a.p;
+  double *Qall = qs.Q.p, *sc = scratch.p;
+  const i64 *qo = qs.qoff.p;
+  const int mx = qs.maxnz + 1;
+  parallel_for(Wt.rn, [=] DEV(i64 i) {
+    const int b = wro[i], nz = wro[i + 1] - b;
+    const int *Qj = wcol + b;
+    double *Q = Qall + qo[i], *sqv1 = sc, *sqv2 = sc + mx;
+    for (int k = 0; k < nz; k++) {
+      const int s = Qj[k];
+      double *qk = Q + tri(k);
+      for (int m = 0; m <= k; m++) sqv1[m] = row_at(acol + aro[s], aa + aro[s], aro[s + 1] - aro[s], Qj[m]);
+      for (int r = 0; r < k; r++) { double v = 0; const double *u = Q + tri(r); for (int j = 0; j <= r; j++) v = v + u[j] * sqv1[j]; sqv2[r] = v; }
+      for (int r = 0; r < k; r++) { double y = 0; for (int j = r; j < k; j++) y = y + Q[tri(j) + r] * sqv2[j]; qk[r] = y; }
+      double alpha = sqv1[k];
+      for (int m = 0; m < k; m++) alpha = alpha - sqv1[m] * qk[m];
+      alpha = -1.0 / sqrt(alpha);
+      for (int m = 0; m < k; m++) qk[m] = qk[m] * alpha;
+      qk[k] = -alpha;
+    }
+  });
+}
+void apply_q(const QStore &qs, Csr &Wt, const Csr &Bt, const double *u, const double *lambda) {
+  Buf<double> scratch((i64)2 * (qs.maxnz + 1));
+  const int *wro = Wt.ro.p, *wcol = Wt.col.p, *bro = Bt.ro.p, *bcol = Bt.col.p;
+  const double *ba = Bt.a.p, *Qall = qs.Q.p;
+  double *wa = Wt.a.p, *sc = scratch.p;
+  const i64 *qo = qs.qoff.p;
+  const int mx = qs.maxnz + 1;
+  parallel_for(Wt.rn, [=] DEV(i64 i) {
+    const int b = wro[i], nz = wro[i + 1] - b;
+    const int *Qj = wcol + b;
+    const double *Q = Qall + qo[i];
+    double *sqv1 = sc, *sqv2 = sc + mx;
+    for (int k = 0; k < nz; k++) {
+      const double v = row_at(bcol + bro[i], ba + bro[i], bro[i + 1] - bro[i], Qj[k]);
+      sqv1[k] = v + u[i] * lambda[Qj[k]];
+    }
+    for (int r = 0; r < nz; r++) { double v = 0; const double *uu = Q + tri(r); for (int j = 0; j <= r; j++) v = v + uu[j] * sqv1[j]; sqv2[r] = v; }
+    for (int r = 0; r < nz; r++) { double y = 0; for (int j = r; j < nz; j++) y = y + Q[tri(j) + r] * sqv2[j]; wa[b + r] = y; }
+  });
+}
+void form_qq(QQStore &qq, const QStore &qs, const Csr &Wt) {
+  qq_offsets(qq, Wt);
+  const int *wro = Wt.ro.p;
+  const double *Qall = qs.Q.p;
+  double *QQ = qq.QQ.p;
+  const i64 *qo = qs.qoff.p, *qqo = qq.qqoff.p;
+  parallel_for(Wt.rn, [=] DEV(i64 i) {
+    const int nz = wro[i + 1] - wro[i];
+    const double *Q = Qall + qo[i];
+    double *out = QQ + qqo[i];
+    for (int m = 0; m < nz; m++)
+      for (int j = m; j < nz; j++) {
+        double acc = 0;
+        for (int k = j; k < nz; k++) acc = acc + Q[tri(k) + m] * Q[tri(k) + j];
+        out[(i64)m * nz + j] = acc; out[(i64)j * nz + m] = acc;
+      }
+  });
+}
+void lmop_accumulate(Csr &S, const QQStore &qq, const double *u, const Csr &Wskt, const Csr &Wsk,
+                     const int *tpos) {
+  const int *sro = S.ro.p, *scol = S.col.p, *kro = Wsk.ro.p, *kcol = Wsk.col.p, *tro = Wskt.ro.p, *tcol = Wskt.col.p;
+  double *sa = S.a.p;
+  const double *QQ = qq.QQ.p;
+  const i64 *qqo = qq.qqoff.p;
+  parallel_for(S.rn, [=] DEV(i64 j) {
+    const int yb = sro[j], yn = sro[j + 1] - yb;
+    for (int q = 0; q < yn; q++) sa[yb + q] = 0.0;
+    if (yn == 0) return;
+    for (int e = kro[j]; e < kro[j + 1]; e++) {
+      const int i = kcol[e];
+      const int b = tro[i], nz = tro[i + 1] - b, k = tpos[e] - b;
+      const double ui = u[i];
+      const double *x = QQ + qqo[i] + (i64)k * nz;
+      for (int kk = 0; kk < nz; kk++) {
+        const int p = pos_of(scol + yb, yn, tcol[b + kk]);
+        if (p >= 0) sa[yb + p] = sa[yb + p] + ui * x[kk];
+      }
+    }
+  });
+}
+
+#else
+// =======================================================================================
+// CUDA: G cooperating threads per coarse column (G = 8, 32, or a whole block)
+// =======================================================================================
+template <class Group>
+__device__ __forceinline__ void build_q_coop(const Group &g, int nz, const int *Qj, const int *aro,
+                                             const int *acol, const double *aa, double *Q,
+                                             double *sqv1, double *sqv2) {
+  const int r0 = g.thread_rank(), G = g.size();
+  for (int k = 0; k < nz; k++) {
+    const int s = Qj[k];
+    const int ab = aro[s], an = aro[s + 1] - ab;
+    double *qk = Q + tri(k);
+    for (int m = r0; m <= k; m += G) sqv1[m] = row_at(acol + ab, aa + ab, an, Qj[m]);
+    g.sync();
+    for (int r = r0; r < k; r += G) {                 // mv_utt: row r of Q^t, left to right
+      double v = 0;
+      const double *u = Q + tri(r);
+      for (int j = 0; j <= r; j++) v = v + u[j] * sqv1[j];
+      sqv2[r] = v;
+    }
+    g.sync();
+    for (int r = r0; r < k; r += G) {                 // mv_ut: ascending j, starting from 0
+      double y = 0;
+      for (int j = r; j < k; j++) y = y + Q[tri(j) + r] * sqv2[j];
+      qk[r] = y;
+    }
+    g.sync();
+    double alpha = sqv1[k];                           // every thread forms the same recurrence
+    for (int m = 0; m < k; m++) alpha = alpha - sqv1[m] * qk[m];
+    alpha = -1.0 / sqrt(alpha);
+    g.sync();
+    for (int m = r0; m < k; m += G) qk[m] = qk[m] * alpha;
+    if (r0 == 0) qk[k] = -alpha;
+    g.sync();
+  }
+}
+
+struct BlockGroup {
+  __device__ __forceinline__ int thread_rank() const { return threadIdx.x; }
+  __device__ __forceinline__ int size() const { return blockDim.x; }
+  __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+
+// small columns: 8 threads per column, everything in shared memory
+template <int NZCAP>
+__global__ void __launch_bounds__(256) k_build_q_tile8(const int *list, int nlist, const int *wro, const int *wcol,
+                                                       const int *aro, const int *acol, const double *aa,
+                                                       double *Qall, const i64 *qoff) {
+  constexpr int PER = 2 * NZCAP + NZCAP * (NZCAP + 1) / 2;
+  __shared__ double sm[32 * PER];
+  auto tile = cg::tiled_partition<8>(cg::this_thread_block());
+  const int slot = threadIdx.x / 8;
+  const int idx = blockIdx.x * 32 + slot;
+  if (idx >= nlist) return;
+  const int i = list[idx];
+  const int b = wro[i], nz = wro[i + 1] - b;
+  double *sqv1 = sm + slot * PER, *sqv2 = sqv1 + NZCAP, *Q = sqv2 + NZCAP;
+  build_q_coop(tile, nz, wcol + b, aro, acol, aa, Q, sqv1, sqv2);
+  double *out = Qall + qoff[i];
+  const int nq = (int)tri(nz);
+  for (int t = tile.thread_rank(); t < nq; t += 8) out[t] = Q[t];
+}
+
+// one block per column; Q in shared memory (QSMEM) or directly in the global store
+template <bool QSMEM>
+__global__ void k_build_q_block(const int *list, int nlist, int nzcap, const int *wro, const int *wcol,
+                                const int *aro, const int *acol, const double *aa, double *Qall,
+                                const i64 *qoff) {
+  extern __shared__ double sm[];
+  const int idx = blockIdx.x;
+  if (idx >= nlist) return;
+  const int i = list[idx];
+  const int b = wro[i], nz = wro[i + 1] - b;
+  double *sqv1 = sm, *sqv2 = sm + nzcap;
+  double *Qg = Qall + qoff[i];
+  double *Q = QSMEM ? (sm + 2 * nzcap) : Qg;
+  BlockGroup g;
+  build_q_coop(g, nz, wcol + b, aro, acol, aa, Q, sqv1, sqv2);
+  if (QSMEM) {
+    const int nq = (int)tri(nz);
+    for (int t = threadIdx.x; t < nq; t += blockDim.x) Qg[t] = Q[t];
+  }
+}
+
+static void set_smem(const void *fn, size_t bytes) {
+  CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+void build_q_store(QStore &qs, const Csr &Wt, const Csr &At) {
+  q_offsets(qs, Wt);
+  const int n = Wt.rn;
+  if (n == 0) return;
+  // bin the columns by support size: <=8 | <=32 | <=144 | larger
+  Buf<int> lists((i64)4 * n), cnt(4);
+  cnt.zero();
+  const int *wro = Wt.ro.p;
+  int *lp = lists.p, *cp = cnt.p;
+  parallel_for(n, [=] DEV(i64 i) {
+    const int nz = wro[i + 1] - wro[i];
+    if (nz == 0) return;
+    const int bin = nz <= 8 ? 0 : nz <= 32 ? 1 : nz <= 144 ? 2 : 3;
+    const int p = atomic_add(&cp[bin], 1);
+    lp[(i64)bin * n + p] = (int)i;
+  });
+  std::vector<int> hc = cnt.download();
+  Context &c = ctx();
+  const int *wcol = Wt.col.p, *aro = At.ro.p, *acol = At.col.p;
+  const double *aa = At.a.p;
+  if (hc[0]) {
+    k_build_q_tile8<8><<<(hc[0] + 31) / 32, 256, 0, c.stream>>>(lp, hc[0], wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
+    c.launches++; post_launch("build_q_tile8");
+  }
+  if (hc[1]) {
+    const size_t sm = sizeof(double) * (2 * 32 + tri(32));
+    k_build_q_block<true><<<hc[1], 32, sm, c.stream>>>(lp + n, hc[1], 32, wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
+    c.launches++; post_launch("build_q_block32");
+  }
+  if (hc[2]) {
+    const size_t sm = sizeof(double) * (2 * 144 + tri(144));
+    static bool attr = false;
+    if (!attr) { set_smem((const void *)k_build_q_block<true>, sizeof(double) * (2 * 144 + tri(144))); attr = true; }
+    k_build_q_block<true><<<hc[2], 128, sm, c.stream>>>(lp + 2 * (i64)n, hc[2], 144, wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
+    c.launches++; post_launch("build_q_block144");
+  }
+  if (hc[3]) {
+    const size_t sm = sizeof(double) * (2 * (size_t)qs.maxnz);
+    k_build_q_block<false><<<hc[3], 256, sm, c.stream>>>(lp + 3 * (i64)n, hc[3], qs.maxnz, wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
+    c.launches++; post_launch("build_q_global");
+  }
+}
+
+// ---- apply: W row := Q (Q^t (R(B e_i + u_i lambda))) ----
+template <int G>
+__global__ void __launch_bounds__(256) k_apply_q(int n, int nzcap, const int *wro, const int *wcol, double *wa,
+                                                 const int *bro, const int *bcol, const double *ba,
+                                                 const double *u, const double *lambda, const double *Qall,
+                                                 const i64 *qoff) {
+  extern __shared__ double sm[];
+  auto tile = cg::tiled_partition<G>(cg::this_thread_block());
+  const int slot = threadIdx.x / G, per = blockDim.x / G;
+  const int i = blockIdx.x * per + slot;
+  if (i >= n) return;
+  const int b = wro[i], nz = wro[i + 1] - b;
+  if (nz == 0) return;
+  const int *Qj = wcol + b;
+  const double *Q = Qall + qoff[i];
+  double *sqv1 = sm + (size_t)slot * 2 * nzcap, *sqv2 = sqv1 + nzcap;
+  const int r0 = tile.thread_rank();
+  const int bb = bro[i], bn = bro[i + 1] - bb;
+  const double ui = u[i];
+  for (int k = r0; k < nz; k += G) {
+    const double v = row_at(bcol + bb, ba + bb, bn, Qj[k]);
+    sqv1[k] = v + ui * lambda[Qj[k]];
+  }
+  tile.sync();
+  for (int r = r0; r < nz; r += G) {
+    double v = 0;
+    const double *uu = Q + tri(r);
+    for (int j = 0; j <= r; j++) v = v + uu[j] * sqv1[j];
+    sqv2[r] = v;
+  }
+  tile.sync();
+  for (int r = r0; r < nz; r += G) {
+    double y = 0;
+    for (int j = r; j < nz; j++) y = y + Q[tri(j) + r] * sqv2[j];
+    wa[b + r] = y;
+  }
+}
+
+void apply_q(const QStore &qs, Csr &Wt, const Csr &Bt, const double *u, const double *lambda) {
+  const int n = Wt.rn;
+  if (n == 0) return;
+  Context &c = ctx();
+  const int nzcap = qs.maxnz > 0 ? qs.maxnz : 1;
+  if (qs.maxnz <= 16) {
+    const int per = 256 / 8;
+    const size_t sm = sizeof(double) * (size_t)per * 2 * nzcap;
+    k_apply_q<8><<<(n + per - 1) / per, 256, sm, c.stream>>>(n, nzcap, Wt.ro.p, Wt.col.p, Wt.a.p, Bt.ro.p, Bt.col.p,
+                                                             Bt.a.p, u, lambda, qs.Q.p, qs.qoff.p);
+  } else {
+    int threads = 256;
+    size_t sm = sizeof(double) * (size_t)(threads / 32) * 2 * nzcap;
+    while (sm > 160 * 1024 && threads > 32) { threads /= 2; sm = sizeof(double) * (size_t)(threads / 32) * 2 * nzcap; }
+    if (sm > 48 * 1024) set_smem((const void *)k_apply_q<32>, sm);
+    const int per = threads / 32;
+    k_apply_q<32><<<(n + per - 1) / per, threads, sm, c.stream>>>(n, nzcap, Wt.ro.p, Wt.col.p, Wt.a.p, Bt.ro.p,
+                                                                  Bt.col.p, Bt.a.p, u, lambda, qs.Q.p, qs.qoff.p);
+  }
+  c.launches++; post_launch("apply_q");
+}
+
+// ---- QQ^t: one block per column (one warp for small ones), pairs (m<=j) over threads ----
+__global__ void __launch_bounds__(128) k_form_qq(int n, const int *wro, const double *Qall, const i64 *qoff,
+                                                 double *QQ, const i64 *qqoff) {
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  const int nz = wro[i + 1] - wro[i];
+  const double *Q = Qall + qoff[i];
+  double *out = QQ + qqoff[i];
+  for (int idx = threadIdx.x; idx < nz * nz; idx += blockDim.x) {
+    const int m = idx / nz, j = idx - m * nz;
+    if (m > j) continue;
+    double acc = 0;
+    for (int k = j; k < nz; k++) acc = acc + Q[tri(k) + m] * Q[tri(k) + j];
+    out[(i64)m * nz + j] = acc;
+    out[(i64)j * nz + m] = acc;
+  }
+}
+// tiny columns: one thread group of 8 per column
+__global__ void __launch_bounds__(256) k_form_qq_small(int n, const int *wro, const double *Qall, const i64 *qoff,
+                                                       double *QQ, const i64 *qqoff) {
+  const int i = blockIdx.x * 32 + threadIdx.x / 8;
+  if (i >= n) return;
+  const int nz = wro[i + 1] - wro[i];
+  const double *Q = Qall + qoff[i];
+  double *out = QQ + qqoff[i];
+  for (int idx = threadIdx.x & 7; idx < nz * nz; idx += 8) {
+    const int m = idx / nz, j = idx - m * nz;
+    if (m > j) continue;
+    double acc = 0;
+    for (int k = j; k < nz; k++) acc = acc + Q[tri(k) + m] * Q[tri(k) + j];
+    out[(i64)m * nz + j] = acc;
+    out[(i64)j * nz + m] = acc;
+  }
+}
+void form_qq(QQStore &qq, const QStore &qs, const Csr &Wt) {
+  qq_offsets(qq, Wt);
+  const int n = Wt.rn;
+  if (n == 0) return;
+  Context &c = ctx();
+  if (qs.maxnz <= 12)
+    k_form_qq_small<<<(n + 31) / 32, 256, 0, c.stream>>>(n, Wt.ro.p, qs.Q.p, qs.qoff.p, qq.QQ.p, qq.qqoff.p);
+  else
+    k_form_qq<<<n, 128, 0, c.stream>>>(n, Wt.ro.p, qs.Q.p, qs.qoff.p, qq.QQ.p, qq.qqoff.p);
+  c.launches++; post_launch("form_qq");
+}
+
+// ---- S accumulation: G threads per row of S; coarse points in ascending order ----
+template <int G>
+__global__ void __launch_bounds__(256) k_lmop_acc(int nrows, const int *sro, const int *scol, double *sa,
+                                                  const int *kro, const int *kcol, const int *tro,
+                                                  const int *tcol, const int *tpos, const double *u,
+                                                  const double *QQ, const i64 *qqoff) {
+  auto tile = cg::tiled_partition<G>(cg::this_thread_block());
+  const int j = blockIdx.x * (blockDim.x / G) + threadIdx.x / G;
+  if (j >= nrows) return;
+  const int r0 = tile.thread_rank();
+  const int yb = sro[j], yn = sro[j + 1] - yb;
+  for (int q = r0; q < yn; q += G) sa[yb + q] = 0.0;
+  if (yn == 0) return;
+  tile.sync();
+  for (int e = kro[j]; e < kro[j + 1]; e++) {
+    const int i = kcol[e];
+    const int b = tro[i], nz = tro[i + 1] - b, k = tpos[e] - b;
+    const double ui = u[i];
+    const double *x = QQ + qqoff[i] + (i64)k * nz;
+    for (int kk = r0; kk < nz; kk += G) {
+      const int p = pos_of(scol + yb, yn, tcol[b + kk]);
+      if (p >= 0) sa[yb + p] = sa[yb + p] + ui * x[kk];
+    }
+    tile.sync();
+  }
+}
+void lmop_accumulate(Csr &S, const QQStore &qq, const double *u, const Csr &Wskt, const Csr &Wsk,
+                     const int *tpos) {
+  const int n = S.rn;
+  if (n == 0) return;
+  Context &c = ctx();
+  const double avg = (double)S.nnz / (double)n;
+  if (avg <= 24.0) {
+    const int per = 256 / 8;
+    k_lmop_acc<8><<<(n + per - 1) / per, 256, 0, c.stream>>>(n, S.ro.p, S.col.p, S.a.p, Wsk.ro.p, Wsk.col.p, Wskt.ro.p,
+                                                             Wskt.col.p, tpos, u, qq.QQ.p, qq.qqoff.p);
+  } else {
+    const int per = 256 / 32;
+    k_lmop_acc<32><<<(n + per - 1) / per, 256, 0, c.stream>>>(n, S.ro.p, S.col.p, S.a.p, Wsk.ro.p, Wsk.col.p, Wskt.ro.p,
+                                                              Wskt.col.p, tpos, u, qq.QQ.p, qq.qqoff.p);
+  }
+  c.launches++; post_launch("lmop_acc");
+}
+#endif
+
+}  // namespace amgb

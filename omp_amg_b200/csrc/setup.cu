@@ -2,6 +2,7 @@
 // Host code only orchestrates: every matrix- or vector-sized operation is a kernel.
 // All citations are amg_setup.c lines of the reference unless another file is named.
 #include "setup.cuh"
+#include "localsolve.cuh"
 #include <chrono>
 
 namespace amgb {
@@ -216,133 +217,17 @@ int lanczos(double *lambda, const Csr &A, hostmath::GlibcRand &rng, int *iters) 
 }
 
 // =======================================================================================
-// local energy-minimising solves: interp (:2053) and interp_lmop (:1589)
+// interpolation weights: the local solves live in localsolve.cu
 // =======================================================================================
-// sp_restrict_sorted (:2180)
-HD inline void restrict_sorted(double *y, int Rn, const int *Ri, int xn, const int *xi, const double *x) {
-  int p = 0;
-  for (int k = 0; k < Rn; k++) {
-    while (p < xn && xi[p] < Ri[k]) p++;
-    y[k] = (p < xn && xi[p] == Ri[k]) ? x[p] : 0.0;
-  }
-}
-// mv_utt (:2122)
-HD inline void tri_t_mv(double *y, int n, const double *U, const double *x) {
-  for (int i = 0; i < n; i++) {
-    double v = 0;
-    const double *u = U + (size_t)i * (i + 1) / 2;
-    for (int j = 0; j <= i; j++) v = v + u[j] * x[j];
-    y[i] = v;
-  }
-}
-// mv_ut (:2138)
-HD inline void tri_mv(double *y, int n, const double *U, const double *x) {
-  for (int j = 0; j < n; j++) {
-    y[j] = 0;
-    const double *u = U + (size_t)j * (j + 1) / 2;
-    for (int i = 0; i <= j; i++) y[i] = y[i] + u[i] * x[j];
-  }
-}
-// A-orthogonalisation of the support Qj (:2081-2099); optional QQt accumulation (:1637)
-HD inline void build_Q(double *Q, double *sqv1, double *sqv2, double *QQt, int nz, const int *Qj,
-                       const int *aro, const int *acol, const double *aa) {
-  double *qk = Q;
-  if (QQt) for (int k = 0; k < nz * nz; k++) QQt[k] = 0;
-  for (int k = 0; k < nz; k++, qk += k) {
-    const int s = Qj[k];
-    restrict_sorted(sqv1, k + 1, Qj, aro[s + 1] - aro[s], acol + aro[s], aa + aro[s]);
-    tri_t_mv(sqv2, k, Q, sqv1);
-    tri_mv(qk, k, Q, sqv2);
-    double alpha = sqv1[k];
-    for (int m = 0; m < k; m++) alpha = alpha - sqv1[m] * qk[m];
-    alpha = -1.0 / sqrt(alpha);
-    for (int m = 0; m < k; m++) qk[m] = qk[m] * alpha;
-    qk[k] = -alpha;
-    if (QQt)
-      for (int m = 0; m <= k; m++) {
-        const double qkm = qk[m];
-        for (int j = 0; j <= k; j++) QQt[m * nz + j] = QQt[m * nz + j] + qkm * qk[j];
-      }
-  }
-}
-
-// scratch layout per coarse column: sqv1[nz] sqv2[nz] Q[nz(nz+1)/2]
-void column_scratch_offsets(const Csr &Wt, Buf<i64> &off, i64 *total) {
-  Buf<i64> sz(Wt.rn + 1);
-  off.alloc(Wt.rn + 1);
-  const int *ro = Wt.ro.p;
-  i64 *s = sz.p;
-  parallel_for(Wt.rn, [=] DEV(i64 i) { i64 nz = ro[i + 1] - ro[i]; s[i] = 2 * nz + nz * (nz + 1) / 2; });
-  *total = exclusive_scan64(sz.p, off.p, Wt.rn);
-}
-
-// interp (:2053): overwrite the values of Wt (one row per coarse point) with
-// Q Q^t R (B e_i + u_i lambda)
-void interp(Csr &Wt, const Csr &At, const Csr &Bt, const double *u, const double *lambda) {
-  Buf<i64> off;
-  i64 total;
-  column_scratch_offsets(Wt, off, &total);
-  Buf<double> scratch(total);
-  const int *wro = Wt.ro.p, *wcol = Wt.col.p, *aro = At.ro.p, *acol = At.col.p, *bro = Bt.ro.p, *bcol = Bt.col.p;
-  const double *aa = At.a.p, *ba = Bt.a.p;
-  double *wa = Wt.a.p, *sc = scratch.p;
-  const i64 *offp = off.p;
-  parallel_for(Wt.rn, [=] DEV(i64 i) {
-    const int wir = wro[i], nz = wro[i + 1] - wir;
-    if (nz == 0) return;
-    const int *Qj = wcol + wir;
-    double *sqv1 = sc + offp[i], *sqv2 = sqv1 + nz, *Q = sqv2 + nz;
-    build_Q(Q, sqv1, sqv2, nullptr, nz, Qj, aro, acol, aa);
-    restrict_sorted(sqv1, nz, Qj, bro[i + 1] - bro[i], bcol + bro[i], ba + bro[i]);
-    for (int k = 0; k < nz; k++) sqv1[k] = sqv1[k] + u[i] * lambda[Qj[k]];
-    tri_t_mv(sqv2, nz, Q, sqv1);
-    tri_mv(wa + wir, nz, Q, sqv2);
-  });
-}
-
-// interp_lmop (:1589): S = sum over coarse points i of u_i * Q_i Q_i^t scattered into the
-// pattern of S.  Phase 1 forms every Q_i Q_i^t; phase 2 lets every row of S collect its
-// contributions in ascending i, which is the order the reference's loop produces.  A target
-// that is absent from the pattern of S is skipped (the reference's sp_add :1665 does not check
-// and writes to a wrong entry there; see DESIGN.md "sp_add").
-void interp_lmop(Csr &S, const Csr &At, const double *u, const Csr &Wskt, const Csr &Wsk,
-                 const int *tpos) {
-  Buf<i64> off, qsz(Wskt.rn + 1), qoff(Wskt.rn + 1);
-  i64 total;
-  column_scratch_offsets(Wskt, off, &total);
-  const int *tro = Wskt.ro.p, *tcol = Wskt.col.p, *aro = At.ro.p, *acol = At.col.p;
-  const double *aa = At.a.p;
-  { i64 *q = qsz.p; parallel_for(Wskt.rn, [=] DEV(i64 i) { i64 nz = tro[i + 1] - tro[i]; q[i] = nz * nz; }); }
-  const i64 qtotal = exclusive_scan64(qsz.p, qoff.p, Wskt.rn);
-  Buf<double> scratch(total), QQ(qtotal);
-  double *sc = scratch.p, *qq = QQ.p;
-  const i64 *offp = off.p, *qo = qoff.p;
-  parallel_for(Wskt.rn, [=] DEV(i64 i) {
-    const int b = tro[i], nz = tro[i + 1] - b;
-    if (nz == 0) return;
-    double *sqv1 = sc + offp[i], *sqv2 = sqv1 + nz, *Q = sqv2 + nz;
-    build_Q(Q, sqv1, sqv2, qq + qo[i], nz, tcol + b, aro, acol, aa);
-  });
-  const int *sro = S.ro.p, *scol = S.col.p, *kro = Wsk.ro.p, *kcol = Wsk.col.p;
-  double *sa = S.a.p;
-  parallel_for(S.rn, [=] DEV(i64 j) {
-    const int yb = sro[j], yn = sro[j + 1] - yb;
-    for (int q = 0; q < yn; q++) sa[yb + q] = 0.0;
-    if (yn == 0) return;
-    for (int e = kro[j]; e < kro[j + 1]; e++) {
-      const int i = kcol[e];
-      const int b = tro[i], nz = tro[i + 1] - b, k = tpos[e] - b;
-      const double ui = u[i];
-      const double *x = qq + qo[i] + (i64)k * nz;
-      const int *xi = tcol + b;
-      int p = 0;
-      for (int kk = 0; kk < nz; kk++) {
-        while (p < yn && scol[yb + p] < xi[kk]) p++;
-        if (p < yn && scol[yb + p] == xi[kk]) { sa[yb + p] = sa[yb + p] + ui * x[kk]; p++; }
-      }
-    }
-  });
-}
+// per-skeleton data shared by the solves of one interpolation round: W_skel^t with its position
+// map, the packed Q of every coarse column, their Q Q^t blocks and the pattern of W_skel*W_skel^t
+struct SkelCache {
+  bool valid = false, has_qq = false, has_S = false;
+  Csr Wskt, Spat;
+  Buf<int> tpos;
+  QStore qs;
+  QQStore qq;
+};
 
 // min_skel (:2198)
 Csr min_skel(const Csr &R) {
@@ -366,13 +251,14 @@ Csr min_skel(const Csr &R) {
 }
 
 // solve_constraint (:1499)
-void solve_constraint(double *lam, const Csr &Wsk, const Csr &Wskt, const int *tpos, const Csr &Af,
-                      const Csr &W0, const double *alpha, const double *u, const double *v, double tol) {
+void solve_constraint(double *lam, const Csr &Wsk, SkelCache &sk, const Csr &W0, const double *alpha,
+                      const double *u, const double *v, double tol) {
   const int nf = Wsk.rn, nc = Wsk.cn;
   Buf<double> au2(nc);
   { double *p = au2.p; parallel_for(nc, [=] DEV(i64 i) { const double uu = u[i] * u[i]; p[i] = uu * alpha[i]; }); }
-  Csr S = spgemm(Wsk, Wskt);
-  interp_lmop(S, Af, au2.p, Wskt, Wsk, tpos);
+  if (!sk.has_qq) { form_qq(sk.qq, sk.qs, sk.Wskt); sk.has_qq = true; }
+  Csr S = sk.Spat.clone();
+  lmop_accumulate(S, sk.qq, au2.p, sk.Wskt, Wsk, sk.tpos.p);
   trace_csr("sc.S", S);
   Buf<double> resid(nf), d(nf), keep(nf);
   spmv(resid.p, 1.0, v, -1.0, W0, u);
@@ -411,21 +297,25 @@ void solve_constraint(double *lam, const Csr &Wsk, const Csr &Wskt, const int *t
 // solve_weights (:1437).  W and W0 share the pattern of W_skel; their values come back from the
 // transposed solves through the transpose position map, which equals transposing them again.
 void solve_weights(Csr &W, Csr &W0, double *lam, const Csr &Wsk, const Csr &Af, const Csr &Armt,
-                   const double *alpha, const double *u, const double *v, double tol) {
+                   const double *alpha, const double *u, const double *v, double tol, SkelCache &sk) {
   const int nf = Af.rn, nc = Wsk.cn;
   Buf<double> au(nc), zeros(nf);
   { double *p = au.p; parallel_for(nc, [=] DEV(i64 i) { p[i] = alpha[i] * u[i]; }); }
   zeros.zero();
-  Buf<int> tpos;
-  Csr Wskt = transpose(Wsk, &tpos);
-  Csr W0t = Wskt.clone();
-  interp(W0t, Af, Armt, au.p, zeros.p);
+  if (!sk.valid) {       // the basis Q of every coarse column depends on the skeleton and Af only
+    sk.Wskt = transpose(Wsk, &sk.tpos);
+    sk.Spat = spgemm(Wsk, sk.Wskt);   // pattern of W_skel*W_skel' (:1513), while Wskt holds 0/1
+    build_q_store(sk.qs, sk.Wskt, Af);
+    sk.valid = true; sk.has_qq = false; sk.has_S = true;
+  }
+  Csr &Wskt = sk.Wskt;
+  const int *tp = sk.tpos.p;
+  apply_q(sk.qs, Wskt, Armt, au.p, zeros.p);          // interp(W0t, Af, -Ar', au, 0) :1467
   W0 = Wsk.clone();
-  const int *tp = tpos.p;
-  { double *dst = W0.a.p; const double *src = W0t.a.p; parallel_for(Wsk.nnz, [=] DEV(i64 e) { dst[e] = src[tp[e]]; }); }
-  solve_constraint(lam, Wsk, Wskt, tp, Af, W0, alpha, u, v, tol);
+  { double *dst = W0.a.p; const double *src = Wskt.a.p; parallel_for(Wsk.nnz, [=] DEV(i64 e) { dst[e] = src[tp[e]]; }); }
+  solve_constraint(lam, Wsk, sk, W0, alpha, u, v, tol);
   trace_dev("sw.lam", lam, sizeof(double) * (size_t)nf);
-  interp(Wskt, Af, Armt, au.p, lam);
+  apply_q(sk.qs, Wskt, Armt, au.p, lam);              // interp(Wt, Af, -Ar', au, lam) :1482
   W = Wsk.clone();
   { double *dst = W.a.p; const double *src = Wskt.a.p; parallel_for(Wsk.nnz, [=] DEV(i64 e) { dst[e] = src[tp[e]]; }); }
 }
@@ -606,6 +496,7 @@ Csr interpolation(const Csr &Af, const Csr &Ac, const Csr &Ar, double gamma2, do
   { double *a = Armt.a.p; parallel_for(Armt.nnz, [=] DEV(i64 e) { a[e] = a[e] * -1.0; }); }
   double *dsq = Dcsqrti.p, *w1p = w1.p, *w2p = w2.p, *rp = r.p, *alp = alpha.p;
   Csr W;
+  SkelCache sk;
   int rounds = 0;
   const std::string pfx_save = ctx().trace_prefix;
   for (;;) {
@@ -614,7 +505,7 @@ Csr interpolation(const Csr &Af, const Csr &Ac, const Csr &Ar, double gamma2, do
     if (ctx().trace_on) ctx().trace_prefix = pfx_save + "r" + std::to_string(rounds) + ".";
     trace_csr("ip.Wsk", Wsk);
     Csr Wt, W0;
-    solve_weights(Wt, W0, lam.p, Wsk, Af, Armt, alp, uc.p, v.p, tol);
+    solve_weights(Wt, W0, lam.p, Wsk, Af, Armt, alp, uc.p, v.p, tol, sk);
     trace_csr("ip.W0", W0);
     trace_csr("ip.Wtmp", Wt);
     Csr R0, R;
@@ -651,7 +542,7 @@ Csr interpolation(const Csr &Af, const Csr &Ac, const Csr &Ar, double gamma2, do
     max_first(w1p, nc, &w1m, nullptr);
     if (nbig == 0 || w1m <= gamma2) {
       Csr W0b;
-      solve_weights(W, W0b, lam.p, Wsk, Af, Armt, alp, uc.p, v.p, 1e-16);
+      solve_weights(W, W0b, lam.p, Wsk, Af, Armt, alp, uc.p, v.p, 1e-16, sk);
       Buf<double> wuc(nf);
       spmv(wuc.p, 0., nullptr, 1., W, uc.p);
       // the reference rescales only entries whose column index equals the row index (:821-837)
@@ -666,6 +557,7 @@ Csr interpolation(const Csr &Af, const Csr &Ac, const Csr &Ar, double gamma2, do
     }
     parallel_for(nc, [=] DEV(i64 i) { const double x = w2p[i] > 1e-6 ? w2p[i] : 1e-6; alp[i] = dcp[i] / x; });
     Wsk = expand_support(Wsk, R, R0, gamma2);
+    sk = SkelCache();
   }
   ctx().trace_prefix = pfx_save;
   if (rounds_out) *rounds_out = rounds;
@@ -704,6 +596,7 @@ void setup(i64 nnz, const int *dAi, const int *dAj, const double *dAv, Hierarchy
   const i64 launches0 = c.launches, syncs0 = c.syncs;
   const double t_begin = now_s();
   double t0 = t_begin;
+  spgemm_stats_reset();
   auto lap = [&](double &acc) { stream_sync(); const double t = now_s(); acc += t - t0; t0 = t; };
   Csr A = build_csr(nnz, dAi, dAj, dAv);
   lap(H.t.build);
@@ -824,6 +717,7 @@ void setup(i64 nnz, const int *dAi, const int *dAj, const double *dAv, Hierarchy
   c.trace_prefix.clear();
   stream_sync();
   H.t.total = now_s() - t_begin;
+  spgemm_stats_get(&H.t.spgemm, &H.t.spgemm_bytes, &H.t.spgemm_calls);
   H.launches = c.launches - launches0;
   H.syncs = c.syncs - syncs0;
 }

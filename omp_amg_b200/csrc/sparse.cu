@@ -46,6 +46,26 @@ static HD inline void row_sort(int *key, V *val, int n) {
   }
 }
 
+#ifndef AMGB_EMU
+// rank sort of every row of the transposed matrix by G cooperating threads: keys (source rows)
+// are unique inside a row, so the rank of a key is the number of smaller keys
+template <int G>
+__global__ void __launch_bounds__(256) k_transpose_rank(int nrows, const int *tro, const int *kin, const int *sin,
+                                                        int *kout, int *sout, const double *a, double *ta) {
+  const int c = blockIdx.x * (256 / G) + threadIdx.x / G;
+  if (c >= nrows) return;
+  const int r0 = threadIdx.x % G;
+  const int b = tro[c], L = tro[c + 1] - b;
+  for (int e = r0; e < L; e += G) {
+    const int key = kin[b + e];
+    int rank = 0;
+    for (int f = 0; f < L; f++) rank += (kin[b + f] < key);
+    const int s = sin[b + e];
+    kout[b + rank] = key; sout[b + rank] = s; ta[b + rank] = a[s];
+  }
+}
+#endif
+
 // ---------------------------------------------------------------------------------------
 // transpose (:2000): A^t rows list the source rows in ascending order
 // ---------------------------------------------------------------------------------------
@@ -69,11 +89,23 @@ Csr transpose(const Csr &A, Buf<int> *tpos_out) {
   });
   const int *tro = T.ro.p;
   double *ta = T.a.p;
+#ifdef AMGB_EMU
   parallel_for(A.cn, [=] DEV(i64 c) {
     int b = tro[c], n = tro[c + 1] - b;
     row_sort<int>(tcol + b, srcp + b, n);
     for (int k = 0; k < n; k++) ta[b + k] = a[srcp[b + k]];
   });
+#else
+  if (A.cn > 0 && A.nnz > 0) {
+    Buf<int> kin = T.col.clone(), sin = src.clone();
+    Context &c = ctx();
+    if ((double)A.nnz / (double)A.cn <= 12.0)
+      k_transpose_rank<8><<<(A.cn + 31) / 32, 256, 0, c.stream>>>(A.cn, tro, kin.p, sin.p, tcol, srcp, a, ta);
+    else
+      k_transpose_rank<32><<<(A.cn + 7) / 8, 256, 0, c.stream>>>(A.cn, tro, kin.p, sin.p, tcol, srcp, a, ta);
+    c.launches++; post_launch("transpose_rank");
+  }
+#endif
   if (tpos_out) {
     tpos_out->alloc(A.nnz);
     int *tp = tpos_out->p;
@@ -356,9 +388,5 @@ Csr spgemm_rowhash(const Csr &A, const Csr &B) {
   });
   return X;
 }
-
-#ifdef AMGB_EMU
-Csr spgemm(const Csr &A, const Csr &B) { return spgemm_rowhash(A, B); }
-#endif
 
 }  // namespace amgb

@@ -53,6 +53,10 @@ int max_row_len(const Csr &A);
 
 void trace_csr(const char *tag, const Csr &A);
 
+// device time / algorithmic bytes of the SpGEMM kernels since the last reset (spgemm.cu)
+void spgemm_stats_reset();
+void spgemm_stats_get(double *seconds, i64 *bytes, i64 *calls);
+
 // element-wise helpers
 void fill(double *p, i64 n, double v);
 void fill_int(int *p, i64 n, int v);

@@ -1,9 +1,269 @@
-// spgemm.cu -- Galerkin-product SpGEMM (mxm, amg_setup.c:1894).
+// spgemm.cu -- the Galerkin-product SpGEMM (mxm, amg_setup.c:1894) as a two-phase hash SpGEMM.
+//
+// Reference semantics that must survive: X[i][c] = sum over k ASCENDING of B[k][c]*A[i][k]
+// (separate multiply and add), entries whose sum is exactly 0 are not stored, columns ascending.
+//
+// Kernel shape: G cooperating threads own one row of X (G = 8, 32 or a block).  They walk the
+// row of A sequentially; for each k the G threads take the entries of row k of B side by side --
+// those have distinct columns, so no two threads ever touch the same accumulator in one step,
+// and the steps are ordered by a group barrier: every accumulator sees its addends in ascending
+// k.  Accumulators live in an open-addressing table in shared memory sized by the row's upper
+// bound (bins), or in HBM for the rare row that does not fit.  Phase 1 counts the surviving
+// entries per row, a scan turns counts into row offsets, phase 2 recomputes, sorts the table
+// (bitonic, zeros and empty slots pushed to the end) and writes the row.
 #include "sparse.cuh"
 
-namespace amgb {
-Csr spgemm_rowhash(const Csr &A, const Csr &B);
 #ifndef AMGB_EMU
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+#endif
+
+namespace amgb {
+
+Csr spgemm_rowhash(const Csr &A, const Csr &B);
+
+#ifndef AMGB_EMU
+namespace {
+constexpr int EMPTY = 0x7fffffff;
+
+struct BlockGroup {
+  __device__ __forceinline__ int thread_rank() const { return threadIdx.x; }
+  __device__ __forceinline__ int size() const { return blockDim.x; }
+  __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+
+__device__ __forceinline__ unsigned hash_col(int c) { return (unsigned)c * 2654435761u; }
+
+// accumulate row i of A*B into the table (keys, vals) of HS slots (power of two)
+template <class Group>
+__device__ __forceinline__ void accumulate_row(const Group &g, int i, const int *aro, const int *acol,
+                                               const double *aa, const int *bro, const int *bcol,
+                                               const double *ba, int *keys, double *vals, int HS) {
+  const int r0 = g.thread_rank(), G = g.size();
+  const unsigned mask = (unsigned)(HS - 1);
+  for (int h = r0; h < HS; h += G) keys[h] = EMPTY;
+  g.sync();
+  for (int ja = aro[i]; ja < aro[i + 1]; ja++) {
+    const int k = acol[ja];
+    const double av = aa[ja];
+    const int be = bro[k + 1];
+    for (int jb = bro[k] + r0; jb < be; jb += G) {
+      const int c = bcol[jb];
+      const double p = ba[jb] * av;
+      unsigned h = hash_col(c) & mask;
+      for (;;) {
+        const int old = atomicCAS(&keys[h], EMPTY, c);
+        if (old == EMPTY) { double v = 0.0; v = v + p; vals[h] = v; break; }
+        if (old == c) { vals[h] = vals[h] + p; break; }
+        h = (h + 1) & mask;
+      }
+    }
+    g.sync();
+  }
+}
+
+// exact zeros leave the row (mxm stores y[ib] only if != 0); returns the survivor count
+template <class Group>
+__device__ __forceinline__ int drop_zeros_count(const Group &g, int *keys, const double *vals, int HS, int *red) {
+  const int r0 = g.thread_rank(), G = g.size();
+  int c = 0;
+  for (int h = r0; h < HS; h += G) {
+    if (keys[h] != EMPTY) { if (vals[h] == 0.0) keys[h] = EMPTY; else c++; }
+  }
+  // group sum through a shared counter
+  if (r0 == 0) *red = 0;
+  g.sync();
+  if (c) atomicAdd(red, c);
+  g.sync();
+  return *red;
+}
+
+template <class Group>
+__device__ __forceinline__ void bitonic_sort(const Group &g, int *keys, double *vals, int HS) {
+  const int r0 = g.thread_rank(), G = g.size();
+  for (int k = 2; k <= HS; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int idx = r0; idx < HS; idx += G) {
+        const int ixj = idx ^ j;
+        if (ixj > idx) {
+          const int ka = keys[idx], kb = keys[ixj];
+          const bool up = ((idx & k) == 0);
+          if ((ka > kb) == up && ka != kb) {
+            keys[idx] = kb; keys[ixj] = ka;
+            const double t = vals[idx]; vals[idx] = vals[ixj]; vals[ixj] = t;
+          }
+        }
+      }
+      g.sync();
+    }
+  }
+}
+
+template <class Group>
+__device__ __forceinline__ void row_phase(const Group &g, int phase, int i, const int *aro, const int *acol,
+                                          const double *aa, const int *bro, const int *bcol, const double *ba,
+                                          int *keys, double *vals, int HS, int *red, int *cnt, const int *xro,
+                                          int *xcol, double *xa) {
+  accumulate_row(g, i, aro, acol, aa, bro, bcol, ba, keys, vals, HS);
+  const int n = drop_zeros_count(g, keys, vals, HS, red);
+  if (phase == 1) { if (g.thread_rank() == 0) cnt[i] = n; return; }
+  bitonic_sort(g, keys, vals, HS);
+  const int base = xro[i];
+  for (int q = g.thread_rank(); q < n; q += g.size()) { xcol[base + q] = keys[q]; xa[base + q] = vals[q]; }
+}
+
+// G-thread tiles, table in shared memory: HS slots per tile
+template <int G, int HS>
+__global__ void __launch_bounds__(256) k_spgemm_tile(int phase, const int *list, int nlist, const int *aro,
+                                                     const int *acol, const double *aa, const int *bro,
+                                                     const int *bcol, const double *ba, int *cnt, const int *xro,
+                                                     int *xcol, double *xa) {
+  constexpr int PER = 256 / G;
+  __shared__ int skeys[PER * HS];
+  __shared__ double svals[PER * HS];
+  __shared__ int sred[PER];
+  auto tile = cg::tiled_partition<G>(cg::this_thread_block());
+  const int slot = threadIdx.x / G;
+  const int idx = blockIdx.x * PER + slot;
+  if (idx >= nlist) return;
+  row_phase(tile, phase, list[idx], aro, acol, aa, bro, bcol, ba, skeys + slot * HS, svals + slot * HS, HS,
+            sred + slot, cnt, xro, xcol, xa);
+}
+
+// one block per row, table in dynamic shared memory
+__global__ void k_spgemm_block(int phase, int HS, const int *list, int nlist, const int *aro, const int *acol,
+                               const double *aa, const int *bro, const int *bcol, const double *ba, int *cnt,
+                               const int *xro, int *xcol, double *xa) {
+  extern __shared__ double dsm[];
+  __shared__ int sred;
+  double *svals = dsm;
+  int *skeys = (int *)(dsm + HS);
+  if ((int)blockIdx.x >= nlist) return;
+  BlockGroup g;
+  row_phase(g, phase, list[blockIdx.x], aro, acol, aa, bro, bcol, ba, skeys, svals, HS, &sred, cnt, xro, xcol, xa);
+}
+
+// one block per row, table in HBM (rows whose bound exceeds the shared-memory bins)
+__global__ void k_spgemm_global(int phase, const int *list, int nlist, const i64 *toff, int *gkeys, double *gvals,
+                                const int *aro, const int *acol, const double *aa, const int *bro,
+                                const int *bcol, const double *ba, int *cnt, const int *xro, int *xcol,
+                                double *xa) {
+  __shared__ int sred;
+  if ((int)blockIdx.x >= nlist) return;
+  const i64 base = toff[blockIdx.x];
+  const int HS = (int)(toff[blockIdx.x + 1] - base);
+  BlockGroup g;
+  row_phase(g, phase, list[blockIdx.x], aro, acol, aa, bro, bcol, ba, gkeys + base, gvals + base, HS, &sred, cnt,
+            xro, xcol, xa);
+}
+}  // namespace
+
+struct SpgemmStats { std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev; i64 bytes = 0; i64 calls = 0; };
+static SpgemmStats g_stats;
+void spgemm_stats_reset() {
+  for (auto &e : g_stats.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  g_stats.ev.clear(); g_stats.bytes = 0; g_stats.calls = 0;
+}
+// device seconds spent between the recorded event pairs; call after a stream sync
+void spgemm_stats_get(double *seconds, i64 *bytes, i64 *calls) {
+  double s = 0;
+  for (auto &e : g_stats.ev) { float ms = 0; if (cudaEventElapsedTime(&ms, e.first, e.second) == cudaSuccess) s += ms * 1e-3; }
+  *seconds = s; *bytes = g_stats.bytes; *calls = g_stats.calls;
+}
+
+static int g_spgemm_impl = -1;
+
+Csr spgemm(const Csr &A, const Csr &B) {
+  if (g_spgemm_impl < 0) { const char *e = getenv("AMGB_SPGEMM"); g_spgemm_impl = (e && !strcmp(e, "rowhash")) ? 0 : 1; }
+  if (g_spgemm_impl == 0) return spgemm_rowhash(A, B);
+  if (A.cn != B.rn) throw Error(-4, "spgemm: dimension mismatch");
+  Context &c = ctx();
+  const int rn = A.rn;
+  if (rn == 0) { Csr X(0, B.cn, 0); X.ro.zero(); return X; }
+  const int *aro = A.ro.p, *acol = A.col.p, *bro = B.ro.p, *bcol = B.col.p;
+  const double *aa = A.a.p, *ba = B.a.p;
+  // bins by the row's bound on distinct columns: min(sum of B row lengths, columns of B)
+  constexpr int NB = 5;
+  Buf<int> lists((i64)NB * rn), bcnt(NB), need(rn);
+  bcnt.zero();
+  int *lp = lists.p, *bc = bcnt.p, *nd = need.p;
+  const int bcn = B.cn;
+  parallel_for(rn, [=] DEV(i64 i) {
+    i64 ub = 0;
+    for (int ja = aro[i]; ja < aro[i + 1]; ja++) ub += bro[acol[ja] + 1] - bro[acol[ja]];
+    if (ub > bcn) ub = bcn;
+    nd[i] = (int)ub;
+    const int bin = ub <= 24 ? 0 : ub <= 96 ? 1 : ub <= 768 ? 2 : ub <= 6144 ? 3 : 4;
+    const int p = atomic_add(&bc[bin], 1);
+    lp[(i64)bin * rn + p] = (int)i;
+  });
+  std::vector<int> hc = bcnt.download();
+  // rows of the last bin get tables in HBM
+  Buf<i64> tsz, toff;
+  Buf<int> gkeys;
+  Buf<double> gvals;
+  if (hc[4]) {
+    tsz.alloc(hc[4] + 1); toff.alloc(hc[4] + 1);
+    i64 *ts = tsz.p;
+    const int *l4 = lp + 4 * (i64)rn;
+    parallel_for(hc[4], [=] DEV(i64 q) { i64 s = 4096; while (s < 2 * (i64)nd[l4[q]]) s <<= 1; ts[q] = s; });
+    const i64 total = exclusive_scan64(tsz.p, toff.p, hc[4]);
+    gkeys.alloc(total); gvals.alloc(total);
+  }
+  Buf<int> cnt(rn + 1), xro(rn + 1);
+  cudaEvent_t e0, e1;
+  CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+  static bool attr = false;
+  if (!attr) {
+    CUDA_CHECK(cudaFuncSetAttribute((const void *)k_spgemm_block, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 12));
+    attr = true;
+  }
+  Csr X;
+  CUDA_CHECK(cudaEventRecord(e0, c.stream));
+  for (int phase = 1; phase <= 2; phase++) {
+    int *xcol = phase == 2 ? X.col.p : nullptr;
+    double *xa = phase == 2 ? X.a.p : nullptr;
+    if (hc[0]) {
+      k_spgemm_tile<8, 64><<<(hc[0] + 31) / 32, 256, 0, c.stream>>>(phase, lp, hc[0], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+      c.launches++; post_launch("spgemm_tile8");
+    }
+    if (hc[1]) {
+      k_spgemm_tile<32, 256><<<(hc[1] + 7) / 8, 256, 0, c.stream>>>(phase, lp + rn, hc[1], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+      c.launches++; post_launch("spgemm_tile32");
+    }
+    if (hc[2]) {
+      k_spgemm_block<<<hc[2], 128, 2048 * 12, c.stream>>>(phase, 2048, lp + 2 * (i64)rn, hc[2], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+      c.launches++; post_launch("spgemm_block2k");
+    }
+    if (hc[3]) {
+      k_spgemm_block<<<hc[3], 256, 16384 * 12, c.stream>>>(phase, 16384, lp + 3 * (i64)rn, hc[3], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+      c.launches++; post_launch("spgemm_block16k");
+    }
+    if (hc[4]) {
+      k_spgemm_global<<<hc[4], 256, 0, c.stream>>>(phase, lp + 4 * (i64)rn, hc[4], toff.p, gkeys.p, gvals.p, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+      c.launches++; post_launch("spgemm_global");
+    }
+    if (phase == 1) {
+      CUDA_CHECK(cudaEventRecord(e1, c.stream));
+      g_stats.ev.emplace_back(e0, e1);
+      const i64 nnz = exclusive_scan(cnt.p, xro.p, rn);
+      X = Csr(rn, B.cn, nnz);
+      d2d(X.ro.p, xro.p, sizeof(int) * (size_t)(rn + 1));
+      CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+      CUDA_CHECK(cudaEventRecord(e0, c.stream));
+    }
+  }
+  CUDA_CHECK(cudaEventRecord(e1, c.stream));
+  g_stats.ev.emplace_back(e0, e1);
+  // algorithmic bytes: A, B and X each moved once (12 B per entry, 4 B per row offset)
+  g_stats.bytes += 12 * (A.nnz + B.nnz + X.nnz) + 4 * ((i64)A.rn + B.rn + X.rn + 3);
+  g_stats.calls++;
+  return X;
+}
+#else
+void spgemm_stats_reset() {}
+void spgemm_stats_get(double *seconds, i64 *bytes, i64 *calls) { *seconds = 0; *bytes = 0; *calls = 0; }
 Csr spgemm(const Csr &A, const Csr &B) { return spgemm_rowhash(A, B); }
 #endif
+
 }  // namespace amgb
