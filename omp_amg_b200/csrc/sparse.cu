@@ -18,10 +18,45 @@ void trace_csr(const char *tag, const Csr &A) {
 // ---------------------------------------------------------------------------------------
 // SpMV: row sums strictly left to right, separate multiply and add (amg_tools.c:71)
 // ---------------------------------------------------------------------------------------
+#ifndef AMGB_EMU
+// G threads per row: the products of G consecutive entries are formed side by side (coalesced
+// loads), then added to the running sum one after the other in entry order, so the row sum has
+// the reference's left-to-right rounding.  Every thread of the group carries the same sum.
+template <int G>
+__global__ void __launch_bounds__(256) k_spmv_tile(int rn, const int *ro, const int *col, const double *vals,
+                                                   const double *x, double *z, double alpha, const double *y,
+                                                   double beta, bool plain) {
+  const int i = blockIdx.x * (256 / G) + threadIdx.x / G;
+  if (i >= rn) return;
+  const int lane = threadIdx.x % G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+  const int end = ro[i + 1];
+  double t = 0;
+  for (int base = ro[i]; base < end; base += G) {
+    const int j = base + lane;
+    const double p = (j < end) ? vals[j] * x[col[j]] : 0.0;
+    const int m = min(G, end - base);
+    for (int l = 0; l < m; l++) t = t + __shfl_sync(gmask, p, l, G);
+  }
+  if (lane == 0) z[i] = plain ? beta * t : alpha * y[i] + beta * t;
+}
+#endif
+
 void spmv_vals(double *z, double alpha, const double *y, double beta, const Csr &M, const double *vals,
                const double *x) {
   const int *ro = M.ro.p, *col = M.col.p;
   const bool plain = (alpha == 0. || y == nullptr);
+#ifndef AMGB_EMU
+  if (M.rn > 0 && (double)M.nnz / (double)M.rn > 8.0) {
+    Context &c = ctx();
+    if ((double)M.nnz / (double)M.rn <= 64.0)
+      k_spmv_tile<8><<<(M.rn + 31) / 32, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain);
+    else
+      k_spmv_tile<32><<<(M.rn + 7) / 8, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain);
+    c.launches++; post_launch("spmv_tile");
+    return;
+  }
+#endif
   parallel_for(M.rn, [=] DEV(i64 i) {
     double t = 0;
     for (int j = ro[i]; j < ro[i + 1]; j++) t = t + vals[j] * x[col[j]];

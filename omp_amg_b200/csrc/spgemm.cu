@@ -156,6 +156,96 @@ __global__ void k_spgemm_global(int phase, const int *list, int nlist, const i64
   row_phase(g, phase, list[blockIdx.x], aro, acol, aa, bro, bcol, ba, gkeys + base, gvals + base, HS, &sred, cnt,
             xro, xcol, xa);
 }
+
+// ---- block-wide exclusive scan of one int per thread (blockDim.x <= 256) ----
+__device__ __forceinline__ int block_excl_scan(int v, int *tmp, int *total) {
+  const int t = threadIdx.x, T = blockDim.x;
+  tmp[t] = v;
+  __syncthreads();
+  for (int off = 1; off < T; off <<= 1) {
+    const int add = (t >= off) ? tmp[t - off] : 0;
+    __syncthreads();
+    tmp[t] += add;
+    __syncthreads();
+  }
+  const int incl = tmp[t];
+  if (total) *total = tmp[T - 1];
+  __syncthreads();
+  return incl - v;
+}
+
+// Dense accumulator: when B has few columns the whole row of X fits in shared memory as a dense
+// array; no hashing and no sorting, the columns come out in order.  Untouched and exactly
+// cancelled entries are both 0.0 and both dropped, which is what mxm does.
+__global__ void __launch_bounds__(256) k_spgemm_dense(int phase, int cn, const int *list, int nlist,
+                                                      const int *aro, const int *acol, const double *aa,
+                                                      const int *bro, const int *bcol, const double *ba, int *cnt,
+                                                      const int *xro, int *xcol, double *xa) {
+  extern __shared__ double acc[];
+  __shared__ int stmp[256];
+  __shared__ int stotal;
+  if ((int)blockIdx.x >= nlist) return;
+  const int i = list[blockIdx.x];
+  const int t = threadIdx.x, T = blockDim.x;
+  for (int c = t; c < cn; c += T) acc[c] = 0.0;
+  __syncthreads();
+  for (int ja = aro[i]; ja < aro[i + 1]; ja++) {
+    const int k = acol[ja];
+    const double av = aa[ja];
+    const int be = bro[k + 1];
+    for (int jb = bro[k] + t; jb < be; jb += T) { const int c = bcol[jb]; acc[c] = acc[c] + ba[jb] * av; }
+    __syncthreads();
+  }
+  const int seg = (cn + T - 1) / T;
+  const int c0 = t * seg, c1 = min(cn, c0 + seg);
+  int mine = 0;
+  for (int c = c0; c < c1; c++) mine += (acc[c] != 0.0);
+  const int off = block_excl_scan(mine, stmp, &stotal);
+  if (phase == 1) { if (t == 0) cnt[i] = stotal; return; }
+  int p = xro[i] + off;
+  for (int c = c0; c < c1; c++) if (acc[c] != 0.0) { xcol[p] = c; xa[p] = acc[c]; p++; }
+}
+
+// Hash table in shared memory plus a bitmap of the surviving columns: the rank of a column is
+// the number of set bits below it, so the row is written in column order without sorting.
+__global__ void __launch_bounds__(256) k_spgemm_block_bitmap(int phase, int HS, int cn, const int *list, int nlist,
+                                                             const int *aro, const int *acol, const double *aa,
+                                                             const int *bro, const int *bcol, const double *ba,
+                                                             int *cnt, const int *xro, int *xcol, double *xa) {
+  extern __shared__ double dsm[];
+  __shared__ int sred;
+  __shared__ int stmp[256];
+  double *svals = dsm;
+  int *skeys = (int *)(dsm + HS);
+  unsigned *bits = (unsigned *)(skeys + HS);
+  const int nw = (cn + 31) / 32;
+  int *wpre = (int *)(bits + nw);
+  if ((int)blockIdx.x >= nlist) return;
+  const int i = list[blockIdx.x];
+  BlockGroup g;
+  accumulate_row(g, i, aro, acol, aa, bro, bcol, ba, skeys, svals, HS);
+  const int n = drop_zeros_count(g, skeys, svals, HS, &sred);
+  if (phase == 1) { if (threadIdx.x == 0) cnt[i] = n; return; }
+  const int t = threadIdx.x, T = blockDim.x;
+  for (int w = t; w < nw; w += T) bits[w] = 0u;
+  __syncthreads();
+  for (int h = t; h < HS; h += T) { const int c = skeys[h]; if (c != EMPTY) atomicOr(&bits[c >> 5], 1u << (c & 31)); }
+  __syncthreads();
+  const int seg = (nw + T - 1) / T;
+  const int w0 = t * seg, w1 = min(nw, w0 + seg);
+  int mine = 0;
+  for (int w = w0; w < w1; w++) mine += __popc(bits[w]);
+  int run = block_excl_scan(mine, stmp, nullptr);
+  for (int w = w0; w < w1; w++) { wpre[w] = run; run += __popc(bits[w]); }
+  __syncthreads();
+  const int base = xro[i];
+  for (int h = t; h < HS; h += T) {
+    const int c = skeys[h];
+    if (c == EMPTY) continue;
+    const int rank = wpre[c >> 5] + __popc(bits[c >> 5] & ((1u << (c & 31)) - 1u));
+    xcol[base + rank] = c; xa[base + rank] = svals[h];
+  }
+}
 }  // namespace
 
 struct SpgemmStats { std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev; i64 bytes = 0; i64 calls = 0; };
@@ -183,17 +273,29 @@ Csr spgemm(const Csr &A, const Csr &B) {
   const int *aro = A.ro.p, *acol = A.col.p, *bro = B.ro.p, *bcol = B.col.p;
   const double *aa = A.a.p, *ba = B.a.p;
   // bins by the row's bound on distinct columns: min(sum of B row lengths, columns of B)
+  //   0: <=24   8-thread tiles, 64-slot tables        1: <=96  warps, 256-slot tables
+  //   rows above that: dense shared-memory accumulator if B has <= DENSE_MAX columns, else
+  //   2: <=768  block, 2048 slots + bitmap   3: <=3072 block, 8192 slots + bitmap
+  //   4: anything else: block, table in HBM, bitonic sort
   constexpr int NB = 5;
+  constexpr int DENSE_MAX = 24576;
+  const int bcn = B.cn;
+  const bool dense = bcn <= DENSE_MAX;
+  const bool bitmap_ok = ((i64)(bcn + 31) / 32) * 8 + 8192 * 12 <= 200 * 1024;
   Buf<int> lists((i64)NB * rn), bcnt(NB), need(rn);
   bcnt.zero();
   int *lp = lists.p, *bc = bcnt.p, *nd = need.p;
-  const int bcn = B.cn;
   parallel_for(rn, [=] DEV(i64 i) {
     i64 ub = 0;
     for (int ja = aro[i]; ja < aro[i + 1]; ja++) ub += bro[acol[ja] + 1] - bro[acol[ja]];
     if (ub > bcn) ub = bcn;
     nd[i] = (int)ub;
-    const int bin = ub <= 24 ? 0 : ub <= 96 ? 1 : ub <= 768 ? 2 : ub <= 6144 ? 3 : 4;
+    int bin;
+    if (ub <= 24) bin = 0;
+    else if (ub <= 96) bin = 1;
+    else if (dense) bin = 2;
+    else if (!bitmap_ok) bin = 4;
+    else bin = ub <= 768 ? 2 : ub <= 3072 ? 3 : 4;
     const int p = atomic_add(&bc[bin], 1);
     lp[(i64)bin * rn + p] = (int)i;
   });
@@ -206,7 +308,7 @@ Csr spgemm(const Csr &A, const Csr &B) {
     tsz.alloc(hc[4] + 1); toff.alloc(hc[4] + 1);
     i64 *ts = tsz.p;
     const int *l4 = lp + 4 * (i64)rn;
-    parallel_for(hc[4], [=] DEV(i64 q) { i64 s = 4096; while (s < 2 * (i64)nd[l4[q]]) s <<= 1; ts[q] = s; });
+    parallel_for(hc[4], [=] DEV(i64 q) { i64 s = 256; while (s < 2 * (i64)nd[l4[q]]) s <<= 1; ts[q] = s; });
     const i64 total = exclusive_scan64(tsz.p, toff.p, hc[4]);
     gkeys.alloc(total); gvals.alloc(total);
   }
@@ -215,9 +317,11 @@ Csr spgemm(const Csr &A, const Csr &B) {
   CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
   static bool attr = false;
   if (!attr) {
-    CUDA_CHECK(cudaFuncSetAttribute((const void *)k_spgemm_block, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 12));
+    CUDA_CHECK(cudaFuncSetAttribute((const void *)k_spgemm_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_MAX * 8));
+    CUDA_CHECK(cudaFuncSetAttribute((const void *)k_spgemm_block_bitmap, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
     attr = true;
   }
+  const size_t bm_bytes = (size_t)((bcn + 31) / 32) * 8;
   Csr X;
   CUDA_CHECK(cudaEventRecord(e0, c.stream));
   for (int phase = 1; phase <= 2; phase++) {
@@ -231,13 +335,17 @@ Csr spgemm(const Csr &A, const Csr &B) {
       k_spgemm_tile<32, 256><<<(hc[1] + 7) / 8, 256, 0, c.stream>>>(phase, lp + rn, hc[1], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
       c.launches++; post_launch("spgemm_tile32");
     }
-    if (hc[2]) {
-      k_spgemm_block<<<hc[2], 128, 2048 * 12, c.stream>>>(phase, 2048, lp + 2 * (i64)rn, hc[2], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
-      c.launches++; post_launch("spgemm_block2k");
+    if (hc[2] && dense) {
+      k_spgemm_dense<<<hc[2], 256, (size_t)bcn * 8, c.stream>>>(phase, bcn, lp + 2 * (i64)rn, hc[2], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+      c.launches++; post_launch("spgemm_dense");
+    }
+    if (hc[2] && !dense) {
+      k_spgemm_block_bitmap<<<hc[2], 128, 2048 * 12 + bm_bytes, c.stream>>>(phase, 2048, bcn, lp + 2 * (i64)rn, hc[2], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+      c.launches++; post_launch("spgemm_bitmap2k");
     }
     if (hc[3]) {
-      k_spgemm_block<<<hc[3], 256, 16384 * 12, c.stream>>>(phase, 16384, lp + 3 * (i64)rn, hc[3], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
-      c.launches++; post_launch("spgemm_block16k");
+      k_spgemm_block_bitmap<<<hc[3], 256, 8192 * 12 + bm_bytes, c.stream>>>(phase, 8192, bcn, lp + 3 * (i64)rn, hc[3], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+      c.launches++; post_launch("spgemm_bitmap8k");
     }
     if (hc[4]) {
       k_spgemm_global<<<hc[4], 256, 0, c.stream>>>(phase, lp + 4 * (i64)rn, hc[4], toff.p, gkeys.p, gvals.p, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
