@@ -68,8 +68,20 @@ int amgb_solve_device(const amgb_hier *h, double *dx, const double *db);      /*
  * t[0]=total t[1]=build_csr t[2]=coarsen t[3]=smoother t[4]=lanczos t[5]=interpolation
  * t[6]=galerkin (host seconds, stream synchronised at stage ends)
  * t[7]=device seconds inside SpGEMM kernels  t[8]=their algorithmic bytes  t[9]=SpGEMM calls
- * t[10]=kernel launches  t[11]=host syncs */
-int amgb_timing(const amgb_hier *h, double t[12]);
+ * t[10]=kernel launches  t[11]=host syncs
+ * t[12]=CUDA-event seconds from the first to the last kernel of the setup  t[13..15] reserved */
+int amgb_timing(const amgb_hier *h, double t[16]);
+
+/* ---- arithmetic mode of the vector-length reductions (dot products, 2-norms) ----
+ * AMGB_REDUCE_SEQUENTIAL (default): summed left to right like the reference's vv_dot
+ *   (amg_setup.c:3193); the hierarchy is then bit-identical to the reference's.
+ * AMGB_REDUCE_TREE: fixed-shape parallel tree; deterministic and much faster, values agree to
+ *   rounding, but the reference algorithm's threshold decisions are sensitive to the last bit, so
+ *   C/F splits and patterns can differ from the reference's (DESIGN.md "Reduction order").
+ * The environment variable AMGB_REDUCE=tree|seq sets the initial mode. */
+enum { AMGB_REDUCE_TREE = 0, AMGB_REDUCE_SEQUENTIAL = 1 };
+int amgb_set_reduce_mode(int mode);
+int amgb_get_reduce_mode(void);
 
 /* ---- stage trace (debug): FNV-1a hashes of intermediate arrays, in stage order ---- */
 void amgb_trace_enable(int on);

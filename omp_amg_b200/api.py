@@ -52,6 +52,7 @@ def _declare(L):
     L.amgb_solve.argtypes = [vp, f64p, f64p]
     L.amgb_solve_device.argtypes = [vp, vp, vp]
     L.amgb_timing.argtypes = [vp, C.POINTER(C.c_double)]
+    L.amgb_set_reduce_mode.argtypes = [C.c_int]
     L.amgb_trace_enable.argtypes = [C.c_int]
     L.amgb_trace_enable.restype = None
     L.amgb_trace_get.argtypes = [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]
@@ -81,6 +82,15 @@ def lib(path=None):
                            "omp_amg_b200 has no CPU implementation" % _LIB_PATH)
         _LIB = _declare(C.CDLL(_LIB_PATH))
     return _LIB
+
+
+REDUCE_TREE, REDUCE_SEQUENTIAL = 0, 1
+
+
+def set_reduce_mode(mode, L=None):
+    """0: parallel tree (fast); 1: left-to-right like the reference (bit-identical results)."""
+    L = L or lib()
+    _check(L, L.amgb_set_reduce_mode(int(mode)))
 
 
 def build_info(L=None):
@@ -157,10 +167,10 @@ class Hierarchy:
         _check(self._L, self._L.amgb_solve_device(self._h, x_ptr, b_ptr))
 
     def timing(self):
-        t = (C.c_double * 12)()
+        t = (C.c_double * 16)()
         _check(self._L, self._L.amgb_timing(self._h, t))
         keys = ("total", "build_csr", "coarsen", "smoother", "lanczos", "interp", "galerkin",
-                "spgemm_device_s", "spgemm_bytes", "spgemm_calls", "launches", "syncs")
+                "spgemm_device_s", "spgemm_bytes", "spgemm_calls", "launches", "syncs", "device_total_s")
         return dict(zip(keys, list(t)))
 
     def free(self):

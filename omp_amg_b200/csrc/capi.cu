@@ -274,14 +274,22 @@ int amgb_solve(const amgb_hier *h, double *x, const double *b) {
   API_END
 }
 
-int amgb_timing(const amgb_hier *h, double t[12]) {
+int amgb_timing(const amgb_hier *h, double t[16]) {
   if (!h) return fail(-2, "null hierarchy");
   const StageTimes &s = h->H.t;
   t[0] = s.total; t[1] = s.build; t[2] = s.coarsen; t[3] = s.smoother; t[4] = s.lanczos;
   t[5] = s.interp; t[6] = s.galerkin; t[7] = s.spgemm; t[8] = (double)s.spgemm_bytes;
   t[9] = (double)s.spgemm_calls; t[10] = (double)h->H.launches; t[11] = (double)h->H.syncs;
+  t[12] = s.device_total; t[13] = t[14] = t[15] = 0;
   return 0;
 }
+
+int amgb_set_reduce_mode(int mode) {
+  if (mode != 0 && mode != 1) return fail(-2, "reduce mode must be 0 (tree) or 1 (sequential)");
+  ctx().reduce_seq = mode;
+  return 0;
+}
+int amgb_get_reduce_mode(void) { return ctx().reduce_seq; }
 
 void amgb_trace_enable(int on) { ctx().trace_on = on != 0; ctx().trace.clear(); }
 int amgb_trace_count(void) { return (int)ctx().trace.size(); }

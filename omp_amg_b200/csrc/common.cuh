@@ -58,6 +58,11 @@ struct Context {
 #endif
   i64 launches = 0;          // kernels launched by this library (bench.py "gpu_launches")
   i64 syncs = 0;             // host<->device synchronisations
+  // order of the vector-length reductions (dot products, 2-norms):
+  //   1  left to right, as the reference's vv_dot/array_op (amg_setup.c:3193,3309): one thread
+  //      carries the sum, so results are bit-identical to the reference
+  //   0  fixed 1024-chunk tree: fast, deterministic, but rounds differently from the reference
+  int reduce_seq = 1;
   bool trace_on = false;
   std::string trace_prefix;
   std::vector<TraceRec> trace;
@@ -211,13 +216,19 @@ i64 exclusive_scan64(const i64 *in, i64 *out, i64 n);
 double tree_sum(const double *v, i64 n);
 // sum_i a[i]*b[i] with the same tree (products rounded first)
 double tree_dot(const double *a, const double *b, i64 n);
-inline double tree_norm2(const double *a, i64 n) { return sqrt(tree_dot(a, a, n)); }
+// the same sums accumulated left to right by one thread (reference order)
+double seq_sum(const double *v, i64 n);
+double seq_dot(const double *a, const double *b, i64 n);
+// the reduction the context asks for
+inline double vdot(const double *a, const double *b, i64 n) { return ctx().reduce_seq ? seq_dot(a, b, n) : tree_dot(a, b, n); }
+inline double vsum(const double *a, i64 n) { return ctx().reduce_seq ? seq_sum(a, n) : tree_sum(a, n); }
+inline double vnorm2(const double *a, i64 n) { return sqrt(vdot(a, a, n)); }
 // largest value and the first index holding it (extr_op(max), amg_setup.c:3281)
 void max_first(const double *v, i64 n, double *val, i64 *idx);
 // number of non-zero flags
 i64 count_nonzero(const double *v, i64 n);
 
-// trace: FNV-1a of a device array, same tags and scheme as oracle/amg_oracle.c
+// trace: FNV-1a of a device array; the tests compare the tag/hash sequence with their checker
 void trace_dev(const char *tag, const void *dptr, size_t bytes);
 
 }  // namespace amgb

@@ -25,6 +25,7 @@ void ctx_init(int device) {
   if (e != cudaSuccess || ndev == 0)
     throw Error(-101, "omp_amg_b200: no CUDA device available (this library has no CPU path)");
   if (g_debug_sync < 0) { const char *e = getenv("AMGB_DEBUG_SYNC"); g_debug_sync = (e && *e && *e != '0') ? 1 : 0; }
+  { const char *e = getenv("AMGB_REDUCE"); if (e && !strcmp(e, "tree")) g_ctx.reduce_seq = 0; else if (e && !strcmp(e, "seq")) g_ctx.reduce_seq = 1; }
   if (device >= 0) CUDA_CHECK(cudaSetDevice(device));
   int dev = 0;
   CUDA_CHECK(cudaGetDevice(&dev));
@@ -181,6 +182,48 @@ double tree_dot(const double *a, const double *b, i64 n) {
   return tree_finish(part, nc);
 }
 
+// ---- left-to-right sum: thread 0 carries the running sum (one rounding per element, in index
+// order, exactly as the reference's loops); the other 31 warps stage the next chunk of products
+// in shared memory so that the chain never waits for HBM ----
+#define SEQ_CHUNK 2048
+__global__ void __launch_bounds__(1024) k_seq_dot(const double *a, const double *b, i64 n, double *out) {
+  __shared__ double buf[2][SEQ_CHUNK];
+  const int t = threadIdx.x;
+  const i64 nchunks = (n + SEQ_CHUNK - 1) / SEQ_CHUNK;
+  for (int j = t; j < SEQ_CHUNK && j < n; j += 1024) buf[0][j] = b ? __dmul_rn(a[j], b[j]) : a[j];
+  double r = 0;
+  for (i64 c = 0; c < nchunks; c++) {
+    __syncthreads();
+    const int cur = (int)(c & 1);
+    if (t >= 32) {
+      const i64 base = (c + 1) * SEQ_CHUNK;
+      for (i64 j = base + (t - 32); j < base + SEQ_CHUNK && j < n; j += 992)
+        buf[cur ^ 1][j - base] = b ? __dmul_rn(a[j], b[j]) : a[j];
+    } else if (t == 0) {
+      const i64 base = c * SEQ_CHUNK;
+      const int len = (int)((n - base < SEQ_CHUNK) ? (n - base) : SEQ_CHUNK);
+      const double *p = buf[cur];
+      int j = 0;
+      for (; j + 8 <= len; j += 8) {
+        const double p0 = p[j], p1 = p[j + 1], p2 = p[j + 2], p3 = p[j + 3], p4 = p[j + 4], p5 = p[j + 5],
+                     p6 = p[j + 6], p7 = p[j + 7];
+        r = __dadd_rn(r, p0); r = __dadd_rn(r, p1); r = __dadd_rn(r, p2); r = __dadd_rn(r, p3);
+        r = __dadd_rn(r, p4); r = __dadd_rn(r, p5); r = __dadd_rn(r, p6); r = __dadd_rn(r, p7);
+      }
+      for (; j < len; j++) r = __dadd_rn(r, p[j]);
+    }
+  }
+  if (t == 0) *out = r;
+}
+double seq_dot(const double *a, const double *b, i64 n) {
+  if (n <= 0) return 0.0;
+  Buf<double> out(1);
+  k_seq_dot<<<1, 1024, 0, g_ctx.stream>>>(a, b, n, out.p);
+  g_ctx.launches++; post_launch(__func__);
+  return out.get(0);
+}
+double seq_sum(const double *v, i64 n) { return seq_dot(v, nullptr, n); }
+
 // ---- max with first index ----
 struct MaxIdx { double v; i64 i; };
 __device__ __forceinline__ MaxIdx better(MaxIdx a, MaxIdx b) {
@@ -304,6 +347,8 @@ static double tree_host(const double *v, const double *b, i64 n) {
 }
 double tree_sum(const double *v, i64 n) { return tree_host(v, nullptr, n); }
 double tree_dot(const double *a, const double *b, i64 n) { return tree_host(a, b, n); }
+double seq_sum(const double *v, i64 n) { double r = 0; for (i64 i = 0; i < n; i++) r += v[i]; return r; }
+double seq_dot(const double *a, const double *b, i64 n) { double r = 0; for (i64 i = 0; i < n; i++) r += a[i] * b[i]; return r; }
 void max_first(const double *v, i64 n, double *val, i64 *idx) {
   if (n <= 0) throw Error(-3, "max_first on an empty vector");
   double m = v[0]; i64 k = 0;

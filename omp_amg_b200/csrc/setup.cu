@@ -122,8 +122,8 @@ int pcg(double *x, const Csr &A, double *r, const double *M, double tol, const d
   Buf<double> p(n), z(n), w(n), t(n);
   double *pp = p.p, *zp = z.p, *wp = w.p, *tp = t.p;
   parallel_for(n, [=] DEV(i64 i) { x[i] = 0.; pp[i] = 0.; zp[i] = M[i] * r[i]; tp[i] = M[i] * b[i]; });
-  double rho = tree_dot(r, zp, n);
-  const double rho_0 = tree_dot(tp, b, n);
+  double rho = vdot(r, zp, n);
+  const double rho_0 = vdot(tp, b, n);
   const double rho_stop = tol * tol * rho_0;
   const int nmax = n <= 100 ? n : 100;
   int k = 0;
@@ -133,7 +133,7 @@ int pcg(double *x, const Csr &A, double *r, const double *M, double tol, const d
     const double beta = rho / rho_old;
     parallel_for(n, [=] DEV(i64 i) { const double pb = pp[i] * beta; pp[i] = pb + zp[i]; });
     spmv(wp, 0, nullptr, 1, A, pp);
-    double alpha = tree_dot(pp, wp, n);
+    double alpha = vdot(pp, wp, n);
     alpha = rho / alpha;
     parallel_for(n, [=] DEV(i64 i) {
       const double pa = pp[i] * alpha;
@@ -144,7 +144,7 @@ int pcg(double *x, const Csr &A, double *r, const double *M, double tol, const d
       zp[i] = M[i] * rn;
     });
     rho_old = rho;
-    rho = tree_dot(r, zp, n);
+    rho = vdot(r, zp, n);
   }
   return k;
 }
@@ -161,7 +161,7 @@ int lanczos(double *lambda, const Csr &A, hostmath::GlibcRand &rng, int *iters) 
   trace_dev("lanczos.r0", r.p, sizeof(double) * (size_t)rn);
   double *l = lambda;
   double y[300], d[301], v[300];
-  double beta = tree_norm2(r.p, rn);
+  double beta = vnorm2(r.p, rn);
   double beta2 = beta * beta;
   beta = sqrt(beta2);
   int k = 0;
@@ -173,7 +173,7 @@ int lanczos(double *lambda, const Csr &A, hostmath::GlibcRand &rng, int *iters) 
     parallel_for(rn, [=] DEV(i64 i) {
       for (int j = ro[i]; j < ro[i + 1]; j++) if (col[j] == i) { ep[j] = ep[j] - 1.; break; }
     });
-    double fro = tree_norm2(e.p, A.nnz);
+    double fro = vnorm2(e.p, A.nnz);
     const double fro2 = fro * fro;
     fro = sqrt(fro2);
     if (fro < 1e-11) { l[0] = 1; l[1] = 1; y[0] = 0; y[1] = 0; k = 2; change = 0.0; }
@@ -187,7 +187,7 @@ int lanczos(double *lambda, const Csr &A, hostmath::GlibcRand &rng, int *iters) 
     const double ib = 1. / beta;
     parallel_for(rn, [=] DEV(i64 i) { qmp[i] = qp[i]; qp[i] = rp[i] * ib; });
     spmv(Ap, 0, nullptr, 1, A, qp);
-    const double alpha = tree_dot(qp, Ap, rn);
+    const double alpha = vdot(qp, Ap, rn);
     const double bt = beta;
     parallel_for(rn, [=] DEV(i64 i) {
       const double aq = qp[i] * alpha, bq = qmp[i] * bt;
@@ -205,7 +205,7 @@ int lanczos(double *lambda, const Csr &A, hostmath::GlibcRand &rng, int *iters) 
       hostmath::tdeig(l, y, d, v, k - 1);
       change = fabs(l0 - l[0]) + fabs(lkm2 - l[k - 1]);
     }
-    beta = tree_norm2(rp, rn);
+    beta = vnorm2(rp, rn);
     beta2 = beta * beta;
     beta = sqrt(beta2);
     if (beta == 0) break;
@@ -597,6 +597,11 @@ void setup(i64 nnz, const int *dAi, const int *dAj, const double *dAv, Hierarchy
   const double t_begin = now_s();
   double t0 = t_begin;
   spgemm_stats_reset();
+#ifndef AMGB_EMU
+  cudaEvent_t ev0, ev1;
+  CUDA_CHECK(cudaEventCreate(&ev0)); CUDA_CHECK(cudaEventCreate(&ev1));
+  CUDA_CHECK(cudaEventRecord(ev0, c.stream));
+#endif
   auto lap = [&](double &acc) { stream_sync(); const double t = now_s(); acc += t - t0; t0 = t; };
   Csr A = build_csr(nnz, dAi, dAj, dAv);
   lap(H.t.build);
@@ -715,8 +720,17 @@ void setup(i64 nnz, const int *dAi, const int *dAj, const double *dAv, Hierarchy
     lap(H.t.galerkin);
   }
   c.trace_prefix.clear();
+#ifndef AMGB_EMU
+  CUDA_CHECK(cudaEventRecord(ev1, c.stream));
+#endif
   stream_sync();
   H.t.total = now_s() - t_begin;
+#ifndef AMGB_EMU
+  { float ms = 0; CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1)); H.t.device_total = ms * 1e-3; }
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+#else
+  H.t.device_total = H.t.total;
+#endif
   spgemm_stats_get(&H.t.spgemm, &H.t.spgemm_bytes, &H.t.spgemm_calls);
   H.launches = c.launches - launches0;
   H.syncs = c.syncs - syncs0;

@@ -21,6 +21,7 @@ struct Level {
 
 struct StageTimes {    // host wall-clock with a stream sync at stage ends, seconds
   double build = 0, coarsen = 0, smoother = 0, lanczos = 0, interp = 0, galerkin = 0, total = 0;
+  double device_total = 0;   // CUDA-event time from the first to the last kernel of the setup
   double spgemm = 0;   // device time (CUDA events) inside the SpGEMM kernels
   i64 spgemm_bytes = 0;  // algorithmic bytes moved by those kernels
   i64 spgemm_calls = 0;

@@ -58,7 +58,7 @@ void vcycle_solve(const Hierarchy &H, double *x, const double *b) {
   const int n = H.n0;
   vcycle_level(H, 0, x, b);
   if (H.nullspace) {
-    const double s = tree_sum(x, n);
+    const double s = vsum(x, n);
     const double avg = (1 / (double)n) * s;
     parallel_for(n, [=] DEV(i64 i) { x[i] = x[i] - avg; });
   }

@@ -1,0 +1,195 @@
+"""CPU tests of the product's host side: the C ABI surface, the loud failure without a GPU,
+the host orchestration (through the host-emulation build of the same sources), the reference-
+format files, the crs_* mirror and the matrix generators."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from util import ROOT, EMU_SO, orc, amg, api, fetch, product_trace, first_trace_mismatch
+from omp_amg_b200 import matrices as M
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+HEADER = os.path.join(ROOT, "include", "omp_amg_b200.h")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.run(["make", "-j4", "-C", os.path.join(ROOT, "omp_amg_b200", "csrc"), "emu"], check=True,
+                   stdout=subprocess.DEVNULL)
+    L = api.lib(EMU_SO)
+    assert "emulation" in api.build_info(L)
+    return L
+
+
+@pytest.fixture(scope="module")
+def O():
+    orc.build(ref=False)
+    return orc.Oracle()
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:amgb|crs_amg)_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_cuda_library_exports_every_declared_symbol():
+    path = amg.lib_path()
+    if not os.path.exists(path):
+        subprocess.run(["make", "-j4", "-C", os.path.join(ROOT, "omp_amg_b200", "csrc")], check=True,
+                       stdout=subprocess.DEVNULL)
+    L = ctypes.CDLL(path)
+    syms = declared_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(L, s), "include/omp_amg_b200.h declares %s but the library does not export it" % s
+
+
+def test_cuda_library_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    L = amg.lib()
+    assert L.amgb_device_count() == 0
+    assert L.amgb_init(0) != 0
+    with pytest.raises(amg.AmgError, match="no CUDA device"):
+        amg.amg_setup(*M.poisson7(3))
+
+
+def test_product_package_never_touches_the_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, "omp_amg_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(root, f)).read()
+                assert "amg_oracle" not in txt and "import oracle" not in txt and "from oracle" not in txt, f
+
+
+CASES = [("dump", 0), ("poisson7", 6), ("poisson7", 11), ("poisson27", 6), ("aniso7", 9), ("sem_hex", 7)]
+
+
+@pytest.mark.parametrize("mode", [orc.SEQ, orc.TREE])
+@pytest.mark.parametrize("name,n", CASES)
+def test_host_orchestration_bit_identical_to_oracle(emu, O, name, n, mode):
+    """The host-emulation build runs the product's orchestration (same sources, kernels executed
+    as loops) and must agree with the oracle in every traced intermediate array, in both
+    reduction modes (sequential = the reference's order, tree = the fast mode)."""
+    mat = M.read_amgdmp(GOLDEN) if name == "dump" else M.by_name(name, n)
+    h = O.setup_raw(*mat, mode, trace=True)
+    want = O.fetch(h); twant = O.trace(); O.free(h)
+    api.set_reduce_mode(api.REDUCE_SEQUENTIAL if mode == orc.SEQ else api.REDUCE_TREE, L=emu)
+    emu.amgb_trace_enable(1)
+    try:
+        H = amg.amg_setup(*mat, L=emu)
+        tgot = product_trace(emu)
+    finally:
+        emu.amgb_trace_enable(0)
+        api.set_reduce_mode(api.REDUCE_SEQUENTIAL, L=emu)
+    assert first_trace_mismatch(tgot, twant) is None
+    assert orc.compare(fetch(H), want) == []
+
+
+def test_ragged_and_degenerate_inputs(emu, O):
+    # zeros in the COO list are dropped, empty rows/columns vanish (build_csr, amg_setup.c:3612)
+    Ai, Aj, Av = M.poisson7(4, 3, 2)
+    extra_i = np.array([30, 40], np.int32); extra_j = np.array([31, 40], np.int32)
+    Ai2 = np.concatenate([Ai, extra_i]); Aj2 = np.concatenate([Aj, extra_j]); Av2 = np.concatenate([Av, [0.0, 0.0]])
+    a = fetch(amg.amg_setup(Ai2, Aj2, Av2, L=emu))
+    b = O.setup(Ai, Aj, Av, orc.SEQ)
+    assert orc.compare(a, b) == []
+    # unsorted input gives the same hierarchy
+    perm = np.random.default_rng(0).permutation(len(Av))
+    c = fetch(amg.amg_setup(Ai[perm], Aj[perm], Av[perm], L=emu))
+    assert orc.compare(c, b) == []
+    # 1x1 and 2x2
+    one = fetch(amg.amg_setup(np.array([0], np.int32), np.array([0], np.int32), np.array([2.0]), L=emu))
+    assert one.nlevels == 1 and one.nullspace == 0
+    two = amg.amg_setup(np.array([0, 0, 1, 1], np.int32), np.array([0, 1, 0, 1], np.int32),
+                        np.array([2.0, -1.0, -1.0, 2.0]), L=emu)
+    assert orc.compare(fetch(two), O.setup(np.array([0, 0, 1, 1], np.int32), np.array([0, 1, 0, 1], np.int32),
+                                           np.array([2.0, -1.0, -1.0, 2.0]), orc.SEQ)) == []
+    # errors: duplicates, empty input
+    with pytest.raises(amg.AmgError, match="duplicate"):
+        amg.amg_setup(np.array([0, 0, 1], np.int32), np.array([0, 0, 1], np.int32), np.array([1.0, 1.0, 1.0]), L=emu)
+    with pytest.raises(amg.AmgError):
+        amg.amg_setup(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0), L=emu)
+
+
+def test_export_matches_reference_files(emu, tmp_path):
+    z = np.load(os.path.join(GOLDEN, "ref_dump.npz"))
+    H = amg.amg_setup_from_dump(GOLDEN, L=emu)
+    H.export(str(tmp_path))
+    for f in ("amg_W.dat", "amg_AfP.dat", "amg_Aff.dat", "amg.dat"):
+        got = np.fromfile(os.path.join(str(tmp_path), f)); want = z["file_" + f.replace(".", "_")]
+        assert got.shape == want.shape
+        assert np.array_equal(got, want), f      # sequential reductions: the files are identical
+
+
+def test_vcycle_matches_oracle_and_reduces_residual(emu, O):
+    mat = M.sem_hex(6)
+    H = amg.amg_setup(*mat, L=emu)
+    h = O.setup_raw(*mat, orc.SEQ)
+    n = H.level_info(0)["n"]
+    rng = np.random.default_rng(3)
+    b = rng.standard_normal(n); b -= b.mean()
+    x = H.solve(b); xo = O.solve(h, b)
+    O.free(h)
+    assert np.abs(x - xo).max() <= 1e-12 * np.abs(xo).max()
+    import scipy.sparse as sp
+    A = sp.coo_matrix((mat[2], (mat[0], mat[1]))).tocsr()
+    # one V-cycle as a preconditioner must contract the error of a few Richardson steps
+    r0 = np.linalg.norm(b)
+    xk = np.zeros(n)
+    for _ in range(8):
+        r = b - A @ xk; r -= r.mean()
+        xk += H.solve(r)
+    assert np.linalg.norm(b - A @ xk - (b - A @ xk).mean()) < 1e-3 * r0
+
+
+def test_crs_interface_mirrors_reference_test(emu):
+    """crs_test.c: the 2x2-element assembly with shared ids, null_space=1."""
+    A = np.array([2, -1, -1, 0, -1, 2, 0, -1, -1, 0, 2, -1, 0, -1, -1, 2], np.float64)
+    Ai = np.repeat(np.arange(4), 4).astype(np.uint32); Aj = np.tile(np.arange(4), 4).astype(np.uint32)
+    # two elements sharing an edge: local dofs of both elements in one call
+    ids = np.array([1, 2, 4, 5, 2, 3, 5, 6], np.uint64)
+    Ai2 = np.concatenate([Ai, Ai + 4]).astype(np.uint32); Aj2 = np.concatenate([Aj, Aj + 4]).astype(np.uint32)
+    A2 = np.concatenate([A, A])
+    d = amg.crs_setup(8, ids, 32, Ai2, Aj2, A2, 1, None, L=emu)
+    b = np.array([1.0, -1, 0.5, -0.5, 0, 0, 0, 0])
+    x = np.zeros(8)
+    amg.crs_solve(x, d, b)
+    # shared dofs get one value
+    assert x[1] == x[4] and x[3] == x[6]
+    assert abs(sum(x[[0, 1, 2, 3, 5, 7]])) < 1e-12     # mean projected out
+    amg.crs_stats(d)
+    amg.crs_free(d)
+    with pytest.raises(amg.AmgError):
+        amg.crs_setup(2, np.array([0, 0], np.uint64), 0, np.zeros(0, np.uint32), np.zeros(0, np.uint32),
+                      np.zeros(0), 0, None, L=emu)
+
+
+def test_matrix_generators():
+    Ai, Aj, Av = M.poisson7(5)
+    assert len(Av) == 125 * 7 - 6 * 25 and Av.sum() == 6 * 25
+    Ai, Aj, Av = M.poisson27(4)
+    assert (Av[Ai == Aj] == 26).all()
+    import scipy.sparse as sp
+    for gen in (lambda: M.aniso7(6), lambda: M.sem_hex(4)):
+        Ai, Aj, Av = gen()
+        A = sp.coo_matrix((Av, (Ai, Aj))).tocsr()
+        assert abs(A - A.T).max() < 1e-12
+        key = Ai.astype(np.int64) * (Ai.max() + 1) + Aj
+        assert (np.diff(key) > 0).all()
+    Ai, Aj, Av = M.sem_hex(4)
+    A = sp.coo_matrix((Av, (Ai, Aj))).tocsr()
+    assert np.abs(A @ np.ones(A.shape[0])).max() < 1e-12      # Neumann: constants in the null space
+
+
+def test_amgdmp_round_trip(tmp_path):
+    Ai, Aj, Av = M.poisson7(3)
+    M.write_amgdmp(str(tmp_path), Ai, Aj, Av)
+    Bi, Bj, Bv = M.read_amgdmp(str(tmp_path))
+    assert np.array_equal(Ai, Bi) and np.array_equal(Aj, Bj) and np.array_equal(Av, Bv)
