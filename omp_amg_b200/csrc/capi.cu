@@ -376,7 +376,7 @@ void crs_amg_solve(double *x, struct crs_data *d, double *b) {
 
 void crs_amg_stats(struct crs_data *d) {
   if (!d) return;
-  double t[12];
+  double t[16];
   amgb_timing(d->h, t);
   printf("AMG stats:\n  levels=%d rows=%u setup=%0.3e s (coarsen %0.3e, lanczos %0.3e, interp %0.3e, galerkin %0.3e)\n"
          "  kernel launches=%.0f  V-cycles=%lld\n",
