@@ -15,28 +15,30 @@ static double now_s() {
 // coarsen (:2737) with mat_max (:3535)
 // =======================================================================================
 // y[k] = max over rows i that hold k as a strong neighbour (|S_ik| >= tol*max_row_i, f[k]!=0)
-// of x[i].  The maximum is order-free, so rows scatter with an atomic max on ordered keys.
-void mat_max(double *y, const Csr &S, const double *f, const double *x, double tol,
-             Buf<unsigned long long> &keys) {
+// of x[i].  The reference scatters row by row; a maximum is order-free, so here every k gathers
+// from row k of S' (which lists exactly the pairs (i, S_ik)) -- no atomics, no init pass.
+void mat_max(double *y, const Csr &S, const Csr &St, const double *f, const double *x, double tol,
+             double *thr) {
   const int *ro = S.ro.p, *col = S.col.p;
   const double *a = S.a.p;
-  unsigned long long *kp = keys.p;
-  const unsigned long long lowest = dbl_key(-DBL_MAX);
-  parallel_for(S.cn, [=] DEV(i64 i) { kp[i] = lowest; });
   parallel_for(S.rn, [=] DEV(i64 i) {
-    const double xj = x[i];
     double amax = 0;
     for (int j = ro[i]; j < ro[i + 1]; j++)
       if (f[col[j]] != 0 && fabs(a[j]) > amax) amax = fabs(a[j]);
-    amax = amax * tol;
-    const unsigned long long kx = dbl_key(xj);
-    for (int j = ro[i]; j < ro[i + 1]; j++) {
-      const int k = col[j];
-      if (f[k] == 0 || fabs(a[j]) < amax) continue;
-      atomic_max_u64(&kp[k], kx);
-    }
+    thr[i] = amax * tol;
   });
-  parallel_for(S.cn, [=] DEV(i64 i) { y[i] = key_dbl(kp[i]); });
+  const int *tro = St.ro.p, *tcol = St.col.p;
+  const double *ta = St.a.p;
+  parallel_for(St.rn, [=] DEV(i64 k) {
+    double m = -DBL_MAX;
+    if (f[k] != 0)
+      for (int p = tro[k]; p < tro[k + 1]; p++) {
+        const int i = tcol[p];
+        if (fabs(ta[p]) < thr[i]) continue;
+        if (x[i] > m) m = x[i];
+      }
+    y[k] = m;
+  });
 }
 
 int coarsen(double *vc, const Csr &A, double ctol) {
@@ -53,8 +55,8 @@ int coarsen(double *vc, const Csr &A, double ctol) {
   sub_diag(S, D.p);
   trace_csr("coarsen.S", S);
 
-  Buf<double> vf(n), g(n), w1(n), w2(n), tmp(n), w(n), mask(n), m(n);
-  Buf<unsigned long long> keys(n);
+  Buf<double> vf(n), g(n), w1(n), w2(n), tmp(n), w(n), mask(n), m(n), thr(n);
+  Csr St = transpose(S);
   fill(vc, n, 0.);
   fill(vf.p, n, 1.);
   double *vfp = vf.p, *gp = g.p, *w1p = w1.p, *w2p = w2.p, *tp = tmp.p, *wp = w.p, *mk = mask.p, *mp = m.p;
@@ -90,14 +92,14 @@ int coarsen(double *vc, const Csr &A, double ctol) {
       mk[i] = mv;
       tp[i] = gp[i] * mv;
     });
-    mat_max(mp, S, vfp, tp, 0.1, keys);
+    mat_max(mp, S, St, vfp, tp, 0.1, thr.p);
     parallel_for(n, [=] DEV(i64 i) {
       const double d = gp[i] - mp[i];
       const double mv = (mk[i] != 0. && d >= 0.) ? 1. : 0.;
       mk[i] = mv;
       tp[i] = mv * ((double)i + 1.0);
     });
-    mat_max(mp, S, vfp, tp, 0.1, keys);
+    mat_max(mp, S, St, vfp, tp, 0.1, thr.p);
     parallel_for(n, [=] DEV(i64 i) {
       const double d = ((double)i + 1.0) - mp[i];
       const double mv = (mk[i] != 0. && d > 0.) ? 1. : 0.;
@@ -320,6 +322,90 @@ void solve_weights(Csr &W, Csr &W0, double *lam, const Csr &Wsk, const Csr &Af, 
   { double *dst = W.a.p; const double *src = Wskt.a.p; parallel_for(Wsk.nnz, [=] DEV(i64 e) { dst[e] = src[tp[e]]; }); }
 }
 
+#ifndef AMGB_EMU
+// One warp per column of R: the column is "bad" if w > thr and it still holds a non-zero (its
+// entries are non-negative, so "sum != 0" of the reference is "some entry != 0"); the warp then
+// finds the first row (ascending) with the largest R_ij * rs_i -- a max with smallest index, which
+// is order-free -- and removes that entry from R and R'.
+__global__ void __launch_bounds__(256) k_find_support_cols(int nc, const int *tro, const int *tcol, double *rtv,
+                                                           const double *rs, const double *w, double thr, int *alive,
+                                                           double *rv, const int *src, int *skel) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= nc) return;
+  const int lane = threadIdx.x & 31;
+  if (!(w[c] > thr)) return;
+  const int b = tro[c], e = tro[c + 1];
+  int any = 0;
+  double best = -DBL_MAX;
+  int arg = 0x7fffffff;
+  for (int p = b + lane; p < e; p += 32) {
+    const double v = rtv[p];
+    any |= (v != 0.);
+    if (!alive[p]) continue;
+    const double x = v * rs[tcol[p]];
+    if (x > best) { best = x; arg = p; }          // p ascending per lane: first maximum kept
+  }
+  any = __any_sync(0xffffffffu, any);
+  if (!any) return;
+  for (int off = 16; off >= 1; off >>= 1) {
+    const double ob = __shfl_down_sync(0xffffffffu, best, off);
+    const int oa = __shfl_down_sync(0xffffffffu, arg, off);
+    if (oa != 0x7fffffff && (arg == 0x7fffffff || ob > best || (ob == best && oa < arg))) { best = ob; arg = oa; }
+  }
+  if (lane == 0 && arg != 0x7fffffff) {
+    alive[arg] = 0; rtv[arg] = 0.0;
+    rv[src[arg]] = 0.0; skel[src[arg]] = 1;
+  }
+}
+
+// expand_support (:965-1114) for one bad row per warp: |X| ranked descending (stable: ties keep
+// column order), the shortest prefix whose running sum reaches half of the row sum is taken (the
+// two sums run left to right over the ranking, as sum()/cumsum() do), and the chosen columns are
+// put back in ascending order.  Scratch: the row's own storage in X plus a same-sized buffer.
+__global__ void __launch_bounds__(256) k_expand_rows(int nf, const double *badrow, const int *xro, int *xcol,
+                                                     double *xa, int *tcol, double *tval, int *take) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= nf) return;
+  const int lane = threadIdx.x & 31;
+  if (badrow[i] == 0.) { if (lane == 0) take[i] = 0; return; }
+  const int b = xro[i], len = xro[i + 1] - b;
+  int *c = xcol + b, *tc = tcol + b;
+  double *v = xa + b, *tv = tval + b;
+  for (int k = lane; k < len; k += 32) v[k] = fabs(v[k]);
+  __syncwarp();
+  for (int k = lane; k < len; k += 32) {           // rank = #larger + #equal before it
+    const double x = v[k];
+    int r = 0;
+    for (int f = 0; f < len; f++) { const double y = v[f]; r += (y > x) || (y == x && f < k); }
+    tv[r] = x; tc[r] = c[k];
+  }
+  __syncwarp();
+  int t = 0;
+  if (lane == 0) {
+    double tot = 0.0;
+    for (int k = 0; k < len; k++) if (tv[k] != 0.) tot = tot + tv[k];
+    const double half = tot * 0.5;
+    int below = 0;
+    double cs = 0.0;
+    for (int k = 0; k < len; k++) {
+      if (tv[k] != 0.) cs = cs + tv[k];
+      const double s = (half != 0.) ? (1. * cs + (-1.) * half) : (1. * cs);
+      if (s < 0.) below++;
+    }
+    t = below + 1;
+    if (t > len) t = len;
+    take[i] = t;
+  }
+  t = __shfl_sync(0xffffffffu, t, 0);
+  for (int k = lane; k < t; k += 32) {             // chosen columns back in ascending order
+    const int x = tc[k];
+    int r = 0;
+    for (int f = 0; f < t; f++) r += (tc[f] < x);
+    c[r] = x;
+  }
+}
+#endif
+
 // find_support (:1260).  Entries leave R one per bad column and round; here they are zeroed and
 // flagged dead instead of compacting R and its transpose every round (a zero adds nothing to any
 // of the sums involved, so all vectors are bit-identical).
@@ -351,6 +437,7 @@ Csr find_support(const Csr &R, double goal) {
     if (nf <= 1) break;   // the reference writes row index 1 here and never terminates
     while (mv <= (1 + theta) * goal) theta = theta / 2.;
     const double thr = (1 + theta) * goal;
+#ifdef AMGB_EMU
     parallel_for(nc, [=] DEV(i64 c) {
       double sum = 0.0;
       for (int p = tro[c]; p < tro[c + 1]; p++) sum = sum + rtv[p];
@@ -366,6 +453,13 @@ Csr find_support(const Csr &R, double goal) {
       alp[arg] = 0; rtv[arg] = 0.0;
       rvp[srcp[arg]] = 0.0; skp[srcp[arg]] = 1;
     });
+#else
+    {
+      Context &cx = ctx();
+      k_find_support_cols<<<(nc + 7) / 8, 256, 0, cx.stream>>>(nc, tro, tcol, rtv, rsp, wp, thr, alp, rvp, srcp, skp);
+      cx.launches++; post_launch("find_support_cols");
+    }
+#endif
     if (++guard > 100000) throw Error(-8, "find_support: no convergence");
   }
   // Skel = sparse(skel_i, skel_j, 1): the flagged entries, in place
@@ -414,6 +508,7 @@ Csr expand_support(const Csr &Wsk, const Csr &R, const Csr &R0, double gamma) {
   const int *xro = X.ro.p;
   int *xcol = X.col.p, *tk = take.p;
   double *xa = X.a.p;
+#ifdef AMGB_EMU
   parallel_for(nf, [=] DEV(i64 i) {
     if (br[i] == 0.) { tk[i] = 0; return; }
     const int b = xro[i], len = xro[i + 1] - b;
@@ -446,6 +541,15 @@ Csr expand_support(const Csr &Wsk, const Csr &R, const Csr &R0, double gamma) {
     }
     tk[i] = t;
   });
+#else
+  {
+    Buf<int> tcolb(X.nnz);
+    Buf<double> tvalb(X.nnz);
+    Context &cx = ctx();
+    k_expand_rows<<<(nf + 7) / 8, 256, 0, cx.stream>>>(nf, br, xro, xcol, xa, tcolb.p, tvalb.p, tk);
+    cx.launches++; post_launch("expand_rows");
+  }
+#endif
   Buf<int> nro2(nf + 1);
   const i64 nn = exclusive_scan(take.p, nro2.p, nf);
   Csr N(nf, nc, nn);

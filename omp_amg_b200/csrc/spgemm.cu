@@ -177,7 +177,8 @@ __device__ __forceinline__ int block_excl_scan(int v, int *tmp, int *total) {
 // Dense accumulator: when B has few columns the whole row of X fits in shared memory as a dense
 // array; no hashing and no sorting, the columns come out in order.  Untouched and exactly
 // cancelled entries are both 0.0 and both dropped, which is what mxm does.
-__global__ void __launch_bounds__(256) k_spgemm_dense(int phase, int cn, const int *list, int nlist,
+__global__ void __launch_bounds__(256) k_spgemm_dense(int phase, const int *cminv, const int *spanv,
+                                                      const int *list, int nlist,
                                                       const int *aro, const int *acol, const double *aa,
                                                       const int *bro, const int *bcol, const double *ba, int *cnt,
                                                       const int *xro, int *xcol, double *xa) {
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(256) k_spgemm_dense(int phase, int cn, const i
   __shared__ int stotal;
   if ((int)blockIdx.x >= nlist) return;
   const int i = list[blockIdx.x];
+  const int cmin = cminv[i], cn = spanv[i];     // the row only touches columns [cmin, cmin+cn)
   const int t = threadIdx.x, T = blockDim.x;
   for (int c = t; c < cn; c += T) acc[c] = 0.0;
   __syncthreads();
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(256) k_spgemm_dense(int phase, int cn, const i
     const int k = acol[ja];
     const double av = aa[ja];
     const int be = bro[k + 1];
-    for (int jb = bro[k] + t; jb < be; jb += T) { const int c = bcol[jb]; acc[c] = acc[c] + ba[jb] * av; }
+    for (int jb = bro[k] + t; jb < be; jb += T) { const int c = bcol[jb] - cmin; acc[c] = acc[c] + ba[jb] * av; }
     __syncthreads();
   }
   const int seg = (cn + T - 1) / T;
@@ -203,33 +205,44 @@ __global__ void __launch_bounds__(256) k_spgemm_dense(int phase, int cn, const i
   const int off = block_excl_scan(mine, stmp, &stotal);
   if (phase == 1) { if (t == 0) cnt[i] = stotal; return; }
   int p = xro[i] + off;
-  for (int c = c0; c < c1; c++) if (acc[c] != 0.0) { xcol[p] = c; xa[p] = acc[c]; p++; }
+  for (int c = c0; c < c1; c++) if (acc[c] != 0.0) { xcol[p] = c + cmin; xa[p] = acc[c]; p++; }
 }
 
-// Hash table in shared memory plus a bitmap of the surviving columns: the rank of a column is
-// the number of set bits below it, so the row is written in column order without sorting.
-__global__ void __launch_bounds__(256) k_spgemm_block_bitmap(int phase, int HS, int cn, const int *list, int nlist,
-                                                             const int *aro, const int *acol, const double *aa,
-                                                             const int *bro, const int *bcol, const double *ba,
-                                                             int *cnt, const int *xro, int *xcol, double *xa) {
+// Hash table (shared memory, or HBM for rows that do not fit) plus a bitmap over the row's column
+// span in shared memory: the rank of a column is the number of set bits below it, so the row is
+// written in column order without sorting.
+__global__ void __launch_bounds__(256) k_spgemm_bitmap(int phase, int HS_smem, int maxwords, const int *cminv,
+                                                       const int *spanv, const int *list, int nlist,
+                                                       const i64 *toff, int *gkeys, double *gvals,
+                                                       const int *aro, const int *acol, const double *aa,
+                                                       const int *bro, const int *bcol, const double *ba,
+                                                       int *cnt, const int *xro, int *xcol, double *xa) {
   extern __shared__ double dsm[];
   __shared__ int sred;
   __shared__ int stmp[256];
-  double *svals = dsm;
-  int *skeys = (int *)(dsm + HS);
-  unsigned *bits = (unsigned *)(skeys + HS);
-  const int nw = (cn + 31) / 32;
-  int *wpre = (int *)(bits + nw);
   if ((int)blockIdx.x >= nlist) return;
   const int i = list[blockIdx.x];
+  int HS;
+  double *svals;
+  int *skeys;
+  unsigned *bits;
+  if (HS_smem > 0) {
+    HS = HS_smem; svals = dsm; skeys = (int *)(dsm + HS); bits = (unsigned *)(skeys + HS);
+  } else {
+    const i64 base = toff[blockIdx.x];
+    HS = (int)(toff[blockIdx.x + 1] - base); svals = gvals + base; skeys = gkeys + base; bits = (unsigned *)dsm;
+  }
+  int *wpre = (int *)(bits + maxwords);
   BlockGroup g;
   accumulate_row(g, i, aro, acol, aa, bro, bcol, ba, skeys, svals, HS);
   const int n = drop_zeros_count(g, skeys, svals, HS, &sred);
   if (phase == 1) { if (threadIdx.x == 0) cnt[i] = n; return; }
+  const int cmin = cminv[i];
+  const int nw = (spanv[i] + 31) / 32;
   const int t = threadIdx.x, T = blockDim.x;
   for (int w = t; w < nw; w += T) bits[w] = 0u;
   __syncthreads();
-  for (int h = t; h < HS; h += T) { const int c = skeys[h]; if (c != EMPTY) atomicOr(&bits[c >> 5], 1u << (c & 31)); }
+  for (int h = t; h < HS; h += T) { const int c = skeys[h]; if (c != EMPTY) { const int d = c - cmin; atomicOr(&bits[d >> 5], 1u << (d & 31)); } }
   __syncthreads();
   const int seg = (nw + T - 1) / T;
   const int w0 = t * seg, w1 = min(nw, w0 + seg);
@@ -242,7 +255,8 @@ __global__ void __launch_bounds__(256) k_spgemm_block_bitmap(int phase, int HS, 
   for (int h = t; h < HS; h += T) {
     const int c = skeys[h];
     if (c == EMPTY) continue;
-    const int rank = wpre[c >> 5] + __popc(bits[c >> 5] & ((1u << (c & 31)) - 1u));
+    const int d = c - cmin;
+    const int rank = wpre[d >> 5] + __popc(bits[d >> 5] & ((1u << (d & 31)) - 1u));
     xcol[base + rank] = c; xa[base + rank] = svals[h];
   }
 }
@@ -272,45 +286,62 @@ Csr spgemm(const Csr &A, const Csr &B) {
   if (rn == 0) { Csr X(0, B.cn, 0); X.ro.zero(); return X; }
   const int *aro = A.ro.p, *acol = A.col.p, *bro = B.ro.p, *bcol = B.col.p;
   const double *aa = A.a.p, *ba = B.a.p;
-  // bins by the row's bound on distinct columns: min(sum of B row lengths, columns of B)
-  //   0: <=24   8-thread tiles, 64-slot tables        1: <=96  warps, 256-slot tables
-  //   rows above that: dense shared-memory accumulator if B has <= DENSE_MAX columns, else
-  //   2: <=768  block, 2048 slots + bitmap   3: <=3072 block, 8192 slots + bitmap
-  //   4: anything else: block, table in HBM, bitonic sort
-  constexpr int NB = 5;
+  // Per row: need = min(sum of B row lengths, columns of B) bounds the distinct columns;
+  // [cmin, cmin+span) is the column range the row can touch (B rows are sorted, so it comes from
+  // their first and last entries).  Bins:
+  //   0  need <= 24                 8-thread tiles, 64-slot hash tables in shared memory
+  //   1  need <= 96                 warps, 256-slot tables
+  //   2  span <= DENSE_MAX          block, dense accumulator over the span in shared memory
+  //   3  need <= 768                block, 2048-slot table + bitmap over the span
+  //   4  need <= 3072               block, 8192-slot table + bitmap over the span
+  //   5  span <= 800k               block, table in HBM + bitmap over the span in shared memory
+  //   6  anything else              block, table in HBM, bitonic sort
+  constexpr int NB = 7;
   constexpr int DENSE_MAX = 24576;
+  constexpr int BM3_SPAN = 700000, BM4_SPAN = 400000, BM5_SPAN = 800000;   // bitmap = span/4 bytes
   const int bcn = B.cn;
-  const bool dense = bcn <= DENSE_MAX;
-  const bool bitmap_ok = ((i64)(bcn + 31) / 32) * 8 + 8192 * 12 <= 200 * 1024;
-  Buf<int> lists((i64)NB * rn), bcnt(NB), need(rn);
-  bcnt.zero();
-  int *lp = lists.p, *bc = bcnt.p, *nd = need.p;
+  Buf<int> lists((i64)NB * rn), bcnt(NB), need(rn), cminv(rn), spanv(rn), maxspan(NB);
+  bcnt.zero(); maxspan.zero();
+  int *lp = lists.p, *bc = bcnt.p, *nd = need.p, *cmv = cminv.p, *spv = spanv.p, *mxs = maxspan.p;
   parallel_for(rn, [=] DEV(i64 i) {
     i64 ub = 0;
-    for (int ja = aro[i]; ja < aro[i + 1]; ja++) ub += bro[acol[ja] + 1] - bro[acol[ja]];
+    int lo = 0x7fffffff, hi = -1;
+    for (int ja = aro[i]; ja < aro[i + 1]; ja++) {
+      const int k = acol[ja], b0 = bro[k], b1 = bro[k + 1];
+      ub += b1 - b0;
+      if (b1 > b0) { const int f = bcol[b0], l = bcol[b1 - 1]; if (f < lo) lo = f; if (l > hi) hi = l; }
+    }
     if (ub > bcn) ub = bcn;
-    nd[i] = (int)ub;
+    const int span = hi >= lo ? hi - lo + 1 : 0;
+    nd[i] = (int)ub; cmv[i] = hi >= lo ? lo : 0; spv[i] = span;
     int bin;
     if (ub <= 24) bin = 0;
     else if (ub <= 96) bin = 1;
-    else if (dense) bin = 2;
-    else if (!bitmap_ok) bin = 4;
-    else bin = ub <= 768 ? 2 : ub <= 3072 ? 3 : 4;
+    else if (span <= DENSE_MAX) bin = 2;
+    else if (ub <= 768 && span <= BM3_SPAN) bin = 3;
+    else if (ub <= 3072 && span <= BM4_SPAN) bin = 4;
+    else if (span <= BM5_SPAN) bin = 5;
+    else bin = 6;
     const int p = atomic_add(&bc[bin], 1);
     lp[(i64)bin * rn + p] = (int)i;
+    atomic_max_i32(&mxs[bin], span);
   });
   std::vector<int> hc = bcnt.download();
-  // rows of the last bin get tables in HBM
-  Buf<i64> tsz, toff;
-  Buf<int> gkeys;
-  Buf<double> gvals;
-  if (hc[4]) {
-    tsz.alloc(hc[4] + 1); toff.alloc(hc[4] + 1);
+  std::vector<int> hms = maxspan.download();
+  // rows of bins 5 and 6 get tables in HBM
+  Buf<i64> tsz5, toff5, tsz6, toff6;
+  Buf<int> gkeys5, gkeys6;
+  Buf<double> gvals5, gvals6;
+  for (int bin = 5; bin <= 6; bin++) {
+    if (!hc[bin]) continue;
+    Buf<i64> &tsz = bin == 5 ? tsz5 : tsz6, &toff = bin == 5 ? toff5 : toff6;
+    tsz.alloc(hc[bin] + 1); toff.alloc(hc[bin] + 1);
     i64 *ts = tsz.p;
-    const int *l4 = lp + 4 * (i64)rn;
-    parallel_for(hc[4], [=] DEV(i64 q) { i64 s = 256; while (s < 2 * (i64)nd[l4[q]]) s <<= 1; ts[q] = s; });
-    const i64 total = exclusive_scan64(tsz.p, toff.p, hc[4]);
-    gkeys.alloc(total); gvals.alloc(total);
+    const int *lb = lp + bin * (i64)rn;
+    parallel_for(hc[bin], [=] DEV(i64 q) { i64 s = 256; while (s < 2 * (i64)nd[lb[q]]) s <<= 1; ts[q] = s; });
+    const i64 total = exclusive_scan64(tsz.p, toff.p, hc[bin]);
+    (bin == 5 ? gkeys5 : gkeys6).alloc(total);
+    (bin == 5 ? gvals5 : gvals6).alloc(total);
   }
   Buf<int> cnt(rn + 1), xro(rn + 1);
   cudaEvent_t e0, e1;
@@ -318,10 +349,10 @@ Csr spgemm(const Csr &A, const Csr &B) {
   static bool attr = false;
   if (!attr) {
     CUDA_CHECK(cudaFuncSetAttribute((const void *)k_spgemm_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_MAX * 8));
-    CUDA_CHECK(cudaFuncSetAttribute((const void *)k_spgemm_block_bitmap, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute((const void *)k_spgemm_bitmap, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
     attr = true;
   }
-  const size_t bm_bytes = (size_t)((bcn + 31) / 32) * 8;
+  auto words = [](int span) { return (span + 31) / 32; };
   Csr X;
   CUDA_CHECK(cudaEventRecord(e0, c.stream));
   for (int phase = 1; phase <= 2; phase++) {
@@ -335,20 +366,27 @@ Csr spgemm(const Csr &A, const Csr &B) {
       k_spgemm_tile<32, 256><<<(hc[1] + 7) / 8, 256, 0, c.stream>>>(phase, lp + rn, hc[1], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
       c.launches++; post_launch("spgemm_tile32");
     }
-    if (hc[2] && dense) {
-      k_spgemm_dense<<<hc[2], 256, (size_t)bcn * 8, c.stream>>>(phase, bcn, lp + 2 * (i64)rn, hc[2], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+    if (hc[2]) {
+      k_spgemm_dense<<<hc[2], 256, (size_t)(hms[2] > 0 ? hms[2] : 1) * 8, c.stream>>>(phase, cmv, spv, lp + 2 * (i64)rn, hc[2], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
       c.launches++; post_launch("spgemm_dense");
     }
-    if (hc[2] && !dense) {
-      k_spgemm_block_bitmap<<<hc[2], 128, 2048 * 12 + bm_bytes, c.stream>>>(phase, 2048, bcn, lp + 2 * (i64)rn, hc[2], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+    if (hc[3]) {
+      const int mw = words(hms[3]);
+      k_spgemm_bitmap<<<hc[3], 128, 2048 * 12 + (size_t)mw * 8, c.stream>>>(phase, 2048, mw, cmv, spv, lp + 3 * (i64)rn, hc[3], nullptr, nullptr, nullptr, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
       c.launches++; post_launch("spgemm_bitmap2k");
     }
-    if (hc[3]) {
-      k_spgemm_block_bitmap<<<hc[3], 256, 8192 * 12 + bm_bytes, c.stream>>>(phase, 8192, bcn, lp + 3 * (i64)rn, hc[3], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+    if (hc[4]) {
+      const int mw = words(hms[4]);
+      k_spgemm_bitmap<<<hc[4], 256, 8192 * 12 + (size_t)mw * 8, c.stream>>>(phase, 8192, mw, cmv, spv, lp + 4 * (i64)rn, hc[4], nullptr, nullptr, nullptr, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
       c.launches++; post_launch("spgemm_bitmap8k");
     }
-    if (hc[4]) {
-      k_spgemm_global<<<hc[4], 256, 0, c.stream>>>(phase, lp + 4 * (i64)rn, hc[4], toff.p, gkeys.p, gvals.p, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+    if (hc[5]) {
+      const int mw = words(hms[5]);
+      k_spgemm_bitmap<<<hc[5], 256, (size_t)mw * 8 + 16, c.stream>>>(phase, 0, mw, cmv, spv, lp + 5 * (i64)rn, hc[5], toff5.p, gkeys5.p, gvals5.p, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+      c.launches++; post_launch("spgemm_bitmap_hbm");
+    }
+    if (hc[6]) {
+      k_spgemm_global<<<hc[6], 256, 0, c.stream>>>(phase, lp + 6 * (i64)rn, hc[6], toff6.p, gkeys6.p, gvals6.p, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
       c.launches++; post_launch("spgemm_global");
     }
     if (phase == 1) {
