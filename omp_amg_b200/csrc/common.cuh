@@ -228,6 +228,15 @@ void max_first(const double *v, i64 n, double *val, i64 *idx);
 // number of non-zero flags
 i64 count_nonzero(const double *v, i64 n);
 
+// optional sub-stage profile (AMGB_STAGE_LOG=1): wall time with a stream sync at scope exit,
+// accumulated by name and printed at the end of setup().  Off by default (no syncs added).
+struct StageTimer {
+  const char *name; double t0; bool on;
+  explicit StageTimer(const char *n);
+  ~StageTimer();
+};
+void stage_report();
+
 // trace: FNV-1a of a device array; the tests compare the tag/hash sequence with their checker
 void trace_dev(const char *tag, const void *dptr, size_t bytes);
 

@@ -1,5 +1,8 @@
 // runtime.cu -- context, stream-ordered memory, prefix scans, deterministic reductions.
 #include "common.cuh"
+#include <algorithm>
+#include <chrono>
+#include <map>
 
 namespace amgb {
 
@@ -357,6 +360,32 @@ void max_first(const double *v, i64 n, double *val, i64 *idx) {
 }
 i64 count_nonzero(const double *v, i64 n) { i64 c = 0; for (i64 i = 0; i < n; i++) c += (v[i] != 0.0); return c; }
 #endif
+
+// ---- sub-stage profile ----
+static std::map<std::string, std::pair<double, long>> g_stage;
+static int g_stage_on = -1;
+static double wall_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+StageTimer::StageTimer(const char *n) : name(n), t0(0), on(false) {
+  if (g_stage_on < 0) { const char *e = getenv("AMGB_STAGE_LOG"); g_stage_on = (e && *e && *e != '0') ? 1 : 0; }
+  on = g_stage_on > 0;
+  if (on) { stream_sync(); t0 = wall_now(); }
+}
+StageTimer::~StageTimer() {
+  if (!on) return;
+  try { stream_sync(); } catch (...) {}
+  auto &r = g_stage[name];
+  r.first += wall_now() - t0; r.second++;
+}
+void stage_report() {
+  if (g_stage_on <= 0) return;
+  std::vector<std::pair<double, std::string>> v;
+  for (auto &kv : g_stage) v.push_back({kv.second.first, kv.first});
+  std::sort(v.begin(), v.end());
+  fprintf(stderr, "---- stage profile (inclusive, synchronised) ----\n");
+  for (auto it = v.rbegin(); it != v.rend(); ++it)
+    fprintf(stderr, "%-28s %10.3f ms  calls %ld\n", it->second.c_str(), it->first * 1e3, g_stage[it->second].second);
+  g_stage.clear();
+}
 
 // ---- trace ----
 static uint64_t fnv1a(const void *p, size_t n) {

@@ -42,6 +42,7 @@ void mat_max(double *y, const Csr &S, const Csr &St, const double *f, const doub
 }
 
 int coarsen(double *vc, const Csr &A, double ctol) {
+  StageTimer st_("coarsen");
   const int n = A.cn;
   int rounds = 0;
   Buf<double> D(n);
@@ -120,6 +121,7 @@ int coarsen(double *vc, const Csr &A, double ctol) {
 // pcg (:2242)
 // =======================================================================================
 int pcg(double *x, const Csr &A, double *r, const double *M, double tol, const double *b) {
+  StageTimer st_("pcg");
   const int n = A.rn;
   Buf<double> p(n), z(n), w(n), t(n);
   double *pp = p.p, *zp = z.p, *wp = w.p, *tp = t.p;
@@ -155,6 +157,7 @@ int pcg(double *x, const Csr &A, double *r, const double *M, double tol, const d
 // lanczos (:2435); tdeig on the host (k x k, k <= 299)
 // =======================================================================================
 int lanczos(double *lambda, const Csr &A, hostmath::GlibcRand &rng, int *iters) {
+  StageTimer st_("lanczos");
   const int rn = A.rn, kmax = 299;
   std::vector<double> hr((size_t)rn);
   for (int i = 0; i < rn; i++) hr[(size_t)i] = rng.uniform();
@@ -255,12 +258,13 @@ Csr min_skel(const Csr &R) {
 // solve_constraint (:1499)
 void solve_constraint(double *lam, const Csr &Wsk, SkelCache &sk, const Csr &W0, const double *alpha,
                       const double *u, const double *v, double tol) {
+  StageTimer st_("solve_constraint(incl pcg)");
   const int nf = Wsk.rn, nc = Wsk.cn;
   Buf<double> au2(nc);
   { double *p = au2.p; parallel_for(nc, [=] DEV(i64 i) { const double uu = u[i] * u[i]; p[i] = uu * alpha[i]; }); }
-  if (!sk.has_qq) { form_qq(sk.qq, sk.qs, sk.Wskt); sk.has_qq = true; }
+  if (!sk.has_qq) { StageTimer t_("sc.form_qq"); form_qq(sk.qq, sk.qs, sk.Wskt); sk.has_qq = true; }
   Csr S = sk.Spat.clone();
-  lmop_accumulate(S, sk.qq, au2.p, sk.Wskt, Wsk, sk.tpos.p);
+  { StageTimer t_("sc.lmop_acc"); lmop_accumulate(S, sk.qq, au2.p, sk.Wskt, Wsk, sk.tpos.p); }
   trace_csr("sc.S", S);
   Buf<double> resid(nf), d(nf), keep(nf);
   spmv(resid.p, 1.0, v, -1.0, W0, u);
@@ -305,19 +309,19 @@ void solve_weights(Csr &W, Csr &W0, double *lam, const Csr &Wsk, const Csr &Af, 
   { double *p = au.p; parallel_for(nc, [=] DEV(i64 i) { p[i] = alpha[i] * u[i]; }); }
   zeros.zero();
   if (!sk.valid) {       // the basis Q of every coarse column depends on the skeleton and Af only
-    sk.Wskt = transpose(Wsk, &sk.tpos);
-    sk.Spat = spgemm(Wsk, sk.Wskt);   // pattern of W_skel*W_skel' (:1513), while Wskt holds 0/1
-    build_q_store(sk.qs, sk.Wskt, Af);
+    { StageTimer t_("sw.transpose"); sk.Wskt = transpose(Wsk, &sk.tpos); }
+    { StageTimer t_("sw.spgemm_S"); sk.Spat = spgemm(Wsk, sk.Wskt); }  // pattern of W_skel*W_skel' (:1513), while Wskt holds 0/1
+    { StageTimer t_("sw.build_q"); build_q_store(sk.qs, sk.Wskt, Af); }
     sk.valid = true; sk.has_qq = false; sk.has_S = true;
   }
   Csr &Wskt = sk.Wskt;
   const int *tp = sk.tpos.p;
-  apply_q(sk.qs, Wskt, Armt, au.p, zeros.p);          // interp(W0t, Af, -Ar', au, 0) :1467
+  { StageTimer t_("sw.apply_q"); apply_q(sk.qs, Wskt, Armt, au.p, zeros.p); }   // interp(W0t, Af, -Ar', au, 0) :1467
   W0 = Wsk.clone();
   { double *dst = W0.a.p; const double *src = Wskt.a.p; parallel_for(Wsk.nnz, [=] DEV(i64 e) { dst[e] = src[tp[e]]; }); }
   solve_constraint(lam, Wsk, sk, W0, alpha, u, v, tol);
   trace_dev("sw.lam", lam, sizeof(double) * (size_t)nf);
-  apply_q(sk.qs, Wskt, Armt, au.p, lam);              // interp(Wt, Af, -Ar', au, lam) :1482
+  { StageTimer t_("sw.apply_q"); apply_q(sk.qs, Wskt, Armt, au.p, lam); }       // interp(Wt, Af, -Ar', au, lam) :1482
   W = Wsk.clone();
   { double *dst = W.a.p; const double *src = Wskt.a.p; parallel_for(Wsk.nnz, [=] DEV(i64 e) { dst[e] = src[tp[e]]; }); }
 }
@@ -410,6 +414,7 @@ __global__ void __launch_bounds__(256) k_expand_rows(int nf, const double *badro
 // flagged dead instead of compacting R and its transpose every round (a zero adds nothing to any
 // of the sums involved, so all vectors are bit-identical).
 Csr find_support(const Csr &R, double goal) {
+  StageTimer st_("find_support");
   const int nf = R.rn, nc = R.cn;
   Buf<int> tpos;
   Csr Rt = transpose(R, &tpos);
@@ -482,6 +487,7 @@ Csr find_support(const Csr &R, double goal) {
 
 // expand_support (:907)
 Csr expand_support(const Csr &Wsk, const Csr &R, const Csr &R0, double gamma) {
+  StageTimer st_("expand_support(incl find)");
   const int nf = Wsk.rn, nc = Wsk.cn;
   Csr M = find_support(R, gamma);
   trace_csr("es.M", M);
@@ -613,8 +619,8 @@ Csr interpolation(const Csr &Af, const Csr &Ac, const Csr &Ar, double gamma2, do
     trace_csr("ip.W0", W0);
     trace_csr("ip.Wtmp", Wt);
     Csr R0, R;
-    { Csr AfW = spgemm(Af, W0); R0 = mpm(1., AfW, 1., Ar); }
-    { Csr AfW = spgemm(Af, Wt); R = mpm(1., AfW, 1., Ar); }
+    { StageTimer t_("ip.AfW_spgemm+mpm"); Csr AfW = spgemm(Af, W0); R0 = mpm(1., AfW, 1., Ar); }
+    { StageTimer t_("ip.AfW_spgemm+mpm"); Csr AfW = spgemm(Af, Wt); R = mpm(1., AfW, 1., Ar); }
     {
       Csr Arr = mpm(1.0, R, 1.0, Ar);
       Csr ArW = mxmpoint(Wt, Arr);
@@ -630,6 +636,7 @@ Csr interpolation(const Csr &Af, const Csr &Ac, const Csr &Ar, double gamma2, do
     trace_csr("ip.R", R);
     trace_csr("ip.R0", R0);
     {
+      StageTimer t_("ip.Rt_w1w2");
       Csr Rt = transpose(R);
       spmv(tmp.p, 0., nullptr, 1., R, ones.p);
       spmv(w1p, 0., nullptr, 1., Rt, tmp.p);
@@ -836,6 +843,7 @@ void setup(i64 nnz, const int *dAi, const int *dAj, const double *dAv, Hierarchy
   H.t.device_total = H.t.total;
 #endif
   spgemm_stats_get(&H.t.spgemm, &H.t.spgemm_bytes, &H.t.spgemm_calls);
+  stage_report();
   H.launches = c.launches - launches0;
   H.syncs = c.syncs - syncs0;
 }

@@ -208,6 +208,57 @@ __global__ void __launch_bounds__(256) k_spgemm_dense(int phase, const int *cmin
   for (int c = c0; c < c1; c++) if (acc[c] != 0.0) { xcol[p] = c + cmin; xa[p] = acc[c]; p++; }
 }
 
+// Mid-sized rows (bound <= 256 distinct columns, span <= 32768 columns): one warp per row, 512-slot
+// table, bitmap and its word prefix over the span, all in the warp's slice of shared memory.
+constexpr int WB_HS = 512, WB_WORDS = 1016;
+__global__ void __launch_bounds__(128) k_spgemm_warp_bitmap(int phase, const int *cminv, const int *spanv,
+                                                            const int *list, int nlist, const int *aro,
+                                                            const int *acol, const double *aa, const int *bro,
+                                                            const int *bcol, const double *ba, int *cnt,
+                                                            const int *xro, int *xcol, double *xa) {
+  __shared__ double svals_all[4 * WB_HS];
+  __shared__ int skeys_all[4 * WB_HS];
+  __shared__ unsigned bits_all[4 * WB_WORDS];
+  __shared__ unsigned short wpre_all[4 * WB_WORDS];
+  __shared__ int sred[4];
+  auto warp = cg::tiled_partition<32>(cg::this_thread_block());
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * 4 + w;
+  if (idx >= nlist) return;
+  const int i = list[idx];
+  int *skeys = skeys_all + w * WB_HS;
+  double *svals = svals_all + w * WB_HS;
+  accumulate_row(warp, i, aro, acol, aa, bro, bcol, ba, skeys, svals, WB_HS);
+  const int n = drop_zeros_count(warp, skeys, svals, WB_HS, sred + w);
+  if (phase == 1) { if (lane == 0) cnt[i] = n; return; }
+  unsigned *bits = bits_all + w * WB_WORDS;
+  unsigned short *wpre = wpre_all + w * WB_WORDS;
+  const int cmin = cminv[i];
+  const int nw = (spanv[i] + 31) / 32;
+  for (int q = lane; q < nw; q += 32) bits[q] = 0u;
+  __syncwarp();
+  for (int h = lane; h < WB_HS; h += 32) { const int c = skeys[h]; if (c != EMPTY) { const int d = c - cmin; atomicOr(&bits[d >> 5], 1u << (d & 31)); } }
+  __syncwarp();
+  // word prefix: each lane owns a contiguous segment, warp scan over the segment sums
+  const int seg = (nw + 31) / 32;
+  const int w0 = lane * seg, w1 = min(nw, w0 + seg);
+  int mine = 0;
+  for (int q = w0; q < w1; q++) mine += __popc(bits[q]);
+  int incl = mine;
+  for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += t; }
+  int run = incl - mine;
+  for (int q = w0; q < w1; q++) { wpre[q] = (unsigned short)run; run += __popc(bits[q]); }
+  __syncwarp();
+  const int base = xro[i];
+  for (int h = lane; h < WB_HS; h += 32) {
+    const int c = skeys[h];
+    if (c == EMPTY) continue;
+    const int d = c - cmin;
+    const int rank = wpre[d >> 5] + __popc(bits[d >> 5] & ((1u << (d & 31)) - 1u));
+    xcol[base + rank] = c; xa[base + rank] = svals[h];
+  }
+}
+
 // Hash table (shared memory, or HBM for rows that do not fit) plus a bitmap over the row's column
 // span in shared memory: the rank of a column is the number of set bits below it, so the row is
 // written in column order without sorting.
@@ -289,16 +340,16 @@ Csr spgemm(const Csr &A, const Csr &B) {
   // Per row: need = min(sum of B row lengths, columns of B) bounds the distinct columns;
   // [cmin, cmin+span) is the column range the row can touch (B rows are sorted, so it comes from
   // their first and last entries).  Bins:
-  //   0  need <= 24                 8-thread tiles, 64-slot hash tables in shared memory
-  //   1  need <= 96                 warps, 256-slot tables
-  //   2  span <= DENSE_MAX          block, dense accumulator over the span in shared memory
-  //   3  need <= 768                block, 2048-slot table + bitmap over the span
-  //   4  need <= 3072               block, 8192-slot table + bitmap over the span
-  //   5  span <= 800k               block, table in HBM + bitmap over the span in shared memory
-  //   6  anything else              block, table in HBM, bitonic sort
-  constexpr int NB = 7;
-  constexpr int DENSE_MAX = 24576;
-  constexpr int BM3_SPAN = 700000, BM4_SPAN = 400000, BM5_SPAN = 800000;   // bitmap = span/4 bytes
+  //   0  need <= 24                  8-thread tiles, 64-slot hash tables in shared memory, bitonic
+  //   1  need <= 96                  warps, 256-slot tables, bitonic
+  //   2  need <= 256, span <= 32512  warps, 512-slot tables + bitmap over the span
+  //   3,4,5  span <= 2048/8192/24576 block, dense accumulator over the span in shared memory
+  //   6  need <= 768                 block, 2048-slot table + bitmap over the span
+  //   7  need <= 3072                block, 8192-slot table + bitmap over the span
+  //   8  span <= 800k                block, table in HBM + bitmap over the span in shared memory
+  //   9  anything else               block, table in HBM, bitonic sort
+  constexpr int NB = 10;
+  constexpr int BM6_SPAN = 700000, BM7_SPAN = 400000, BM8_SPAN = 800000;   // bitmap = span/4 bytes
   const int bcn = B.cn;
   Buf<int> lists((i64)NB * rn), bcnt(NB), need(rn), cminv(rn), spanv(rn), maxspan(NB);
   bcnt.zero(); maxspan.zero();
@@ -313,80 +364,90 @@ Csr spgemm(const Csr &A, const Csr &B) {
     }
     if (ub > bcn) ub = bcn;
     const int span = hi >= lo ? hi - lo + 1 : 0;
+    if (ub > span) ub = span;
     nd[i] = (int)ub; cmv[i] = hi >= lo ? lo : 0; spv[i] = span;
     int bin;
     if (ub <= 24) bin = 0;
     else if (ub <= 96) bin = 1;
-    else if (span <= DENSE_MAX) bin = 2;
-    else if (ub <= 768 && span <= BM3_SPAN) bin = 3;
-    else if (ub <= 3072 && span <= BM4_SPAN) bin = 4;
-    else if (span <= BM5_SPAN) bin = 5;
-    else bin = 6;
+    else if (ub <= 256 && span <= 32512) bin = 2;
+    else if (span <= 2048) bin = 3;
+    else if (span <= 8192) bin = 4;
+    else if (span <= 24576) bin = 5;
+    else if (ub <= 768 && span <= BM6_SPAN) bin = 6;
+    else if (ub <= 3072 && span <= BM7_SPAN) bin = 7;
+    else if (span <= BM8_SPAN) bin = 8;
+    else bin = 9;
     const int p = atomic_add(&bc[bin], 1);
     lp[(i64)bin * rn + p] = (int)i;
     atomic_max_i32(&mxs[bin], span);
   });
   std::vector<int> hc = bcnt.download();
   std::vector<int> hms = maxspan.download();
-  // rows of bins 5 and 6 get tables in HBM
+  // rows of bins 8 and 9 get tables in HBM
   Buf<i64> tsz5, toff5, tsz6, toff6;
   Buf<int> gkeys5, gkeys6;
   Buf<double> gvals5, gvals6;
-  for (int bin = 5; bin <= 6; bin++) {
+  for (int bin = 8; bin <= 9; bin++) {
     if (!hc[bin]) continue;
-    Buf<i64> &tsz = bin == 5 ? tsz5 : tsz6, &toff = bin == 5 ? toff5 : toff6;
+    Buf<i64> &tsz = bin == 8 ? tsz5 : tsz6, &toff = bin == 8 ? toff5 : toff6;
     tsz.alloc(hc[bin] + 1); toff.alloc(hc[bin] + 1);
     i64 *ts = tsz.p;
     const int *lb = lp + bin * (i64)rn;
     parallel_for(hc[bin], [=] DEV(i64 q) { i64 s = 256; while (s < 2 * (i64)nd[lb[q]]) s <<= 1; ts[q] = s; });
     const i64 total = exclusive_scan64(tsz.p, toff.p, hc[bin]);
-    (bin == 5 ? gkeys5 : gkeys6).alloc(total);
-    (bin == 5 ? gvals5 : gvals6).alloc(total);
+    (bin == 8 ? gkeys5 : gkeys6).alloc(total);
+    (bin == 8 ? gvals5 : gvals6).alloc(total);
   }
   Buf<int> cnt(rn + 1), xro(rn + 1);
   cudaEvent_t e0, e1;
   CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
   static bool attr = false;
   if (!attr) {
-    CUDA_CHECK(cudaFuncSetAttribute((const void *)k_spgemm_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_MAX * 8));
+    CUDA_CHECK(cudaFuncSetAttribute((const void *)k_spgemm_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, 24576 * 8));
     CUDA_CHECK(cudaFuncSetAttribute((const void *)k_spgemm_bitmap, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
     attr = true;
   }
   auto words = [](int span) { return (span + 31) / 32; };
+  auto L = [&](int bin) { return lp + bin * (i64)rn; };
   Csr X;
   CUDA_CHECK(cudaEventRecord(e0, c.stream));
   for (int phase = 1; phase <= 2; phase++) {
     int *xcol = phase == 2 ? X.col.p : nullptr;
     double *xa = phase == 2 ? X.a.p : nullptr;
     if (hc[0]) {
-      k_spgemm_tile<8, 64><<<(hc[0] + 31) / 32, 256, 0, c.stream>>>(phase, lp, hc[0], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+      k_spgemm_tile<8, 64><<<(hc[0] + 31) / 32, 256, 0, c.stream>>>(phase, L(0), hc[0], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
       c.launches++; post_launch("spgemm_tile8");
     }
     if (hc[1]) {
-      k_spgemm_tile<32, 256><<<(hc[1] + 7) / 8, 256, 0, c.stream>>>(phase, lp + rn, hc[1], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+      k_spgemm_tile<32, 256><<<(hc[1] + 7) / 8, 256, 0, c.stream>>>(phase, L(1), hc[1], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
       c.launches++; post_launch("spgemm_tile32");
     }
     if (hc[2]) {
-      k_spgemm_dense<<<hc[2], 256, (size_t)(hms[2] > 0 ? hms[2] : 1) * 8, c.stream>>>(phase, cmv, spv, lp + 2 * (i64)rn, hc[2], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+      k_spgemm_warp_bitmap<<<(hc[2] + 3) / 4, 128, 0, c.stream>>>(phase, cmv, spv, L(2), hc[2], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+      c.launches++; post_launch("spgemm_warp_bitmap");
+    }
+    for (int bin = 3; bin <= 5; bin++) {
+      if (!hc[bin]) continue;
+      k_spgemm_dense<<<hc[bin], 256, (size_t)(hms[bin] > 0 ? hms[bin] : 1) * 8, c.stream>>>(phase, cmv, spv, L(bin), hc[bin], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
       c.launches++; post_launch("spgemm_dense");
     }
-    if (hc[3]) {
-      const int mw = words(hms[3]);
-      k_spgemm_bitmap<<<hc[3], 128, 2048 * 12 + (size_t)mw * 8, c.stream>>>(phase, 2048, mw, cmv, spv, lp + 3 * (i64)rn, hc[3], nullptr, nullptr, nullptr, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+    if (hc[6]) {
+      const int mw = words(hms[6]);
+      k_spgemm_bitmap<<<hc[6], 128, 2048 * 12 + (size_t)mw * 8, c.stream>>>(phase, 2048, mw, cmv, spv, L(6), hc[6], nullptr, nullptr, nullptr, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
       c.launches++; post_launch("spgemm_bitmap2k");
     }
-    if (hc[4]) {
-      const int mw = words(hms[4]);
-      k_spgemm_bitmap<<<hc[4], 256, 8192 * 12 + (size_t)mw * 8, c.stream>>>(phase, 8192, mw, cmv, spv, lp + 4 * (i64)rn, hc[4], nullptr, nullptr, nullptr, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+    if (hc[7]) {
+      const int mw = words(hms[7]);
+      k_spgemm_bitmap<<<hc[7], 256, 8192 * 12 + (size_t)mw * 8, c.stream>>>(phase, 8192, mw, cmv, spv, L(7), hc[7], nullptr, nullptr, nullptr, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
       c.launches++; post_launch("spgemm_bitmap8k");
     }
-    if (hc[5]) {
-      const int mw = words(hms[5]);
-      k_spgemm_bitmap<<<hc[5], 256, (size_t)mw * 8 + 16, c.stream>>>(phase, 0, mw, cmv, spv, lp + 5 * (i64)rn, hc[5], toff5.p, gkeys5.p, gvals5.p, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+    if (hc[8]) {
+      const int mw = words(hms[8]);
+      k_spgemm_bitmap<<<hc[8], 256, (size_t)mw * 8 + 16, c.stream>>>(phase, 0, mw, cmv, spv, L(8), hc[8], toff5.p, gkeys5.p, gvals5.p, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
       c.launches++; post_launch("spgemm_bitmap_hbm");
     }
-    if (hc[6]) {
-      k_spgemm_global<<<hc[6], 256, 0, c.stream>>>(phase, lp + 6 * (i64)rn, hc[6], toff6.p, gkeys6.p, gvals6.p, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+    if (hc[9]) {
+      k_spgemm_global<<<hc[9], 256, 0, c.stream>>>(phase, L(9), hc[9], toff6.p, gkeys6.p, gvals6.p, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
       c.launches++; post_launch("spgemm_global");
     }
     if (phase == 1) {
@@ -401,6 +462,21 @@ Csr spgemm(const Csr &A, const Csr &B) {
   }
   CUDA_CHECK(cudaEventRecord(e1, c.stream));
   g_stats.ev.emplace_back(e0, e1);
+  {
+    static int logit = -1;
+    if (logit < 0) { const char *e = getenv("AMGB_SPGEMM_LOG"); logit = (e && *e && *e != '0') ? 1 : 0; }
+    if (logit) {
+      stream_sync();
+      float m1 = 0, m2 = 0;
+      const size_t ne = g_stats.ev.size();
+      cudaEventElapsedTime(&m1, g_stats.ev[ne - 2].first, g_stats.ev[ne - 2].second);
+      cudaEventElapsedTime(&m2, g_stats.ev[ne - 1].first, g_stats.ev[ne - 1].second);
+      fprintf(stderr, "spgemm A %dx%d nnz %lld  B %dx%d nnz %lld  X nnz %lld | bins %d %d %d %d %d %d %d %d %d %d | phase1 %.3f ms phase2 %.3f ms | %.1f GB/s\n",
+              A.rn, A.cn, (long long)A.nnz, B.rn, B.cn, (long long)B.nnz, (long long)X.nnz, hc[0], hc[1], hc[2], hc[3], hc[4],
+              hc[5], hc[6], hc[7], hc[8], hc[9], m1, m2,
+              (12.0 * (A.nnz + B.nnz + X.nnz)) / ((m1 + m2) * 1e-3) / 1e9);
+    }
+  }
   // algorithmic bytes: A, B and X each moved once (12 B per entry, 4 B per row offset)
   g_stats.bytes += 12 * (A.nnz + B.nnz + X.nnz) + 4 * ((i64)A.rn + B.rn + X.rn + 3);
   g_stats.calls++;
