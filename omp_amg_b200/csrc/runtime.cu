@@ -207,11 +207,19 @@ __global__ void __launch_bounds__(1024) k_seq_dot(const double *a, const double 
       const int len = (int)((n - base < SEQ_CHUNK) ? (n - base) : SEQ_CHUNK);
       const double *p = buf[cur];
       int j = 0;
-      for (; j + 8 <= len; j += 8) {
-        const double p0 = p[j], p1 = p[j + 1], p2 = p[j + 2], p3 = p[j + 3], p4 = p[j + 4], p5 = p[j + 5],
-                     p6 = p[j + 6], p7 = p[j + 7];
-        r = __dadd_rn(r, p0); r = __dadd_rn(r, p1); r = __dadd_rn(r, p2); r = __dadd_rn(r, p3);
-        r = __dadd_rn(r, p4); r = __dadd_rn(r, p5); r = __dadd_rn(r, p6); r = __dadd_rn(r, p7);
+      if (len >= 8) {
+        // software pipeline: the next eight values are in registers before the chain needs them
+        double a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3], a4 = p[4], a5 = p[5], a6 = p[6], a7 = p[7];
+        for (; j + 16 <= len; j += 8) {
+          const double b0 = p[j + 8], b1 = p[j + 9], b2 = p[j + 10], b3 = p[j + 11], b4 = p[j + 12],
+                       b5 = p[j + 13], b6 = p[j + 14], b7 = p[j + 15];
+          r = __dadd_rn(r, a0); r = __dadd_rn(r, a1); r = __dadd_rn(r, a2); r = __dadd_rn(r, a3);
+          r = __dadd_rn(r, a4); r = __dadd_rn(r, a5); r = __dadd_rn(r, a6); r = __dadd_rn(r, a7);
+          a0 = b0; a1 = b1; a2 = b2; a3 = b3; a4 = b4; a5 = b5; a6 = b6; a7 = b7;
+        }
+        r = __dadd_rn(r, a0); r = __dadd_rn(r, a1); r = __dadd_rn(r, a2); r = __dadd_rn(r, a3);
+        r = __dadd_rn(r, a4); r = __dadd_rn(r, a5); r = __dadd_rn(r, a6); r = __dadd_rn(r, a7);
+        j += 8;
       }
       for (; j < len; j++) r = __dadd_rn(r, p[j]);
     }
@@ -220,6 +228,7 @@ __global__ void __launch_bounds__(1024) k_seq_dot(const double *a, const double 
 }
 double seq_dot(const double *a, const double *b, i64 n) {
   if (n <= 0) return 0.0;
+  StageTimer st_("prim.seq_dot");
   Buf<double> out(1);
   k_seq_dot<<<1, 1024, 0, g_ctx.stream>>>(a, b, n, out.p);
   g_ctx.launches++; post_launch(__func__);
@@ -258,6 +267,7 @@ __global__ void __launch_bounds__(256) k_max_first(const double *v, const i64 *i
 }
 void max_first(const double *v, i64 n, double *val, i64 *idx) {
   if (n <= 0) throw Error(-3, "max_first on an empty vector");
+  StageTimer st_("prim.max_first");
   i64 nb = (n + 255) / 256;
   if (nb > 1024) nb = 1024;
   Buf<double> pv(nb), fv(1);

@@ -413,11 +413,9 @@ __global__ void __launch_bounds__(256) k_expand_rows(int nf, const double *badro
 // find_support (:1260).  Entries leave R one per bad column and round; here they are zeroed and
 // flagged dead instead of compacting R and its transpose every round (a zero adds nothing to any
 // of the sums involved, so all vectors are bit-identical).
-Csr find_support(const Csr &R, double goal) {
+Csr find_support(const Csr &R, Csr &Rt, Buf<int> &tpos, double goal) {   // Rt = R' (values are consumed)
   StageTimer st_("find_support");
   const int nf = R.rn, nc = R.cn;
-  Buf<int> tpos;
-  Csr Rt = transpose(R, &tpos);
   Buf<int> src(R.nnz), skel(R.nnz), alive_t(R.nnz);
   Buf<double> rv = R.a.clone();
   skel.zero();
@@ -486,10 +484,10 @@ Csr find_support(const Csr &R, double goal) {
 }
 
 // expand_support (:907)
-Csr expand_support(const Csr &Wsk, const Csr &R, const Csr &R0, double gamma) {
+Csr expand_support(const Csr &Wsk, const Csr &R, Csr &Rt, Buf<int> &rtpos, const Csr &R0, double gamma) {
   StageTimer st_("expand_support(incl find)");
   const int nf = Wsk.rn, nc = Wsk.cn;
-  Csr M = find_support(R, gamma);
+  Csr M = find_support(R, Rt, rtpos, gamma);
   trace_csr("es.M", M);
   Csr ns = mpm(1., M, 1., Wsk);
   Buf<double> badrow(nf);
@@ -573,6 +571,53 @@ Csr expand_support(const Csr &Wsk, const Csr &R, const Csr &R0, double gamma) {
   return out;
 }
 
+// s[c] = sum over the entries (i, w) of row c of Tt, i ascending, of w * M[i][c] where M holds
+// (i,c); equals sum(Tt' .* M, 1) of the reference (mxmpoint :1807 + sum :1193)
+#ifndef AMGB_EMU
+__global__ void __launch_bounds__(256) k_col_dot_transposed(int nc, const int *tro, const int *tcol, const double *ta,
+                                                            const int *mro, const int *mcol, const double *ma,
+                                                            double *s) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= nc) return;
+  const int lane = threadIdx.x & 31;
+  const int end = tro[c + 1];
+  double t = 0.0;
+  for (int base = tro[c]; base < end; base += 32) {
+    const int p = base + lane;
+    double prod = 0.0;
+    if (p < end) {
+      const int i = tcol[p];
+      int lo = mro[i], hi = mro[i + 1];
+      const int e = hi;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (mcol[mid] < c) lo = mid + 1; else hi = mid; }
+      if (lo < e && mcol[lo] == c) prod = ta[p] * ma[lo];
+    }
+    const int m = min(32, end - base);
+    for (int l = 0; l < m; l++) t = t + __shfl_sync(0xffffffffu, prod, l);
+  }
+  if (lane == 0) s[c] = t;
+}
+#endif
+void col_dot_transposed(double *s, const Csr &Tt, const Csr &M) {
+  const int *tro = Tt.ro.p, *tcol = Tt.col.p, *mro = M.ro.p, *mcol = M.col.p;
+  const double *ta = Tt.a.p, *ma = M.a.p;
+#ifdef AMGB_EMU
+  parallel_for(Tt.rn, [=] DEV(i64 c) {
+    double t = 0.0;
+    for (int p = tro[c]; p < tro[c + 1]; p++) {
+      const int i = tcol[p];
+      for (int q = mro[i]; q < mro[i + 1]; q++) if (mcol[q] == c) { t = t + ta[p] * ma[q]; break; }
+    }
+    s[c] = t;
+  });
+#else
+  if (Tt.rn == 0) return;
+  Context &cx = ctx();
+  k_col_dot_transposed<<<(Tt.rn + 7) / 8, 256, 0, cx.stream>>>(Tt.rn, tro, tcol, ta, mro, mcol, ma, s);
+  cx.launches++; post_launch("col_dot_transposed");
+#endif
+}
+
 // interpolation (:598)
 Csr interpolation(const Csr &Af, const Csr &Ac, const Csr &Ar, double gamma2, double tol, int *rounds_out) {
   const int nf = Af.rn, nc = Ac.cn;
@@ -622,9 +667,11 @@ Csr interpolation(const Csr &Af, const Csr &Ac, const Csr &Ar, double gamma2, do
     { StageTimer t_("ip.AfW_spgemm+mpm"); Csr AfW = spgemm(Af, W0); R0 = mpm(1., AfW, 1., Ar); }
     { StageTimer t_("ip.AfW_spgemm+mpm"); Csr AfW = spgemm(Af, Wt); R = mpm(1., AfW, 1., Ar); }
     {
+      // dchat = sum(W .* (Arhat + Ar), 1): column c collects W_ic * Arr_ic over the rows i of its
+      // support in ascending order -- row c of W_skel' (whose values are W' after the solve)
+      // against row i of Arr, no transpose of the product needed
       Csr Arr = mpm(1.0, R, 1.0, Ar);
-      Csr ArW = mxmpoint(Wt, Arr);
-      col_sums(dsq, ArW);
+      col_dot_transposed(dsq, sk.Wskt, Arr);
     }
     parallel_for(nc, [=] DEV(i64 i) { double t = dsq[i] + dcp[i]; t = 1. / t; dsq[i] = sqrt(t); });
     scale_rows(R, dfi);
@@ -635,9 +682,11 @@ Csr interpolation(const Csr &Af, const Csr &Ac, const Csr &Ar, double gamma2, do
     scale_cols(R0, dsq);
     trace_csr("ip.R", R);
     trace_csr("ip.R0", R0);
+    Csr Rt;
+    Buf<int> rtpos;
     {
       StageTimer t_("ip.Rt_w1w2");
-      Csr Rt = transpose(R);
+      Rt = transpose(R, &rtpos);
       spmv(tmp.p, 0., nullptr, 1., R, ones.p);
       spmv(w1p, 0., nullptr, 1., Rt, tmp.p);
       spmv(tmp.p, 0., nullptr, 1., R, w1p);
@@ -667,7 +716,7 @@ Csr interpolation(const Csr &Af, const Csr &Ac, const Csr &Ar, double gamma2, do
       break;
     }
     parallel_for(nc, [=] DEV(i64 i) { const double x = w2p[i] > 1e-6 ? w2p[i] : 1e-6; alp[i] = dcp[i] / x; });
-    Wsk = expand_support(Wsk, R, R0, gamma2);
+    Wsk = expand_support(Wsk, R, Rt, rtpos, R0, gamma2);
     sk = SkelCache();
   }
   ctx().trace_prefix = pfx_save;

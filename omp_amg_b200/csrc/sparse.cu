@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(256) k_spmv_tile(int rn, const int *ro, const 
 
 void spmv_vals(double *z, double alpha, const double *y, double beta, const Csr &M, const double *vals,
                const double *x) {
+  StageTimer st_("prim.spmv");
   const int *ro = M.ro.p, *col = M.col.p;
   const bool plain = (alpha == 0. || y == nullptr);
 #ifndef AMGB_EMU
@@ -84,13 +85,16 @@ static HD inline void row_sort(int *key, V *val, int n) {
 #ifndef AMGB_EMU
 // rank sort of every row of the transposed matrix by G cooperating threads: keys (source rows)
 // are unique inside a row, so the rank of a key is the number of smaller keys
+#define TR_LONG 96        // rows longer than this are sorted by a block (bitonic) instead
 template <int G>
 __global__ void __launch_bounds__(256) k_transpose_rank(int nrows, const int *tro, const int *kin, const int *sin,
-                                                        int *kout, int *sout, const double *a, double *ta) {
+                                                        int *kout, int *sout, const double *a, double *ta,
+                                                        int *longlist, int *nlong) {
   const int c = blockIdx.x * (256 / G) + threadIdx.x / G;
   if (c >= nrows) return;
   const int r0 = threadIdx.x % G;
   const int b = tro[c], L = tro[c + 1] - b;
+  if (L > TR_LONG && L <= 4096) { if (r0 == 0) longlist[atomicAdd(nlong, 1)] = c; return; }
   for (int e = r0; e < L; e += G) {
     const int key = kin[b + e];
     int rank = 0;
@@ -99,12 +103,40 @@ __global__ void __launch_bounds__(256) k_transpose_rank(int nrows, const int *tr
     kout[b + rank] = key; sout[b + rank] = s; ta[b + rank] = a[s];
   }
 }
+// long rows: one block, (key, source) pairs sorted by a bitonic network in shared memory
+__global__ void __launch_bounds__(128) k_transpose_bitonic(const int *list, int nlist, const int *tro, const int *kin,
+                                                           const int *sin, int *kout, int *sout, const double *a,
+                                                           double *ta) {
+  extern __shared__ int tsm[];
+  if ((int)blockIdx.x >= nlist) return;
+  const int c = list[blockIdx.x];
+  const int b = tro[c], L = tro[c + 1] - b;
+  int P = 128;
+  while (P < L) P <<= 1;
+  int *key = tsm, *src = tsm + P;
+  for (int e = threadIdx.x; e < P; e += blockDim.x) { key[e] = e < L ? kin[b + e] : 0x7fffffff; src[e] = e < L ? sin[b + e] : -1; }
+  __syncthreads();
+  for (int k = 2; k <= P; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int idx = threadIdx.x; idx < P; idx += blockDim.x) {
+        const int ixj = idx ^ j;
+        if (ixj > idx) {
+          const int ka = key[idx], kb = key[ixj];
+          const bool up = ((idx & k) == 0);
+          if ((ka > kb) == up && ka != kb) { key[idx] = kb; key[ixj] = ka; const int t = src[idx]; src[idx] = src[ixj]; src[ixj] = t; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int e = threadIdx.x; e < L; e += blockDim.x) { kout[b + e] = key[e]; sout[b + e] = src[e]; ta[b + e] = a[src[e]]; }
+}
 #endif
 
 // ---------------------------------------------------------------------------------------
 // transpose (:2000): A^t rows list the source rows in ascending order
 // ---------------------------------------------------------------------------------------
 Csr transpose(const Csr &A, Buf<int> *tpos_out) {
+  StageTimer st_("prim.transpose");
   Csr T(A.cn, A.rn, A.nnz);
   Buf<int> cnt(A.cn + 1);
   cnt.zero();
@@ -132,13 +164,19 @@ Csr transpose(const Csr &A, Buf<int> *tpos_out) {
   });
 #else
   if (A.cn > 0 && A.nnz > 0) {
-    Buf<int> kin = T.col.clone(), sin = src.clone();
+    Buf<int> kin = T.col.clone(), sin = src.clone(), longlist(A.cn), nlong(1);
+    nlong.zero();
     Context &c = ctx();
     if ((double)A.nnz / (double)A.cn <= 12.0)
-      k_transpose_rank<8><<<(A.cn + 31) / 32, 256, 0, c.stream>>>(A.cn, tro, kin.p, sin.p, tcol, srcp, a, ta);
+      k_transpose_rank<8><<<(A.cn + 31) / 32, 256, 0, c.stream>>>(A.cn, tro, kin.p, sin.p, tcol, srcp, a, ta, longlist.p, nlong.p);
     else
-      k_transpose_rank<32><<<(A.cn + 7) / 8, 256, 0, c.stream>>>(A.cn, tro, kin.p, sin.p, tcol, srcp, a, ta);
+      k_transpose_rank<32><<<(A.cn + 7) / 8, 256, 0, c.stream>>>(A.cn, tro, kin.p, sin.p, tcol, srcp, a, ta, longlist.p, nlong.p);
     c.launches++; post_launch("transpose_rank");
+    const int nl = nlong.get(0);
+    if (nl) {
+      k_transpose_bitonic<<<nl, 128, 4096 * 8, c.stream>>>(longlist.p, nl, tro, kin.p, sin.p, tcol, srcp, a, ta);
+      c.launches++; post_launch("transpose_bitonic");
+    }
   }
 #endif
   if (tpos_out) {
@@ -153,6 +191,7 @@ Csr transpose(const Csr &A, Buf<int> *tpos_out) {
 // sub_mat (:3058)
 // ---------------------------------------------------------------------------------------
 Csr sub_mat(const Csr &A, const double *vr, const double *vc) {
+  StageTimer st_("prim.sub_mat");
   const int rn = A.rn, cn = A.cn;
   const int *ro = A.ro.p, *col = A.col.p;
   const double *a = A.a.p;
@@ -191,6 +230,7 @@ Csr sub_mat(const Csr &A, const double *vr, const double *vc) {
 // mpm (:1684): X = alpha*A + beta*B
 // ---------------------------------------------------------------------------------------
 Csr mpm(double alpha, const Csr &A, double beta, const Csr &B) {
+  StageTimer st_("prim.mpm");
   if (A.rn != B.rn || A.cn != B.cn) throw Error(-4, "mpm: dimension mismatch");
   const int rn = A.rn;
   const int *aro = A.ro.p, *acol = A.col.p, *bro = B.ro.p, *bcol = B.col.p;
@@ -237,6 +277,7 @@ Csr mpm(double alpha, const Csr &A, double beta, const Csr &B) {
 // mxmpoint (:1807): X = A.*B on the intersection pattern (zeros kept)
 // ---------------------------------------------------------------------------------------
 Csr mxmpoint(const Csr &A, const Csr &B) {
+  StageTimer st_("prim.mxmpoint");
   if (A.rn != B.rn || A.cn != B.cn) throw Error(-4, "mxmpoint: dimension mismatch");
   const int rn = A.rn;
   const int *aro = A.ro.p, *acol = A.col.p, *bro = B.ro.p, *bcol = B.col.p;

@@ -208,38 +208,74 @@ __global__ void __launch_bounds__(256) k_spgemm_dense(int phase, const int *cmin
   for (int c = c0; c < c1; c++) if (acc[c] != 0.0) { xcol[p] = c + cmin; xa[p] = acc[c]; p++; }
 }
 
-// Mid-sized rows (bound <= 256 distinct columns, span <= 32768 columns): one warp per row, 512-slot
-// table, bitmap and its word prefix over the span, all in the warp's slice of shared memory.
-constexpr int WB_HS = 512, WB_WORDS = 1016;
+// Warp-per-row kernel for rows of moderate size: a hash table of HS slots, a bitmap over the
+// row's column span and its word prefix, all in the warp's slice of shared memory.  Used in two
+// ways: with a table that is certainly large enough (bound <= HS/2), and OPTIMISTICALLY for rows
+// whose bound (sum of B row lengths) is large but whose number of distinct columns is usually
+// small: the warp counts its insertions and gives the row up once the table is 3/4 full; such
+// rows are collected in `overflow` and redone by the dense block kernel.
+template <int HS, int WORDS>
 __global__ void __launch_bounds__(128) k_spgemm_warp_bitmap(int phase, const int *cminv, const int *spanv,
                                                             const int *list, int nlist, const int *aro,
                                                             const int *acol, const double *aa, const int *bro,
                                                             const int *bcol, const double *ba, int *cnt,
-                                                            const int *xro, int *xcol, double *xa) {
-  __shared__ double svals_all[4 * WB_HS];
-  __shared__ int skeys_all[4 * WB_HS];
-  __shared__ unsigned bits_all[4 * WB_WORDS];
-  __shared__ unsigned short wpre_all[4 * WB_WORDS];
-  __shared__ int sred[4];
-  auto warp = cg::tiled_partition<32>(cg::this_thread_block());
+                                                            const int *xro, int *xcol, double *xa,
+                                                            int *overflow, int *noverflow, const int *skip) {
+  extern __shared__ double wsm[];
+  // per warp: svals[HS] | skeys[HS] | bits[WORDS] | wpre[WORDS] (ushort)
+  constexpr int PER_BYTES = HS * 12 + WORDS * 4 + WORDS * 2;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int idx = blockIdx.x * 4 + w;
   if (idx >= nlist) return;
   const int i = list[idx];
-  int *skeys = skeys_all + w * WB_HS;
-  double *svals = svals_all + w * WB_HS;
-  accumulate_row(warp, i, aro, acol, aa, bro, bcol, ba, skeys, svals, WB_HS);
-  const int n = drop_zeros_count(warp, skeys, svals, WB_HS, sred + w);
+  if (skip && skip[i]) return;              // phase 2: rows that overflowed in phase 1
+  char *basep = (char *)wsm + (size_t)w * PER_BYTES;
+  double *svals = (double *)basep;
+  int *skeys = (int *)(basep + HS * 8);
+  unsigned *bits = (unsigned *)(basep + HS * 12);
+  unsigned short *wpre = (unsigned short *)(basep + HS * 12 + WORDS * 4);
+  const unsigned mask = (unsigned)(HS - 1);
+  for (int h = lane; h < HS; h += 32) skeys[h] = EMPTY;
+  __syncwarp();
+  int filled = 0;
+  bool gaveup = false;
+  for (int ja = aro[i]; ja < aro[i + 1]; ja++) {
+    const int k = acol[ja];
+    const double av = aa[ja];
+    const int be = bro[k + 1];
+    if (overflow && filled + (be - bro[k]) > HS - 64) { gaveup = true; break; }   // never let the table fill up
+    int mine = 0;
+    for (int jb = bro[k] + lane; jb < be; jb += 32) {
+      const int c = bcol[jb];
+      const double p = ba[jb] * av;
+      unsigned h = hash_col(c) & mask;
+      for (;;) {
+        const int old = atomicCAS(&skeys[h], EMPTY, c);
+        if (old == EMPTY) { double v = 0.0; v = v + p; svals[h] = v; mine++; break; }
+        if (old == c) { svals[h] = svals[h] + p; break; }
+        h = (h + 1) & mask;
+      }
+    }
+    filled += __reduce_add_sync(0xffffffffu, mine);
+    __syncwarp();
+    // a B row adds at most its length; stop while the table still has room for the longest row
+    if (overflow && filled > HS * 3 / 4) { gaveup = true; break; }
+  }
+  if (gaveup) {
+    if (lane == 0) { overflow[atomicAdd(noverflow, 1)] = i; }
+    return;
+  }
+  int n = 0;
+  for (int h = lane; h < HS; h += 32)
+    if (skeys[h] != EMPTY) { if (svals[h] == 0.0) skeys[h] = EMPTY; else n++; }
+  n = __reduce_add_sync(0xffffffffu, n);
   if (phase == 1) { if (lane == 0) cnt[i] = n; return; }
-  unsigned *bits = bits_all + w * WB_WORDS;
-  unsigned short *wpre = wpre_all + w * WB_WORDS;
   const int cmin = cminv[i];
   const int nw = (spanv[i] + 31) / 32;
   for (int q = lane; q < nw; q += 32) bits[q] = 0u;
   __syncwarp();
-  for (int h = lane; h < WB_HS; h += 32) { const int c = skeys[h]; if (c != EMPTY) { const int d = c - cmin; atomicOr(&bits[d >> 5], 1u << (d & 31)); } }
+  for (int h = lane; h < HS; h += 32) { const int c = skeys[h]; if (c != EMPTY) { const int d = c - cmin; atomicOr(&bits[d >> 5], 1u << (d & 31)); } }
   __syncwarp();
-  // word prefix: each lane owns a contiguous segment, warp scan over the segment sums
   const int seg = (nw + 31) / 32;
   const int w0 = lane * seg, w1 = min(nw, w0 + seg);
   int mine = 0;
@@ -250,7 +286,7 @@ __global__ void __launch_bounds__(128) k_spgemm_warp_bitmap(int phase, const int
   for (int q = w0; q < w1; q++) { wpre[q] = (unsigned short)run; run += __popc(bits[q]); }
   __syncwarp();
   const int base = xro[i];
-  for (int h = lane; h < WB_HS; h += 32) {
+  for (int h = lane; h < HS; h += 32) {
     const int c = skeys[h];
     if (c == EMPTY) continue;
     const int d = c - cmin;
@@ -331,6 +367,7 @@ static int g_spgemm_impl = -1;
 Csr spgemm(const Csr &A, const Csr &B) {
   if (g_spgemm_impl < 0) { const char *e = getenv("AMGB_SPGEMM"); g_spgemm_impl = (e && !strcmp(e, "rowhash")) ? 0 : 1; }
   if (g_spgemm_impl == 0) return spgemm_rowhash(A, B);
+  StageTimer st_("prim.spgemm");
   if (A.cn != B.rn) throw Error(-4, "spgemm: dimension mismatch");
   Context &c = ctx();
   const int rn = A.rn;
@@ -343,7 +380,8 @@ Csr spgemm(const Csr &A, const Csr &B) {
   //   0  need <= 24                  8-thread tiles, 64-slot hash tables in shared memory, bitonic
   //   1  need <= 96                  warps, 256-slot tables, bitonic
   //   2  need <= 256, span <= 32512  warps, 512-slot tables + bitmap over the span
-  //   3,4,5  span <= 2048/8192/24576 block, dense accumulator over the span in shared memory
+  //   3  span <= 24576               warps, 1024-slot tables + bitmap, optimistic; rows whose distinct
+  //                                  columns do not fit are redone by a block with a dense accumulator
   //   6  need <= 768                 block, 2048-slot table + bitmap over the span
   //   7  need <= 3072                block, 8192-slot table + bitmap over the span
   //   8  span <= 800k                block, table in HBM + bitmap over the span in shared memory
@@ -370,9 +408,7 @@ Csr spgemm(const Csr &A, const Csr &B) {
     if (ub <= 24) bin = 0;
     else if (ub <= 96) bin = 1;
     else if (ub <= 256 && span <= 32512) bin = 2;
-    else if (span <= 2048) bin = 3;
-    else if (span <= 8192) bin = 4;
-    else if (span <= 24576) bin = 5;
+    else if (span <= 24576) bin = 3;          // optimistic warp kernel first, dense fallback (bins 4,5 unused)
     else if (ub <= 768 && span <= BM6_SPAN) bin = 6;
     else if (ub <= 3072 && span <= BM7_SPAN) bin = 7;
     else if (span <= BM8_SPAN) bin = 8;
@@ -405,10 +441,14 @@ Csr spgemm(const Csr &A, const Csr &B) {
   if (!attr) {
     CUDA_CHECK(cudaFuncSetAttribute((const void *)k_spgemm_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, 24576 * 8));
     CUDA_CHECK(cudaFuncSetAttribute((const void *)k_spgemm_bitmap, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute((const void *)k_spgemm_warp_bitmap<512, 1016>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (512 * 12 + 1016 * 6)));
+    CUDA_CHECK(cudaFuncSetAttribute((const void *)k_spgemm_warp_bitmap<1024, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (1024 * 12 + 768 * 6)));
     attr = true;
   }
   auto words = [](int span) { return (span + 31) / 32; };
   auto L = [&](int bin) { return lp + bin * (i64)rn; };
+  Buf<int> ovf, novf, ovflag;
+  int n_ovf = 0;
   Csr X;
   CUDA_CHECK(cudaEventRecord(e0, c.stream));
   for (int phase = 1; phase <= 2; phase++) {
@@ -423,13 +463,27 @@ Csr spgemm(const Csr &A, const Csr &B) {
       c.launches++; post_launch("spgemm_tile32");
     }
     if (hc[2]) {
-      k_spgemm_warp_bitmap<<<(hc[2] + 3) / 4, 128, 0, c.stream>>>(phase, cmv, spv, L(2), hc[2], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+      k_spgemm_warp_bitmap<512, 1016><<<(hc[2] + 3) / 4, 128, 4 * (512 * 12 + 1016 * 6), c.stream>>>(
+          phase, cmv, spv, L(2), hc[2], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, nullptr, nullptr, nullptr);
       c.launches++; post_launch("spgemm_warp_bitmap");
     }
-    for (int bin = 3; bin <= 5; bin++) {
-      if (!hc[bin]) continue;
-      k_spgemm_dense<<<hc[bin], 256, (size_t)(hms[bin] > 0 ? hms[bin] : 1) * 8, c.stream>>>(phase, cmv, spv, L(bin), hc[bin], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
-      c.launches++; post_launch("spgemm_dense");
+    if (hc[3]) {
+      if (phase == 1) {
+        ovf.alloc(hc[3]); novf.alloc(1); ovflag.alloc(rn);
+        novf.zero(); ovflag.zero();
+      }
+      k_spgemm_warp_bitmap<1024, 768><<<(hc[3] + 3) / 4, 128, 4 * (1024 * 12 + 768 * 6), c.stream>>>(
+          phase, cmv, spv, L(3), hc[3], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa,
+          phase == 1 ? ovf.p : nullptr, phase == 1 ? novf.p : nullptr, phase == 2 ? ovflag.p : nullptr);
+      c.launches++; post_launch("spgemm_warp_optimistic");
+      if (phase == 1) {
+        n_ovf = novf.get(0);
+        if (n_ovf) { int *fl = ovflag.p; const int *ol = ovf.p; parallel_for(n_ovf, [=] DEV(i64 q) { fl[ol[q]] = 1; }); }
+      }
+      if (n_ovf) {
+        k_spgemm_dense<<<n_ovf, 256, (size_t)(hms[3] > 0 ? hms[3] : 1) * 8, c.stream>>>(phase, cmv, spv, ovf.p, n_ovf, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+        c.launches++; post_launch("spgemm_dense");
+      }
     }
     if (hc[6]) {
       const int mw = words(hms[6]);
@@ -473,7 +527,7 @@ Csr spgemm(const Csr &A, const Csr &B) {
       cudaEventElapsedTime(&m2, g_stats.ev[ne - 1].first, g_stats.ev[ne - 1].second);
       fprintf(stderr, "spgemm A %dx%d nnz %lld  B %dx%d nnz %lld  X nnz %lld | bins %d %d %d %d %d %d %d %d %d %d | phase1 %.3f ms phase2 %.3f ms | %.1f GB/s\n",
               A.rn, A.cn, (long long)A.nnz, B.rn, B.cn, (long long)B.nnz, (long long)X.nnz, hc[0], hc[1], hc[2], hc[3], hc[4],
-              hc[5], hc[6], hc[7], hc[8], hc[9], m1, m2,
+              n_ovf, hc[6], hc[7], hc[8], hc[9], m1, m2,
               (12.0 * (A.nnz + B.nnz + X.nnz)) / ((m1 + m2) * 1e-3) / 1e9);
     }
   }
