@@ -190,13 +190,36 @@ __global__ void __launch_bounds__(256) k_spgemm_dense(int phase, const int *cmin
   const int cmin = cminv[i], cn = spanv[i];     // the row only touches columns [cmin, cmin+cn)
   const int t = threadIdx.x, T = blockDim.x;
   for (int c = t; c < cn; c += T) acc[c] = 0.0;
-  __syncthreads();
-  for (int ja = aro[i]; ja < aro[i + 1]; ja++) {
-    const int k = acol[ja];
-    const double av = aa[ja];
-    const int be = bro[k + 1];
-    for (int jb = bro[k] + t; jb < be; jb += T) { const int c = bcol[jb] - cmin; acc[c] = acc[c] + ba[jb] * av; }
+  // 256 entries of the row of A (a_ik and the bounds of row k of B) are staged in shared memory
+  // at a time; every thread keeps its entry of the next row of B in registers while the current
+  // one is added, so only the barrier separates consecutive k.
+  __shared__ int sb0[256], sb1[256];
+  __shared__ double sav[256];
+  const int a0 = aro[i], a1 = aro[i + 1];
+  for (int jc = a0; jc < a1; jc += 256) {
     __syncthreads();
+    const int my = jc + t;
+    if (my < a1) { const int mk = acol[my]; sav[t] = aa[my]; sb0[t] = bro[mk]; sb1[t] = bro[mk + 1]; }
+    __syncthreads();
+    const int ns = min(256, a1 - jc);
+    int b0 = sb0[0], b1 = sb1[0];
+    int pc = 0;
+    double pv = 0.0;
+    if (b0 + t < b1) { pc = bcol[b0 + t]; pv = ba[b0 + t]; }
+    for (int st = 0; st < ns; st++) {
+      const int cb0 = b0, cb1 = b1, cc = pc;
+      const double cv = pv, av = sav[st];
+      if (st + 1 < ns) {
+        b0 = sb0[st + 1]; b1 = sb1[st + 1];
+        if (b0 + t < b1) { pc = bcol[b0 + t]; pv = ba[b0 + t]; }
+      }
+      for (int jb = cb0 + t; jb < cb1; jb += T) {
+        const bool first = (jb < cb0 + T);
+        const int c = (first ? cc : bcol[jb]) - cmin;
+        acc[c] = acc[c] + (first ? cv : ba[jb]) * av;
+      }
+      __syncthreads();
+    }
   }
   const int seg = (cn + T - 1) / T;
   const int c0 = t * seg, c1 = min(cn, c0 + seg);
@@ -239,27 +262,48 @@ __global__ void __launch_bounds__(128) k_spgemm_warp_bitmap(int phase, const int
   __syncwarp();
   int filled = 0;
   bool gaveup = false;
-  for (int ja = aro[i]; ja < aro[i + 1]; ja++) {
-    const int k = acol[ja];
-    const double av = aa[ja];
-    const int be = bro[k + 1];
-    if (overflow && filled + (be - bro[k]) > HS - 64) { gaveup = true; break; }   // never let the table fill up
-    int mine = 0;
-    for (int jb = bro[k] + lane; jb < be; jb += 32) {
-      const int c = bcol[jb];
-      const double p = ba[jb] * av;
-      unsigned h = hash_col(c) & mask;
-      for (;;) {
-        const int old = atomicCAS(&skeys[h], EMPTY, c);
-        if (old == EMPTY) { double v = 0.0; v = v + p; svals[h] = v; mine++; break; }
-        if (old == c) { svals[h] = svals[h] + p; break; }
-        h = (h + 1) & mask;
+  // The row of A is taken 32 entries at a time (one per lane: k, a_ik and the bounds of row k of
+  // B), and the first 32 entries of the NEXT row of B are already in registers while the current
+  // one is accumulated, so the chain acol -> bro -> bcol/ba of dependent loads is off the critical
+  // path.  The accumulation order (k ascending, one k at a time) is unchanged.
+  const int a0 = aro[i], a1 = aro[i + 1];
+  for (int jc = a0; jc < a1 && !gaveup; jc += 32) {
+    const int my = jc + lane;
+    int mb0 = 0, mb1 = 0;
+    double mav = 0.0;
+    if (my < a1) { const int mk = acol[my]; mav = aa[my]; mb0 = bro[mk]; mb1 = bro[mk + 1]; }
+    const int ns = min(32, a1 - jc);
+    int b0 = __shfl_sync(0xffffffffu, mb0, 0), b1 = __shfl_sync(0xffffffffu, mb1, 0);
+    int pc = EMPTY;
+    double pv = 0.0;
+    if (b0 + lane < b1) { pc = bcol[b0 + lane]; pv = ba[b0 + lane]; }
+    for (int st = 0; st < ns; st++) {
+      const int cb0 = b0, cb1 = b1, cc = pc;
+      const double cv = pv;
+      const double av = __shfl_sync(0xffffffffu, mav, st);
+      if (st + 1 < ns) {
+        b0 = __shfl_sync(0xffffffffu, mb0, st + 1); b1 = __shfl_sync(0xffffffffu, mb1, st + 1);
+        pc = EMPTY;
+        if (b0 + lane < b1) { pc = bcol[b0 + lane]; pv = ba[b0 + lane]; }
       }
+      if (overflow && filled + (cb1 - cb0) > HS - 64) { gaveup = true; break; }   // never let the table fill up
+      int mine = 0;
+      for (int jb = cb0 + lane; jb < cb1; jb += 32) {
+        const bool first = (jb < cb0 + 32);
+        const int c = first ? cc : bcol[jb];
+        const double p = (first ? cv : ba[jb]) * av;
+        unsigned h = hash_col(c) & mask;
+        for (;;) {
+          const int old = atomicCAS(&skeys[h], EMPTY, c);
+          if (old == EMPTY) { double v = 0.0; v = v + p; svals[h] = v; mine++; break; }
+          if (old == c) { svals[h] = svals[h] + p; break; }
+          h = (h + 1) & mask;
+        }
+      }
+      filled += __reduce_add_sync(0xffffffffu, mine);
+      __syncwarp();
+      if (overflow && filled > HS * 3 / 4) { gaveup = true; break; }
     }
-    filled += __reduce_add_sync(0xffffffffu, mine);
-    __syncwarp();
-    // a B row adds at most its length; stop while the table still has room for the longest row
-    if (overflow && filled > HS * 3 / 4) { gaveup = true; break; }
   }
   if (gaveup) {
     if (lane == 0) { overflow[atomicAdd(noverflow, 1)] = i; }
