@@ -225,6 +225,8 @@ inline double vsum(const double *a, i64 n) { return ctx().reduce_seq ? seq_sum(a
 inline double vnorm2(const double *a, i64 n) { return sqrt(vdot(a, a, n)); }
 // largest value and the first index holding it (extr_op(max), amg_setup.c:3281)
 void max_first(const double *v, i64 n, double *val, i64 *idx);
+// both maxima of one coarsening round in one pass and one read-back
+void max_first2(const double *a, const double *b, i64 n, double *amax, i64 *aidx, double *bmax);
 // number of non-zero flags
 i64 count_nonzero(const double *v, i64 n);
 

@@ -266,6 +266,8 @@ void build_q_store(QStore &qs, const Csr &Wt, const Csr &At) {
   }
   if (hc[3]) {
     const size_t sm = sizeof(double) * (2 * (size_t)qs.maxnz);
+    if (sm > 200 * 1024) throw Error(-12, "interpolation support of " + std::to_string(qs.maxnz) + " rows exceeds the kernel limit (12800)");
+    if (sm > 48 * 1024) set_smem((const void *)k_build_q_block<false>, sm);
     k_build_q_block<false><<<hc[3], 256, sm, c.stream>>>(lp + 3 * (i64)n, hc[3], qs.maxnz, wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
     c.launches++; post_launch("build_q_global");
   }

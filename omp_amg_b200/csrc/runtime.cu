@@ -290,6 +290,64 @@ __global__ void __launch_bounds__(256) k_count_nonzero(const double *v, i64 n, u
   for (int off = 16; off >= 1; off >>= 1) c += __shfl_down_sync(0xffffffffu, c, off);
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
+__global__ void __launch_bounds__(256) k_max_first2_final(const double *pv, const i64 *pi, const double *qv, i64 nb,
+                                                          double *out) {
+  __shared__ double sv[8], sq[8];
+  __shared__ i64 si[8];
+  MaxIdx m{0.0, -1};
+  double q = -DBL_MAX;
+  for (i64 i = threadIdx.x; i < nb; i += blockDim.x) { m = better(m, MaxIdx{pv[i], pi[i]}); q = fmax(q, qv[i]); }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    MaxIdx o{__shfl_down_sync(0xffffffffu, m.v, off), __shfl_down_sync(0xffffffffu, m.i, off)};
+    m = better(m, o);
+    q = fmax(q, __shfl_down_sync(0xffffffffu, q, off));
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { sv[w] = m.v; si[w] = m.i; sq[w] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; k++) { m = better(m, MaxIdx{sv[k], si[k]}); q = fmax(q, sq[k]); }
+    out[0] = m.v; out[1] = (double)m.i; out[2] = q;
+  }
+}
+__global__ void __launch_bounds__(256) k_max_first2(const double *a, const double *b, i64 n, double *ov, i64 *oi, double *oq) {
+  __shared__ double sv[8], sq[8];
+  __shared__ i64 si[8];
+  MaxIdx m{0.0, -1};
+  double q = -DBL_MAX;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+    m = better(m, MaxIdx{a[i], i});
+    q = fmax(q, b[i]);
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    MaxIdx o{__shfl_down_sync(0xffffffffu, m.v, off), __shfl_down_sync(0xffffffffu, m.i, off)};
+    m = better(m, o);
+    q = fmax(q, __shfl_down_sync(0xffffffffu, q, off));
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { sv[w] = m.v; si[w] = m.i; sq[w] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; k++) { m = better(m, MaxIdx{sv[k], si[k]}); q = fmax(q, sq[k]); }
+    ov[blockIdx.x] = m.v; oi[blockIdx.x] = m.i; oq[blockIdx.x] = q;
+  }
+}
+void max_first2(const double *a, const double *b, i64 n, double *amax, i64 *aidx, double *bmax) {
+  if (n <= 0) throw Error(-3, "max_first2 on an empty vector");
+  i64 nb = (n + 255) / 256;
+  if (nb > 592) nb = 592;
+  Buf<double> pv(nb), qv(nb), out(3);
+  Buf<i64> pi(nb);
+  k_max_first2<<<(unsigned)nb, 256, 0, g_ctx.stream>>>(a, b, n, pv.p, pi.p, qv.p);
+  k_max_first2_final<<<1, 256, 0, g_ctx.stream>>>(pv.p, pi.p, qv.p, nb, out.p);
+  g_ctx.launches += 2; post_launch(__func__);
+  double h[3];
+  d2h(h, out.p, sizeof h);
+  *amax = h[0]; *aidx = (i64)h[1]; *bmax = h[2];
+}
+
 i64 count_nonzero(const double *v, i64 n) {
   if (n <= 0) return 0;
   Buf<unsigned long long> c(1);
@@ -369,6 +427,10 @@ void max_first(const double *v, i64 n, double *val, i64 *idx) {
   *val = m; if (idx) *idx = k;
 }
 i64 count_nonzero(const double *v, i64 n) { i64 c = 0; for (i64 i = 0; i < n; i++) c += (v[i] != 0.0); return c; }
+void max_first2(const double *a, const double *b, i64 n, double *amax, i64 *aidx, double *bmax) {
+  max_first(a, n, amax, aidx);
+  max_first(b, n, bmax, nullptr);
+}
 #endif
 
 // ---- sub-stage profile ----

@@ -14,33 +14,11 @@ static double now_s() {
 // =======================================================================================
 // coarsen (:2737) with mat_max (:3535)
 // =======================================================================================
-// y[k] = max over rows i that hold k as a strong neighbour (|S_ik| >= tol*max_row_i, f[k]!=0)
-// of x[i].  The reference scatters row by row; a maximum is order-free, so here every k gathers
-// from row k of S' (which lists exactly the pairs (i, S_ik)) -- no atomics, no init pass.
-void mat_max(double *y, const Csr &S, const Csr &St, const double *f, const double *x, double tol,
-             double *thr) {
-  const int *ro = S.ro.p, *col = S.col.p;
-  const double *a = S.a.p;
-  parallel_for(S.rn, [=] DEV(i64 i) {
-    double amax = 0;
-    for (int j = ro[i]; j < ro[i + 1]; j++)
-      if (f[col[j]] != 0 && fabs(a[j]) > amax) amax = fabs(a[j]);
-    thr[i] = amax * tol;
-  });
-  const int *tro = St.ro.p, *tcol = St.col.p;
-  const double *ta = St.a.p;
-  parallel_for(St.rn, [=] DEV(i64 k) {
-    double m = -DBL_MAX;
-    if (f[k] != 0)
-      for (int p = tro[k]; p < tro[k + 1]; p++) {
-        const int i = tcol[p];
-        if (fabs(ta[p]) < thr[i]) continue;
-        if (x[i] > m) m = x[i];
-      }
-    y[k] = m;
-  });
-}
-
+// mat_max (:3535): y[k] = max over rows i that hold k as a strong neighbour (|S_ik| >= thr_i,
+// thr_i = tol * max over F neighbours of |S_i.|, and f[k] != 0) of x[i].  The reference scatters
+// row by row; a maximum is order-free, so every k gathers from row k of S' (which lists exactly the
+// pairs (i, S_ik)) -- no atomics.  thr depends on (S, f) only and is shared by the two mat_max
+// calls of a coarsening round; the element-wise mask updates around them are fused in.
 int coarsen(double *vc, const Csr &A, double ctol) {
   StageTimer st_("coarsen");
   const int n = A.cn;
@@ -56,23 +34,23 @@ int coarsen(double *vc, const Csr &A, double ctol) {
   sub_diag(S, D.p);
   trace_csr("coarsen.S", S);
 
-  Buf<double> vf(n), g(n), w1(n), w2(n), tmp(n), w(n), mask(n), m(n), thr(n);
+  Buf<double> vf(n), g(n), w1(n), w2(n), tmp(n), w(n), mask(n), thr(n);
   Csr St = transpose(S);
   fill(vc, n, 0.);
   fill(vf.p, n, 1.);
-  double *vfp = vf.p, *gp = g.p, *w1p = w1.p, *w2p = w2.p, *tp = tmp.p, *wp = w.p, *mk = mask.p, *mp = m.p;
-  const double ctol2 = ctol * ctol;
+  double *vfp = vf.p, *gp = g.p, *w1p = w1.p, *w2p = w2.p, *tp = tmp.p, *wp = w.p, *mk = mask.p, *thp = thr.p;
+  const int *ro = S.ro.p, *col = S.col.p, *tro = St.ro.p, *tcol = St.col.p;
+  const double *sa = S.a.p, *ta = St.a.p;
+  const double ctol2 = ctol * ctol, mtol = 0.1;
   for (;;) {
     rounds++;
-    spmv(gp, 0, vfp, 1., S, vfp);
-    parallel_for(n, [=] DEV(i64 i) { gp[i] = gp[i] * vfp[i]; });
-    spmv(w1p, 0, gp, 1., S, gp);
-    parallel_for(n, [=] DEV(i64 i) { w1p[i] = w1p[i] * vfp[i]; });
-    spmv(w2p, 0, w1p, 1., S, w1p);
-    parallel_for(n, [=] DEV(i64 i) { w2p[i] = w2p[i] * vfp[i]; });
-    spmv(tp, 0, w2p, 1., S, w2p);
+    // w1 = vf.*(S*(vf.*(S*vf))), w2 = vf.*(S*(vf.*(S*w1))), w = (1./w1).*w2 (0 where w1 == 0)
+    spmv_vals(gp, 0, nullptr, 1., S, sa, vfp, vfp);
+    spmv_vals(w1p, 0, nullptr, 1., S, sa, gp, vfp);
+    spmv_vals(w2p, 0, nullptr, 1., S, sa, w1p, vfp);
+    spmv_vals(tp, 0, nullptr, 1., S, sa, w2p, vfp);
     parallel_for(n, [=] DEV(i64 i) {
-      const double w2v = tp[i] * vfp[i];
+      const double w2v = tp[i];
       w2p[i] = w2v;
       const double inv = 1. / w1p[i];
       double wv = inv * w2v;
@@ -81,38 +59,57 @@ int coarsen(double *vc, const Csr &A, double ctol) {
     });
     double w1m, wm;
     i64 mi;
-    max_first(w1p, n, &w1m, &mi);
-    max_first(wp, n, &wm, nullptr);
+    max_first2(w1p, wp, n, &w1m, &mi, &wm);
     const double b = (w1m < wm) ? sqrt(w1m) : sqrt(wm);
     if (b <= ctol) {
       if (count_nonzero(vc, n) == 0) parallel_for(1, [=] DEV(i64) { vc[mi] = 1.; });
       break;
     }
+    // thr_i of this round
     parallel_for(n, [=] DEV(i64 i) {
-      const double mv = (wp[i] > ctol2) ? 1. : 0.;
-      mk[i] = mv;
-      tp[i] = gp[i] * mv;
+      double amax = 0;
+      for (int j = ro[i]; j < ro[i + 1]; j++)
+        if (vfp[col[j]] != 0 && fabs(sa[j]) > amax) amax = fabs(sa[j]);
+      thp[i] = amax * mtol;
     });
-    mat_max(mp, S, St, vfp, tp, 0.1, thr.p);
-    parallel_for(n, [=] DEV(i64 i) {
-      const double d = gp[i] - mp[i];
-      const double mv = (mk[i] != 0. && d >= 0.) ? 1. : 0.;
-      mk[i] = mv;
-      tp[i] = mv * ((double)i + 1.0);
+    // mask = (w > ctol^2) & (g - mat_max(S, vf, mask.*g) >= 0);  tmp = mask.*id
+    parallel_for(n, [=] DEV(i64 k) {
+      double m = -DBL_MAX;
+      if (vfp[k] != 0)
+        for (int p = tro[k]; p < tro[k + 1]; p++) {
+          const int i = tcol[p];
+          if (fabs(ta[p]) < thp[i]) continue;
+          const double mi0 = (wp[i] > ctol2) ? 1. : 0.;
+          const double x = gp[i] * mi0;
+          if (x > m) m = x;
+        }
+      const double m0 = (wp[k] > ctol2) ? 1. : 0.;
+      const double d = gp[k] - m;
+      const double mv = (m0 != 0. && d >= 0.) ? 1. : 0.;
+      mk[k] = mv;
+      tp[k] = mv * ((double)k + 1.0);
     });
-    mat_max(mp, S, St, vfp, tp, 0.1, thr.p);
-    parallel_for(n, [=] DEV(i64 i) {
-      const double d = ((double)i + 1.0) - mp[i];
-      const double mv = (mk[i] != 0. && d > 0.) ? 1. : 0.;
-      if (mv != 0.) vc[i] = 1.;
-      vfp[i] = ((vfp[i] == 0.) != (mv == 0.)) ? 1. : 0.;
+    // mask = mask & (id - mat_max(S, vf, mask.*id) > 0);  vc |= mask;  vf ^= mask
+    parallel_for(n, [=] DEV(i64 k) {
+      double m = -DBL_MAX;
+      if (vfp[k] != 0)
+        for (int p = tro[k]; p < tro[k + 1]; p++) {
+          const int i = tcol[p];
+          if (fabs(ta[p]) < thp[i]) continue;
+          if (tp[i] > m) m = tp[i];
+        }
+      const double d = ((double)k + 1.0) - m;
+      const double mv = (mk[k] != 0. && d > 0.) ? 1. : 0.;
+      if (mv != 0.) vc[k] = 1.;
+      w2p[k] = ((vfp[k] == 0.) != (mv == 0.)) ? 1. : 0.;     // next vf, applied after the kernel
     });
+    { double *t = vfp; vfp = w2p; w2p = t; }
     if (ctx().trace_on) {
       char t[64];
       snprintf(t, sizeof t, "coarsen.vc.r%d", rounds);
       trace_dev(t, vc, sizeof(double) * (size_t)n);
     }
-    if (rounds > 10000) throw Error(-7, "coarsen: no convergence");
+    if (rounds > 100000) throw Error(-7, "coarsen: no convergence");
   }
   return rounds;
 }

@@ -25,7 +25,7 @@ void trace_csr(const char *tag, const Csr &A) {
 template <int G>
 __global__ void __launch_bounds__(256) k_spmv_tile(int rn, const int *ro, const int *col, const double *vals,
                                                    const double *x, double *z, double alpha, const double *y,
-                                                   double beta, bool plain) {
+                                                   double beta, bool plain, const double *post) {
   const int i = blockIdx.x * (256 / G) + threadIdx.x / G;
   if (i >= rn) return;
   const int lane = threadIdx.x % G;
@@ -38,12 +38,16 @@ __global__ void __launch_bounds__(256) k_spmv_tile(int rn, const int *ro, const 
     const int m = min(G, end - base);
     for (int l = 0; l < m; l++) t = t + __shfl_sync(gmask, p, l, G);
   }
-  if (lane == 0) z[i] = plain ? beta * t : alpha * y[i] + beta * t;
+  if (lane == 0) {
+    double r = plain ? beta * t : alpha * y[i] + beta * t;
+    if (post) r = r * post[i];
+    z[i] = r;
+  }
 }
 #endif
 
 void spmv_vals(double *z, double alpha, const double *y, double beta, const Csr &M, const double *vals,
-               const double *x) {
+               const double *x, const double *post) {
   StageTimer st_("prim.spmv");
   const int *ro = M.ro.p, *col = M.col.p;
   const bool plain = (alpha == 0. || y == nullptr);
@@ -51,9 +55,9 @@ void spmv_vals(double *z, double alpha, const double *y, double beta, const Csr 
   if (M.rn > 0 && (double)M.nnz / (double)M.rn > 8.0) {
     Context &c = ctx();
     if ((double)M.nnz / (double)M.rn <= 64.0)
-      k_spmv_tile<8><<<(M.rn + 31) / 32, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain);
+      k_spmv_tile<8><<<(M.rn + 31) / 32, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post);
     else
-      k_spmv_tile<32><<<(M.rn + 7) / 8, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain);
+      k_spmv_tile<32><<<(M.rn + 7) / 8, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post);
     c.launches++; post_launch("spmv_tile");
     return;
   }
@@ -61,8 +65,9 @@ void spmv_vals(double *z, double alpha, const double *y, double beta, const Csr 
   parallel_for(M.rn, [=] DEV(i64 i) {
     double t = 0;
     for (int j = ro[i]; j < ro[i + 1]; j++) t = t + vals[j] * x[col[j]];
-    if (plain) z[i] = beta * t;
-    else z[i] = alpha * y[i] + beta * t;
+    double r = plain ? beta * t : alpha * y[i] + beta * t;
+    if (post) r = r * post[i];
+    z[i] = r;
   });
 }
 void spmv(double *z, double alpha, const double *y, double beta, const Csr &M, const double *x) {

@@ -29,7 +29,7 @@ struct Csr {
 void spmv(double *z, double alpha, const double *y, double beta, const Csr &M, const double *x);
 // values-only variant: same pattern as M, other value array
 void spmv_vals(double *z, double alpha, const double *y, double beta, const Csr &M, const double *vals,
-               const double *x);
+               const double *x, const double *post = nullptr);   // post != null: z[i] = (...) * post[i]
 
 // transpose :2000.  If tpos != null it receives, for every entry e of A, its position in A^t.
 Csr transpose(const Csr &A, Buf<int> *tpos = nullptr);

@@ -112,8 +112,10 @@ __device__ __forceinline__ void row_phase(const Group &g, int phase, int i, cons
   for (int q = g.thread_rank(); q < n; q += g.size()) { xcol[base + q] = keys[q]; xa[base + q] = vals[q]; }
 }
 
-// G-thread tiles, table in shared memory: HS slots per tile
-template <int G, int HS>
+// G-thread tiles, table in shared memory: HS slots per tile.  The few survivors (at most CAP) are
+// compacted into a list and ranked by column (rank = number of smaller columns), which is much
+// cheaper than sorting the whole table.
+template <int G, int HS, int CAP>
 __global__ void __launch_bounds__(256) k_spgemm_tile(int phase, const int *list, int nlist, const int *aro,
                                                      const int *acol, const double *aa, const int *bro,
                                                      const int *bcol, const double *ba, int *cnt, const int *xro,
@@ -121,13 +123,38 @@ __global__ void __launch_bounds__(256) k_spgemm_tile(int phase, const int *list,
   constexpr int PER = 256 / G;
   __shared__ int skeys[PER * HS];
   __shared__ double svals[PER * HS];
+  __shared__ int lkeys[PER * CAP];
+  __shared__ double lvals[PER * CAP];
   __shared__ int sred[PER];
   auto tile = cg::tiled_partition<G>(cg::this_thread_block());
   const int slot = threadIdx.x / G;
   const int idx = blockIdx.x * PER + slot;
   if (idx >= nlist) return;
-  row_phase(tile, phase, list[idx], aro, acol, aa, bro, bcol, ba, skeys + slot * HS, svals + slot * HS, HS,
-            sred + slot, cnt, xro, xcol, xa);
+  const int i = list[idx];
+  int *keys = skeys + slot * HS;
+  double *vals = svals + slot * HS;
+  accumulate_row(tile, i, aro, acol, aa, bro, bcol, ba, keys, vals, HS);
+  const int r0 = tile.thread_rank();
+  if (phase == 1) {
+    const int n = drop_zeros_count(tile, keys, vals, HS, sred + slot);
+    if (r0 == 0) cnt[i] = n;
+    return;
+  }
+  int *lk = lkeys + slot * CAP;
+  double *lv = lvals + slot * CAP;
+  if (r0 == 0) sred[slot] = 0;
+  tile.sync();
+  for (int h = r0; h < HS; h += G)
+    if (keys[h] != EMPTY && vals[h] != 0.0) { const int p = atomicAdd(&sred[slot], 1); lk[p] = keys[h]; lv[p] = vals[h]; }
+  tile.sync();
+  const int n = sred[slot];
+  const int base = xro[i];
+  for (int e = r0; e < n; e += G) {
+    const int key = lk[e];
+    int rank = 0;
+    for (int f = 0; f < n; f++) rank += (lk[f] < key);
+    xcol[base + rank] = key; xa[base + rank] = lv[e];
+  }
 }
 
 // one block per row, table in dynamic shared memory
@@ -499,11 +526,11 @@ Csr spgemm(const Csr &A, const Csr &B) {
     int *xcol = phase == 2 ? X.col.p : nullptr;
     double *xa = phase == 2 ? X.a.p : nullptr;
     if (hc[0]) {
-      k_spgemm_tile<8, 64><<<(hc[0] + 31) / 32, 256, 0, c.stream>>>(phase, L(0), hc[0], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+      k_spgemm_tile<8, 64, 24><<<(hc[0] + 31) / 32, 256, 0, c.stream>>>(phase, L(0), hc[0], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
       c.launches++; post_launch("spgemm_tile8");
     }
     if (hc[1]) {
-      k_spgemm_tile<32, 256><<<(hc[1] + 7) / 8, 256, 0, c.stream>>>(phase, L(1), hc[1], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+      k_spgemm_tile<32, 256, 96><<<(hc[1] + 7) / 8, 256, 0, c.stream>>>(phase, L(1), hc[1], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
       c.launches++; post_launch("spgemm_tile32");
     }
     if (hc[2]) {
