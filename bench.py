@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- AMG hierarchy setup time on B200 (BASELINE.json's headline metric).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload poisson7 --n 128]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload poisson7 --size 128]
 
 One "step" = one full hierarchy setup (amg_setup, amg_setup.c:60) of the workload.
   value   seconds per setup with the COO input already resident in HBM (device CUDA events
@@ -139,7 +139,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="poisson7")
-    ap.add_argument("--n", type=int, default=128)
+    ap.add_argument("--size", dest="n", type=int, default=128, help="grid points per side")
     ap.add_argument("--sample-n", type=int, default=40, help="grid size of the CPU baseline's bounded sample")
     ap.add_argument("--reduce", default="seq", choices=["seq", "tree"],
                     help="seq: reference-order dot products (bit-identical hierarchy); tree: fast mode")

@@ -1,0 +1,54 @@
+"""N > 1 launch contract on CPU (gloo, world_size 2).  The setup path does not shard in this round
+("replicas only", DESIGN.md row e): every rank runs its own setup and only the timing is reduced.
+What can be tested without a GPU is the launch protocol of bench.py's reference arm (rank 0
+prints one JSON line, the other ranks exit 0 without work) and the max-over-ranks reduction."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from util import ROOT
+
+
+def test_reference_arm_under_torchrun_world2():
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29631", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+           "--steps", "1", "--warmup", "0", "--size", "16", "--sample-n", "8"]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "amg_setup_time" and d["unit"] == "s"
+    assert d["higher_is_better"] is False and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # the reduction bench.py applies to its per-rank step times: MAX over ranks after a barrier
+    t = torch.tensor([1.0 + rank, 10.0 - rank], dtype=torch.float64)
+    dist.barrier()
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    q.put((rank, t.tolist()))
+    dist.destroy_process_group()
+
+
+def test_max_over_ranks_reduction_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker, args=(r, 2, 29632, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(60)
+        assert p.exitcode == 0
+    assert out[0][1] == [2.0, 10.0] and out[1][1] == [2.0, 10.0]
