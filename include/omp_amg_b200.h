@@ -83,6 +83,10 @@ enum { AMGB_REDUCE_TREE = 0, AMGB_REDUCE_SEQUENTIAL = 1 };
 int amgb_set_reduce_mode(int mode);
 int amgb_get_reduce_mode(void);
 
+/* diagnostics: sum_i a[i]*b[i] (b == NULL: sum_i a[i]) of HOST vectors with the library's
+ * reduction kernels; mode as above.  Mode 1 equals the plain left-to-right loop bit for bit. */
+int amgb_debug_dot(const double *a, const double *b, int64_t n, int mode, double *out);
+
 /* ---- stage trace (debug): FNV-1a hashes of intermediate arrays, in stage order ---- */
 void amgb_trace_enable(int on);
 int amgb_trace_count(void);

@@ -53,6 +53,7 @@ def _declare(L):
     L.amgb_solve_device.argtypes = [vp, vp, vp]
     L.amgb_timing.argtypes = [vp, C.POINTER(C.c_double)]
     L.amgb_set_reduce_mode.argtypes = [C.c_int]
+    L.amgb_debug_dot.argtypes = [f64p, C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_double)]
     L.amgb_trace_enable.argtypes = [C.c_int]
     L.amgb_trace_enable.restype = None
     L.amgb_trace_get.argtypes = [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]
@@ -91,6 +92,19 @@ def set_reduce_mode(mode, L=None):
     """0: parallel tree (fast); 1: left-to-right like the reference (bit-identical results)."""
     L = L or lib()
     _check(L, L.amgb_set_reduce_mode(int(mode)))
+
+
+def debug_dot(a, b=None, mode=REDUCE_SEQUENTIAL, L=None):
+    """The library's reduction kernel on host vectors (diagnostics / tests)."""
+    L = L or lib()
+    a = np.ascontiguousarray(a, np.float64)
+    out = C.c_double()
+    if b is None:
+        _check(L, L.amgb_debug_dot(a, None, len(a), mode, C.byref(out)))
+    else:
+        b = np.ascontiguousarray(b, np.float64)
+        _check(L, L.amgb_debug_dot(a, b.ctypes.data, len(a), mode, C.byref(out)))
+    return out.value
 
 
 def build_info(L=None):

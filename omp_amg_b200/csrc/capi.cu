@@ -291,6 +291,18 @@ int amgb_set_reduce_mode(int mode) {
 }
 int amgb_get_reduce_mode(void) { return ctx().reduce_seq; }
 
+// diagnostics: the library's dot product on host vectors (mode 0 tree, 1 sequential order)
+int amgb_debug_dot(const double *a, const double *b, int64_t n, int mode, double *out) {
+  API_BEGIN
+  ctx_init(-1);
+  Buf<double> da(n), db(n);
+  da.upload(a, n);
+  if (b) db.upload(b, n);
+  *out = mode ? seq_dot(da.p, b ? db.p : nullptr, n) : tree_dot(da.p, b ? db.p : da.p, n);
+  return 0;
+  API_END
+}
+
 void amgb_trace_enable(int on) { ctx().trace_on = on != 0; ctx().trace.clear(); }
 int amgb_trace_count(void) { return (int)ctx().trace.size(); }
 int amgb_trace_get(int i, char *tag, int taglen, uint64_t *hash, int64_t *bytes) {

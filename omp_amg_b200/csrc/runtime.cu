@@ -226,11 +226,191 @@ __global__ void __launch_bounds__(1024) k_seq_dot(const double *a, const double 
   }
   if (t == 0) *out = r;
 }
+// ---------------------------------------------------------------------------------------
+// Exact left-to-right sum in parallel.
+//
+// The reference adds the terms one by one, rounding after every addition.  While the running
+// sum s stays inside one binade (same sign, same exponent e, ulp u = 2^(e-52)) every step is
+//     S' = S + r(x),  S = |s|/u (a 53-bit integer),  x = (+-p)/u,
+// where r(x) is x rounded to the nearest integer -- independent of S -- except for exact ties
+// (fractional part 1/2), which go to the even result and therefore depend on the PARITY of S only.
+// So a chunk of terms is reduced by (1) per-term integer/fraction split of x, (2) a scan over the
+// two-state parity automaton (a tie resets the parity to even, any other term xors it with its
+// increment), (3) an integer prefix sum.  The first term at which the running sum could leave the
+// binade (or is not finite/normal) ends the chunk: everything before it is exact, that term and a
+// short adaptive burst after it are added the plain way by one thread, and the next chunk starts
+// in the new binade.  For the sums this library needs (norms, r'z, p'Ap: essentially positive
+// terms) such events are O(log n), so the cost is ~n/8192 block-wide scans instead of n dependent
+// additions; in the worst case (a sum hovering around zero) it degrades to the plain chain.
+// The result is bit-identical to the sequential loop for every input (tests/test_gpu_parity.py).
+// ---------------------------------------------------------------------------------------
+#define EPS_T 1024
+#define EPS_E 8
+#define EPS_BURST_MAX 2048
+struct ParFn { unsigned char reset, x; };   // parity_out = reset ? x : parity_in ^ x
+__device__ __forceinline__ ParFn par_compose(ParFn f, ParFn g) {   // apply f, then g
+  ParFn r;
+  r.reset = f.reset | g.reset;
+  r.x = g.reset ? g.x : (unsigned char)(f.x ^ g.x);
+  return r;
+}
+// split x = sg * |p| / 2^se: fl = floor(x), up = 1 if frac > 1/2, tie = 1 if frac == 1/2, bad = cannot
+__device__ __forceinline__ void eps_split(double p, int ssign, int se, long long &fl, int &up, int &tie, int &bad) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(p);
+  const int ex = (int)((bits >> 52) & 0x7ff);
+  unsigned long long pm = bits & 0xfffffffffffffULL;
+  fl = 0; up = 0; tie = 0; bad = 0;
+  if (ex == 0x7ff) { bad = 1; return; }
+  int pe;
+  if (ex == 0) { pe = -1074; } else { pm |= (1ULL << 52); pe = ex - 1075; }
+  if (pm == 0) return;
+  const int sg = ((bits >> 63) ? -1 : 1) * ssign;
+  const int sh = se - pe;
+  if (sh <= 0) {
+    if (-sh > 9) { bad = 1; return; }
+    const long long I = (long long)(pm << (-sh));
+    fl = sg > 0 ? I : -I;
+    return;
+  }
+  if (sh > 63) { if (sg < 0) { fl = -1; up = 1; } return; }
+  const unsigned long long I = (sh >= 64) ? 0ULL : (pm >> sh);
+  const unsigned long long F = pm & ((1ULL << sh) - 1ULL), half = 1ULL << (sh - 1);
+  if (sg > 0) {
+    fl = (long long)I;
+    if (F > half) up = 1; else if (F == half) tie = 1;
+  } else if (F == 0) {
+    fl = -(long long)I;
+  } else {
+    fl = -(long long)I - 1;
+    const unsigned long long G = (1ULL << sh) - F;
+    if (G > half) up = 1; else if (G == half) tie = 1;
+  }
+}
+__global__ void __launch_bounds__(EPS_T) k_eps_dot(const double *a, const double *b, i64 n, double *out) {
+  __shared__ double s_sh;
+  __shared__ i64 pos_sh;
+  __shared__ int burst_sh, need_serial_sh, vmin_sh;
+  __shared__ long long Sv_sh;
+  __shared__ double prod[EPS_BURST_MAX];
+  __shared__ ParFn pf[EPS_T];
+  __shared__ long long ls[EPS_T];
+  const int t = threadIdx.x;
+  if (t == 0) { s_sh = 0.0; pos_sh = 0; burst_sh = 16; need_serial_sh = 1; }
+  __syncthreads();
+  while (true) {
+    const i64 pos = pos_sh;
+    if (pos >= n) break;
+    const double s = s_sh;
+    const unsigned long long sbits = (unsigned long long)__double_as_longlong(s);
+    const int sex = (int)((sbits >> 52) & 0x7ff);
+    const bool s_ok = (sex != 0 && sex != 0x7ff);           // normal, non-zero, finite
+    if (need_serial_sh || !s_ok) {
+      // plain chain for a short burst: products staged by all threads, added by thread 0
+      const int cntb = (int)((n - pos < burst_sh) ? (n - pos) : burst_sh);
+      for (int j = t; j < cntb; j += EPS_T) prod[j] = b ? __dmul_rn(a[pos + j], b[pos + j]) : a[pos + j];
+      __syncthreads();
+      if (t == 0) {
+        double r = s;
+        for (int j = 0; j < cntb; j++) r = __dadd_rn(r, prod[j]);
+        s_sh = r; pos_sh = pos + cntb; need_serial_sh = 0;
+      }
+      __syncthreads();
+      continue;
+    }
+    const int ssign = (sbits >> 63) ? -1 : 1;
+    const int se = sex - 1075;
+    const long long S0 = (long long)((sbits & 0xfffffffffffffULL) | (1ULL << 52));
+    // ---- per-term split ----
+    long long fl[EPS_E];
+    int up[EPS_E], tie[EPS_E], bad[EPS_E];
+    const i64 base = pos + (i64)t * EPS_E;
+    ParFn mine; mine.reset = 0; mine.x = 0;
+#pragma unroll
+    for (int k = 0; k < EPS_E; k++) {
+      const i64 j = base + k;
+      if (j < n) {
+        const double p = b ? __dmul_rn(a[j], b[j]) : a[j];
+        eps_split(p, ssign, se, fl[k], up[k], tie[k], bad[k]);
+      } else { fl[k] = 0; up[k] = 0; tie[k] = 0; bad[k] = 0; }
+      ParFn e;
+      e.reset = (unsigned char)tie[k];
+      e.x = tie[k] ? 0 : (unsigned char)((fl[k] + up[k]) & 1);
+      mine = par_compose(mine, e);
+    }
+    // ---- exclusive scan of the parity functions over threads (Hillis-Steele in shared memory) ----
+    pf[t] = mine;
+    __syncthreads();
+    for (int off = 1; off < EPS_T; off <<= 1) {
+      ParFn v = pf[t];
+      if (t >= off) v = par_compose(pf[t - off], v);
+      __syncthreads();
+      pf[t] = v;
+      __syncthreads();
+    }
+    int par = (int)(S0 & 1);
+    if (t > 0) { const ParFn f = pf[t - 1]; par = f.reset ? f.x : (par ^ f.x); }
+    // ---- increments with the tie decision, local sums ----
+    long long c[EPS_E], lsum = 0;
+#pragma unroll
+    for (int k = 0; k < EPS_E; k++) {
+      long long ck = fl[k] + up[k];
+      if (tie[k]) { ck += ((par + fl[k]) & 1); par = 0; }
+      else par ^= (int)(ck & 1);
+      if (bad[k]) ck = 0;
+      c[k] = ck; lsum += ck;
+    }
+    ls[t] = lsum;
+    __syncthreads();
+    for (int off = 1; off < EPS_T; off <<= 1) {
+      long long v = ls[t];
+      if (t >= off) v += ls[t - off];
+      __syncthreads();
+      ls[t] = v;
+      __syncthreads();
+    }
+    long long S = S0 + (t > 0 ? ls[t - 1] : 0);
+    // ---- first term that may leave the binade ----
+    if (t == 0) vmin_sh = EPS_T * EPS_E;
+    __syncthreads();
+    long long Sbefore[EPS_E + 1];
+    int myv = -1;
+#pragma unroll
+    for (int k = 0; k < EPS_E; k++) {
+      Sbefore[k] = S;
+      const i64 j = base + k;
+      if (myv < 0 && (j >= n || bad[k] || S + fl[k] < (1LL << 52) || S + fl[k] + 1 >= (1LL << 53))) myv = k;
+      S += c[k];
+    }
+    Sbefore[EPS_E] = S;
+    if (myv >= 0) atomicMin(&vmin_sh, t * EPS_E + myv);
+    __syncthreads();
+    const int v = vmin_sh;                                   // accepted terms: [pos, pos+v)
+    if (v == EPS_T * EPS_E) { if (t == EPS_T - 1) Sv_sh = Sbefore[EPS_E]; }
+    else if (v / EPS_E == t) Sv_sh = Sbefore[v % EPS_E];
+    __syncthreads();
+    if (t == 0) {
+      const unsigned long long m = (unsigned long long)Sv_sh;
+      const unsigned long long nb = ((unsigned long long)(ssign < 0) << 63) | ((unsigned long long)(se + 1075) << 52) |
+                                    (m & 0xfffffffffffffULL);
+      s_sh = __longlong_as_double((long long)nb);
+      pos_sh = pos + v;
+      const bool hit = (pos + v < n) && (v < EPS_T * EPS_E);
+      need_serial_sh = hit ? 1 : 0;
+      if (hit) burst_sh = (v < 256) ? min(burst_sh * 2, EPS_BURST_MAX) : max(16, burst_sh / 2);
+    }
+    __syncthreads();
+  }
+  if (t == 0) *out = s_sh;
+}
+static int g_eps = -1;
+
 double seq_dot(const double *a, const double *b, i64 n) {
   if (n <= 0) return 0.0;
   StageTimer st_("prim.seq_dot");
   Buf<double> out(1);
-  k_seq_dot<<<1, 1024, 0, g_ctx.stream>>>(a, b, n, out.p);
+  if (g_eps < 0) { const char *e = getenv("AMGB_SEQDOT"); g_eps = (e && !strcmp(e, "chain")) ? 0 : 1; }
+  if (g_eps) k_eps_dot<<<1, EPS_T, 0, g_ctx.stream>>>(a, b, n, out.p);
+  else k_seq_dot<<<1, 1024, 0, g_ctx.stream>>>(a, b, n, out.p);
   g_ctx.launches++; post_launch(__func__);
   return out.get(0);
 }

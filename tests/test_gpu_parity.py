@@ -157,3 +157,37 @@ def test_size_independent_properties(L, name, n):
         assert (lev["D"] > 0).all() and 0 <= lev["rho"] < 1 and lev["m"] >= 1
     H2 = amg.amg_setup(*mat, L=L)
     assert orc.compare(fetch(H2), g) == []
+
+
+def _seq(p):
+    return float(np.add.accumulate(np.asarray(p, np.float64))[-1])     # strictly left to right
+
+
+def test_sequential_reduction_kernel_is_exact(L):
+    """The parallel left-to-right sum (runtime.cu: k_eps_dot) must equal the plain loop bit for
+    bit on friendly and on adversarial inputs: ties, binade crossings, cancellation, wide ranges,
+    sums hovering around zero, denormals, non-finite values."""
+    rng = np.random.default_rng(0)
+    cases = {
+        "squares": rng.standard_normal(300001) ** 2,
+        "signed": rng.standard_normal(100003),
+        "wide_signed": rng.standard_normal(50000) * 10.0 ** rng.uniform(-8, 8, 50000),
+        "wide_positive": np.abs(rng.standard_normal(200000)) * 10.0 ** rng.uniform(-12, 3, 200000),
+        "quarter_ties": rng.integers(-8, 9, 60000) * 0.25,
+        "ints_plus_ones": rng.integers(1, 1 << 20, 100000) * 2.0 ** -30 + 1.0 * (rng.random(100000) < 0.01),
+        "half_ulp_ties": np.concatenate([[1.0], rng.integers(-3, 4, 100000) * 2.0 ** -53]),
+        "ties_at_2p52": np.concatenate([[2.0 ** 52], rng.integers(-3, 4, 50000) * 0.5]),
+        "cancel": np.concatenate([[1.0, -1.0], rng.standard_normal(1000)]),
+        "tenth": np.full(1000000, 0.1),
+        "palindrome": (lambda x: np.concatenate([x, -x[::-1]]))(rng.standard_normal(40000)),
+        "denormals": rng.integers(-5, 6, 5000) * 5e-324,
+        "tiny": np.array([3.0]), "empty_like": np.zeros(17),
+        "with_inf": np.concatenate([rng.standard_normal(100), [np.inf], rng.standard_normal(100)]),
+    }
+    for name, p in cases.items():
+        got = api.debug_dot(p, None, api.REDUCE_SEQUENTIAL, L=L)
+        want = _seq(p)
+        assert got == want or (np.isnan(got) and np.isnan(want)), (name, got, want)
+    a = rng.standard_normal(1 << 20); b = a * rng.uniform(0.5, 1.5, 1 << 20)
+    assert api.debug_dot(a, b, api.REDUCE_SEQUENTIAL, L=L) == _seq(a * b)
+    assert api.debug_dot(a, a, api.REDUCE_SEQUENTIAL, L=L) == _seq(a * a)
