@@ -72,6 +72,12 @@ int amgb_solve_device(const amgb_hier *h, double *dx, const double *db);      /*
  * t[12]=CUDA-event seconds from the first to the last kernel of the setup  t[13..15] reserved */
 int amgb_timing(const amgb_hier *h, double t[16]);
 
+/* ---- device memory ----
+ * Temporaries come from a caching allocator inside the library; amgb_release_memory() hands the
+ * cached (free) blocks back to the driver, amgb_peak_device_bytes() is the high-water mark. */
+void amgb_release_memory(void);
+int64_t amgb_peak_device_bytes(void);
+
 /* ---- arithmetic mode of the vector-length reductions (dot products, 2-norms) ----
  * AMGB_REDUCE_SEQUENTIAL (default): summed left to right like the reference's vv_dot
  *   (amg_setup.c:3193); the hierarchy is then bit-identical to the reference's.

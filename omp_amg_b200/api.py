@@ -53,6 +53,8 @@ def _declare(L):
     L.amgb_solve_device.argtypes = [vp, vp, vp]
     L.amgb_timing.argtypes = [vp, C.POINTER(C.c_double)]
     L.amgb_set_reduce_mode.argtypes = [C.c_int]
+    L.amgb_release_memory.restype = None
+    L.amgb_peak_device_bytes.restype = C.c_int64
     L.amgb_debug_dot.argtypes = [f64p, C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_double)]
     L.amgb_trace_enable.argtypes = [C.c_int]
     L.amgb_trace_enable.restype = None

@@ -284,6 +284,9 @@ int amgb_timing(const amgb_hier *h, double t[16]) {
   return 0;
 }
 
+void amgb_release_memory(void) { dev_release_cache(); }
+int64_t amgb_peak_device_bytes(void) { return (int64_t)dev_peak_bytes(); }
+
 int amgb_set_reduce_mode(int mode) {
   if (mode != 0 && mode != 1) return fail(-2, "reduce mode must be 0 (tree) or 1 (sequential)");
   ctx().reduce_seq = mode;

@@ -78,6 +78,8 @@ void post_launch(const char *what);
 // ---------------------------------------------------------------------------------------
 void *dev_alloc(size_t bytes);
 void dev_free(void *p);
+void dev_release_cache();      // hand cached blocks back to the driver
+size_t dev_peak_bytes();       // high-water mark of live device memory
 void dev_memset(void *p, int v, size_t bytes);
 void h2d(void *dst, const void *src, size_t bytes);
 void d2h(void *dst, const void *src, size_t bytes);   // synchronises the stream

@@ -42,12 +42,67 @@ void ctx_init(int device) {
   CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
   g_inited = true;
 }
+// Device memory: a caching allocator over cudaMalloc.  A setup makes ~10^5 allocations whose sizes
+// repeat from level to level and from setup to setup; the stream-ordered pool of the driver
+// re-maps physical memory when it fragments, which showed up as 10x run-to-run swings in kernels
+// that allocate several large temporaries (transpose).  Blocks are rounded up to 1/8-octave size
+// classes and kept in per-class free lists; all work is on one stream, so a freed block may be
+// handed out again immediately.  AMGB_ALLOC=async selects the driver pool instead.
+static std::multimap<size_t, void *> g_free_blocks;
+static std::map<void *, size_t> g_block_size;
+static size_t g_cached_bytes = 0, g_live_bytes = 0, g_peak_bytes = 0;
+static int g_alloc_async = -1;
+static size_t size_class(size_t b) {
+  if (b < 512) return 512;
+  size_t p = 512;
+  while (p * 2 <= b) p *= 2;               // p <= b < 2p
+  const size_t step = p / 8;
+  return ((b + step - 1) / step) * step;
+}
+void dev_release_cache() {
+  for (auto &kv : g_free_blocks) { cudaFree(kv.second); g_block_size.erase(kv.second); }
+  g_free_blocks.clear();
+  g_cached_bytes = 0;
+}
 void *dev_alloc(size_t bytes) {
+  if (g_alloc_async < 0) { const char *e = getenv("AMGB_ALLOC"); g_alloc_async = (e && !strcmp(e, "async")) ? 1 : 0; }
   void *p = nullptr;
-  CUDA_CHECK(cudaMallocAsync(&p, bytes ? bytes : 8, g_ctx.stream));
+  if (g_alloc_async) {
+    CUDA_CHECK(cudaMallocAsync(&p, bytes ? bytes : 8, g_ctx.stream));
+    return p;
+  }
+  const size_t sz = size_class(bytes ? bytes : 8);
+  auto it = g_free_blocks.find(sz);
+  if (it != g_free_blocks.end()) {
+    p = it->second;
+    g_free_blocks.erase(it);
+    g_cached_bytes -= sz;
+  } else {
+    cudaError_t e = cudaMalloc(&p, sz);
+    if (e != cudaSuccess) {                 // give the cache back to the driver and retry once
+      cudaGetLastError();
+      CUDA_CHECK(cudaStreamSynchronize(g_ctx.stream));
+      dev_release_cache();
+      e = cudaMalloc(&p, sz);
+      if (e != cudaSuccess)
+        throw Error(-102, std::string("out of device memory allocating ") + std::to_string(sz) + " bytes");
+    }
+    g_block_size[p] = sz;
+  }
+  g_live_bytes += sz;
+  if (g_live_bytes > g_peak_bytes) g_peak_bytes = g_live_bytes;
   return p;
 }
-void dev_free(void *p) { if (p) cudaFreeAsync(p, g_ctx.stream); }
+void dev_free(void *p) {
+  if (!p) return;
+  if (g_alloc_async) { cudaFreeAsync(p, g_ctx.stream); return; }
+  auto it = g_block_size.find(p);
+  if (it == g_block_size.end()) { cudaFree(p); return; }
+  g_free_blocks.emplace(it->second, p);
+  g_cached_bytes += it->second;
+  g_live_bytes -= it->second;
+}
+size_t dev_peak_bytes() { return g_peak_bytes; }
 void dev_memset(void *p, int v, size_t bytes) { if (bytes) CUDA_CHECK(cudaMemsetAsync(p, v, bytes, g_ctx.stream)); }
 void h2d(void *dst, const void *src, size_t bytes) {
   if (bytes) CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_ctx.stream));
@@ -547,6 +602,8 @@ void ctx_init(int) {}
 void post_launch(const char *) {}
 void *dev_alloc(size_t bytes) { void *p = malloc(bytes ? bytes : 8); if (!p) throw Error(-2, "out of memory"); return p; }
 void dev_free(void *p) { free(p); }
+void dev_release_cache() {}
+size_t dev_peak_bytes() { return 0; }
 void dev_memset(void *p, int v, size_t bytes) { memset(p, v, bytes); }
 void h2d(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); }
 void d2h(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); g_ctx.syncs++; }
