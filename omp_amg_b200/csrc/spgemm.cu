@@ -34,6 +34,22 @@ struct BlockGroup {
 
 __device__ __forceinline__ unsigned hash_col(int c) { return (unsigned)c * 2654435761u; }
 
+// Fused mode (phase 3): the row is counted AND written in one pass.  Its place is not known yet
+// (the row offsets come from a scan over all counts), so the sorted row goes to an arena at an
+// offset taken from an atomic bump pointer and is copied to its final place afterwards.  If the
+// arena is too small the row only reports its count and the classic second pass redoes the work.
+struct Arena {
+  int *cols; double *vals; unsigned long long *top; long long cap; long long *roff; int *ovf;
+};
+// called by ONE thread of the row's group once the survivor count n is known
+__device__ __forceinline__ long long arena_claim(const Arena &ar, int i, int n, int *cnt) {
+  cnt[i] = n;
+  const unsigned long long off = atomicAdd(ar.top, (unsigned long long)n);
+  if ((long long)(off + (unsigned long long)n) > ar.cap) { *ar.ovf = 1; ar.roff[i] = -1; return -1; }
+  ar.roff[i] = (long long)off;
+  return (long long)off;
+}
+
 // accumulate row i of A*B into the table (keys, vals) of HS slots (power of two)
 template <class Group>
 __device__ __forceinline__ void accumulate_row(const Group &g, int i, const int *aro, const int *acol,
@@ -103,12 +119,19 @@ template <class Group>
 __device__ __forceinline__ void row_phase(const Group &g, int phase, int i, const int *aro, const int *acol,
                                           const double *aa, const int *bro, const int *bcol, const double *ba,
                                           int *keys, double *vals, int HS, int *red, int *cnt, const int *xro,
-                                          int *xcol, double *xa) {
+                                          int *xcol, double *xa, const Arena &ar, long long *sbase) {
   accumulate_row(g, i, aro, acol, aa, bro, bcol, ba, keys, vals, HS);
   const int n = drop_zeros_count(g, keys, vals, HS, red);
   if (phase == 1) { if (g.thread_rank() == 0) cnt[i] = n; return; }
+  long long base = xro ? xro[i] : 0;
+  if (phase == 3) {
+    if (g.thread_rank() == 0) *sbase = arena_claim(ar, i, n, cnt);
+    g.sync();
+    base = *sbase;
+    if (base < 0) return;
+    xcol = ar.cols; xa = ar.vals;
+  }
   bitonic_sort(g, keys, vals, HS);
-  const int base = xro[i];
   for (int q = g.thread_rank(); q < n; q += g.size()) { xcol[base + q] = keys[q]; xa[base + q] = vals[q]; }
 }
 
@@ -119,13 +142,14 @@ template <int G, int HS, int CAP>
 __global__ void __launch_bounds__(256) k_spgemm_tile(int phase, const int *list, int nlist, const int *aro,
                                                      const int *acol, const double *aa, const int *bro,
                                                      const int *bcol, const double *ba, int *cnt, const int *xro,
-                                                     int *xcol, double *xa) {
+                                                     int *xcol, double *xa, Arena ar) {
   constexpr int PER = 256 / G;
   __shared__ int skeys[PER * HS];
   __shared__ double svals[PER * HS];
   __shared__ int lkeys[PER * CAP];
   __shared__ double lvals[PER * CAP];
   __shared__ int sred[PER];
+  __shared__ long long sbase[PER];
   auto tile = cg::tiled_partition<G>(cg::this_thread_block());
   const int slot = threadIdx.x / G;
   const int idx = blockIdx.x * PER + slot;
@@ -148,7 +172,14 @@ __global__ void __launch_bounds__(256) k_spgemm_tile(int phase, const int *list,
     if (keys[h] != EMPTY && vals[h] != 0.0) { const int p = atomicAdd(&sred[slot], 1); lk[p] = keys[h]; lv[p] = vals[h]; }
   tile.sync();
   const int n = sred[slot];
-  const int base = xro[i];
+  long long base = xro ? xro[i] : 0;
+  if (phase == 3) {
+    if (r0 == 0) sbase[slot] = arena_claim(ar, i, n, cnt);
+    tile.sync();
+    base = sbase[slot];
+    if (base < 0) return;
+    xcol = ar.cols; xa = ar.vals;
+  }
   for (int e = r0; e < n; e += G) {
     const int key = lk[e];
     int rank = 0;
@@ -157,31 +188,19 @@ __global__ void __launch_bounds__(256) k_spgemm_tile(int phase, const int *list,
   }
 }
 
-// one block per row, table in dynamic shared memory
-__global__ void k_spgemm_block(int phase, int HS, const int *list, int nlist, const int *aro, const int *acol,
-                               const double *aa, const int *bro, const int *bcol, const double *ba, int *cnt,
-                               const int *xro, int *xcol, double *xa) {
-  extern __shared__ double dsm[];
-  __shared__ int sred;
-  double *svals = dsm;
-  int *skeys = (int *)(dsm + HS);
-  if ((int)blockIdx.x >= nlist) return;
-  BlockGroup g;
-  row_phase(g, phase, list[blockIdx.x], aro, acol, aa, bro, bcol, ba, skeys, svals, HS, &sred, cnt, xro, xcol, xa);
-}
-
 // one block per row, table in HBM (rows whose bound exceeds the shared-memory bins)
 __global__ void k_spgemm_global(int phase, const int *list, int nlist, const i64 *toff, int *gkeys, double *gvals,
                                 const int *aro, const int *acol, const double *aa, const int *bro,
                                 const int *bcol, const double *ba, int *cnt, const int *xro, int *xcol,
-                                double *xa) {
+                                double *xa, Arena ar) {
   __shared__ int sred;
+  __shared__ long long sbase;
   if ((int)blockIdx.x >= nlist) return;
   const i64 base = toff[blockIdx.x];
   const int HS = (int)(toff[blockIdx.x + 1] - base);
   BlockGroup g;
   row_phase(g, phase, list[blockIdx.x], aro, acol, aa, bro, bcol, ba, gkeys + base, gvals + base, HS, &sred, cnt,
-            xro, xcol, xa);
+            xro, xcol, xa, ar, &sbase);
 }
 
 // ---- block-wide exclusive scan of one int per thread (blockDim.x <= 256) ----
@@ -208,10 +227,11 @@ __global__ void __launch_bounds__(256) k_spgemm_dense(int phase, const int *cmin
                                                       const int *list, int nlist,
                                                       const int *aro, const int *acol, const double *aa,
                                                       const int *bro, const int *bcol, const double *ba, int *cnt,
-                                                      const int *xro, int *xcol, double *xa) {
+                                                      const int *xro, int *xcol, double *xa, Arena ar) {
   extern __shared__ double acc[];
   __shared__ int stmp[256];
   __shared__ int stotal;
+  __shared__ long long sbase;
   if ((int)blockIdx.x >= nlist) return;
   const int i = list[blockIdx.x];
   const int cmin = cminv[i], cn = spanv[i];     // the row only touches columns [cmin, cmin+cn)
@@ -254,7 +274,15 @@ __global__ void __launch_bounds__(256) k_spgemm_dense(int phase, const int *cmin
   for (int c = c0; c < c1; c++) mine += (acc[c] != 0.0);
   const int off = block_excl_scan(mine, stmp, &stotal);
   if (phase == 1) { if (t == 0) cnt[i] = stotal; return; }
-  int p = xro[i] + off;
+  long long rowbase = xro ? xro[i] : 0;
+  if (phase == 3) {
+    if (t == 0) sbase = arena_claim(ar, i, stotal, cnt);
+    __syncthreads();
+    rowbase = sbase;
+    if (rowbase < 0) return;
+    xcol = ar.cols; xa = ar.vals;
+  }
+  long long p = rowbase + off;
   for (int c = c0; c < c1; c++) if (acc[c] != 0.0) { xcol[p] = c + cmin; xa[p] = acc[c]; p++; }
 }
 
@@ -264,21 +292,22 @@ __global__ void __launch_bounds__(256) k_spgemm_dense(int phase, const int *cmin
 // whose bound (sum of B row lengths) is large but whose number of distinct columns is usually
 // small: the warp counts its insertions and gives the row up once the table is 3/4 full; such
 // rows are collected in `overflow` and redone by the dense block kernel.
-template <int HS, int WORDS>
-__global__ void __launch_bounds__(128) k_spgemm_warp_bitmap(int phase, const int *cminv, const int *spanv,
+template <int HS, int WORDS, int WPB>
+__global__ void __launch_bounds__(WPB * 32) k_spgemm_warp_bitmap(int phase, const int *cminv, const int *spanv,
                                                             const int *list, int nlist, const int *aro,
                                                             const int *acol, const double *aa, const int *bro,
                                                             const int *bcol, const double *ba, int *cnt,
                                                             const int *xro, int *xcol, double *xa,
-                                                            int *overflow, int *noverflow, const int *skip) {
+                                                            int *overflow, int *noverflow, const int *tier,
+                                                            int mytier, Arena ar) {
   extern __shared__ double wsm[];
   // per warp: svals[HS] | skeys[HS] | bits[WORDS] | wpre[WORDS] (ushort)
   constexpr int PER_BYTES = HS * 12 + WORDS * 4 + WORDS * 2;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int idx = blockIdx.x * 4 + w;
+  const int idx = blockIdx.x * WPB + w;
   if (idx >= nlist) return;
   const int i = list[idx];
-  if (skip && skip[i]) return;              // phase 2: rows that overflowed in phase 1
+  if (tier && tier[i] != mytier) return;    // phase 2: only the rows this table size completed
   char *basep = (char *)wsm + (size_t)w * PER_BYTES;
   double *svals = (double *)basep;
   int *skeys = (int *)(basep + HS * 8);
@@ -341,6 +370,14 @@ __global__ void __launch_bounds__(128) k_spgemm_warp_bitmap(int phase, const int
     if (skeys[h] != EMPTY) { if (svals[h] == 0.0) skeys[h] = EMPTY; else n++; }
   n = __reduce_add_sync(0xffffffffu, n);
   if (phase == 1) { if (lane == 0) cnt[i] = n; return; }
+  long long base = xro ? xro[i] : 0;
+  if (phase == 3) {
+    long long bb = 0;
+    if (lane == 0) bb = arena_claim(ar, i, n, cnt);
+    base = __shfl_sync(0xffffffffu, bb, 0);
+    if (base < 0) return;
+    xcol = ar.cols; xa = ar.vals;
+  }
   const int cmin = cminv[i];
   const int nw = (spanv[i] + 31) / 32;
   for (int q = lane; q < nw; q += 32) bits[q] = 0u;
@@ -356,7 +393,6 @@ __global__ void __launch_bounds__(128) k_spgemm_warp_bitmap(int phase, const int
   int run = incl - mine;
   for (int q = w0; q < w1; q++) { wpre[q] = (unsigned short)run; run += __popc(bits[q]); }
   __syncwarp();
-  const int base = xro[i];
   for (int h = lane; h < HS; h += 32) {
     const int c = skeys[h];
     if (c == EMPTY) continue;
@@ -374,10 +410,11 @@ __global__ void __launch_bounds__(256) k_spgemm_bitmap(int phase, int HS_smem, i
                                                        const i64 *toff, int *gkeys, double *gvals,
                                                        const int *aro, const int *acol, const double *aa,
                                                        const int *bro, const int *bcol, const double *ba,
-                                                       int *cnt, const int *xro, int *xcol, double *xa) {
+                                                       int *cnt, const int *xro, int *xcol, double *xa, Arena ar) {
   extern __shared__ double dsm[];
   __shared__ int sred;
   __shared__ int stmp[256];
+  __shared__ long long sbase;
   if ((int)blockIdx.x >= nlist) return;
   const int i = list[blockIdx.x];
   int HS;
@@ -395,6 +432,14 @@ __global__ void __launch_bounds__(256) k_spgemm_bitmap(int phase, int HS_smem, i
   accumulate_row(g, i, aro, acol, aa, bro, bcol, ba, skeys, svals, HS);
   const int n = drop_zeros_count(g, skeys, svals, HS, &sred);
   if (phase == 1) { if (threadIdx.x == 0) cnt[i] = n; return; }
+  long long base = xro ? xro[i] : 0;
+  if (phase == 3) {
+    if (threadIdx.x == 0) sbase = arena_claim(ar, i, n, cnt);
+    __syncthreads();
+    base = sbase;
+    if (base < 0) return;
+    xcol = ar.cols; xa = ar.vals;
+  }
   const int cmin = cminv[i];
   const int nw = (spanv[i] + 31) / 32;
   const int t = threadIdx.x, T = blockDim.x;
@@ -409,7 +454,6 @@ __global__ void __launch_bounds__(256) k_spgemm_bitmap(int phase, int HS_smem, i
   int run = block_excl_scan(mine, stmp, nullptr);
   for (int w = w0; w < w1; w++) { wpre[w] = run; run += __popc(bits[w]); }
   __syncthreads();
-  const int base = xro[i];
   for (int h = t; h < HS; h += T) {
     const int c = skeys[h];
     if (c == EMPTY) continue;
@@ -417,6 +461,16 @@ __global__ void __launch_bounds__(256) k_spgemm_bitmap(int phase, int HS_smem, i
     const int rank = wpre[d >> 5] + __popc(bits[d >> 5] & ((1u << (d & 31)) - 1u));
     xcol[base + rank] = c; xa[base + rank] = svals[h];
   }
+}
+template <int G>
+__global__ void __launch_bounds__(256) k_arena_copy(int rn, const int *xro, const long long *roff, const int *acols,
+                                                    const double *avals, int *xcol, double *xa) {
+  const int i = blockIdx.x * (256 / G) + threadIdx.x / G;
+  if (i >= rn) return;
+  const int lane = threadIdx.x % G;
+  const int b = xro[i], n = xro[i + 1] - b;
+  const long long o = roff[i];
+  for (int q = lane; q < n; q += G) { xcol[b + q] = acols[o + q]; xa[b + q] = avals[o + q]; }
 }
 }  // namespace
 
@@ -512,70 +566,124 @@ Csr spgemm(const Csr &A, const Csr &B) {
   if (!attr) {
     CUDA_CHECK(cudaFuncSetAttribute((const void *)k_spgemm_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, 24576 * 8));
     CUDA_CHECK(cudaFuncSetAttribute((const void *)k_spgemm_bitmap, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
-    CUDA_CHECK(cudaFuncSetAttribute((const void *)k_spgemm_warp_bitmap<512, 1016>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (512 * 12 + 1016 * 6)));
-    CUDA_CHECK(cudaFuncSetAttribute((const void *)k_spgemm_warp_bitmap<1024, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (1024 * 12 + 768 * 6)));
+    CUDA_CHECK(cudaFuncSetAttribute((const void *)k_spgemm_warp_bitmap<512, 1016, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (512 * 12 + 1016 * 6)));
+    CUDA_CHECK(cudaFuncSetAttribute((const void *)k_spgemm_warp_bitmap<1024, 768, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (1024 * 12 + 768 * 6)));
+    CUDA_CHECK(cudaFuncSetAttribute((const void *)k_spgemm_warp_bitmap<2048, 768, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (2048 * 12 + 768 * 6)));
+    CUDA_CHECK(cudaFuncSetAttribute((const void *)k_spgemm_warp_bitmap<4096, 768, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 12 + 768 * 6));
     attr = true;
   }
   auto words = [](int span) { return (span + 31) / 32; };
   auto L = [&](int bin) { return lp + bin * (i64)rn; };
-  Buf<int> ovf, novf, ovflag;
-  int n_ovf = 0;
+  Buf<int> ovf[3], novf, tierv;
+  int n_ovf[3] = {0, 0, 0};
   Csr X;
   CUDA_CHECK(cudaEventRecord(e0, c.stream));
-  for (int phase = 1; phase <= 2; phase++) {
+  // Fused mode: one pass counts and writes every row into an arena, a copy puts the rows in
+  // place.  Only if the arena was too small does the classic second pass recompute the rows.
+  static int fused_on = -1;
+  if (fused_on < 0) { const char *e = getenv("AMGB_SPGEMM_FUSED"); fused_on = (e && *e == '0') ? 0 : 1; }
+  Arena ar{nullptr, nullptr, nullptr, 0, nullptr, nullptr};
+  Buf<int> acols, aflag;
+  Buf<double> avals;
+  Buf<unsigned long long> atop;
+  Buf<i64> aroff;
+  if (fused_on) {
+    i64 cap = 6 * (A.nnz + B.nnz) + rn;
+    if (cap < (1 << 20)) cap = 1 << 20;
+    acols.alloc(cap); avals.alloc(cap); atop.alloc(1); aflag.alloc(1); aroff.alloc(rn);
+    atop.zero(); aflag.zero();
+    ar = Arena{acols.p, avals.p, atop.p, cap, aroff.p, aflag.p};
+  }
+  bool done = false;
+  for (int pass = 0; pass < 2 && !done; pass++) {
+    const int phase = fused_on ? (pass == 0 ? 3 : 2) : pass + 1;
+    const bool first = (pass == 0);
     int *xcol = phase == 2 ? X.col.p : nullptr;
     double *xa = phase == 2 ? X.a.p : nullptr;
     if (hc[0]) {
-      k_spgemm_tile<8, 64, 24><<<(hc[0] + 31) / 32, 256, 0, c.stream>>>(phase, L(0), hc[0], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+      k_spgemm_tile<8, 64, 24><<<(hc[0] + 31) / 32, 256, 0, c.stream>>>(phase, L(0), hc[0], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, ar);
       c.launches++; post_launch("spgemm_tile8");
     }
     if (hc[1]) {
-      k_spgemm_tile<32, 256, 96><<<(hc[1] + 7) / 8, 256, 0, c.stream>>>(phase, L(1), hc[1], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+      k_spgemm_tile<32, 256, 96><<<(hc[1] + 7) / 8, 256, 0, c.stream>>>(phase, L(1), hc[1], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, ar);
       c.launches++; post_launch("spgemm_tile32");
     }
     if (hc[2]) {
-      k_spgemm_warp_bitmap<512, 1016><<<(hc[2] + 3) / 4, 128, 4 * (512 * 12 + 1016 * 6), c.stream>>>(
-          phase, cmv, spv, L(2), hc[2], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, nullptr, nullptr, nullptr);
+      k_spgemm_warp_bitmap<512, 1016, 4><<<(hc[2] + 3) / 4, 128, 4 * (512 * 12 + 1016 * 6), c.stream>>>(
+          phase, cmv, spv, L(2), hc[2], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, nullptr, nullptr, nullptr, 0, ar);
       c.launches++; post_launch("spgemm_warp_bitmap");
     }
     if (hc[3]) {
-      if (phase == 1) {
-        ovf.alloc(hc[3]); novf.alloc(1); ovflag.alloc(rn);
-        novf.zero(); ovflag.zero();
+      // optimistic ladder: 1024-, 2048-, 4096-slot tables, then the dense block kernel
+      if (first) {
+        for (int t = 0; t < 3; t++) { ovf[t].alloc(hc[3]); }
+        novf.alloc(3); tierv.alloc(rn);
+        novf.zero(); tierv.zero();
       }
-      k_spgemm_warp_bitmap<1024, 768><<<(hc[3] + 3) / 4, 128, 4 * (1024 * 12 + 768 * 6), c.stream>>>(
-          phase, cmv, spv, L(3), hc[3], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa,
-          phase == 1 ? ovf.p : nullptr, phase == 1 ? novf.p : nullptr, phase == 2 ? ovflag.p : nullptr);
-      c.launches++; post_launch("spgemm_warp_optimistic");
-      if (phase == 1) {
-        n_ovf = novf.get(0);
-        if (n_ovf) { int *fl = ovflag.p; const int *ol = ovf.p; parallel_for(n_ovf, [=] DEV(i64 q) { fl[ol[q]] = 1; }); }
+      static int ntiers = -1;
+      if (ntiers < 0) { const char *e = getenv("AMGB_SPGEMM_TIERS"); ntiers = e ? atoi(e) : 1; if (ntiers < 0 || ntiers > 3) ntiers = 1; }
+      const int *lists3[4] = {L(3), ovf[0].p, ovf[1].p, ovf[2].p};
+      int counts3[4] = {hc[3], n_ovf[0], n_ovf[1], n_ovf[2]};
+      if (first && ntiers < 3) {
+        // rows skip the tiers that are switched off: everything left goes to the dense kernel
+        const int last = ntiers;    // first disabled tier
+        if (last == 0) { n_ovf[0] = n_ovf[1] = n_ovf[2] = hc[3]; d2d(ovf[2].p, L(3), sizeof(int) * (size_t)hc[3]);
+                         int *fl = tierv.p; const int *ol = L(3); parallel_for(hc[3], [=] DEV(i64 q) { fl[ol[q]] = 3; }); }
       }
-      if (n_ovf) {
-        k_spgemm_dense<<<n_ovf, 256, (size_t)(hms[3] > 0 ? hms[3] : 1) * 8, c.stream>>>(phase, cmv, spv, ovf.p, n_ovf, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+      for (int t = 0; t < 3; t++) {
+        if (t >= ntiers) {
+          if (first && t > 0 && t == ntiers && n_ovf[t - 1]) {   // hand the overflow of the last enabled tier to dense
+            n_ovf[2] = n_ovf[t - 1];
+            if (t - 1 != 2) d2d(ovf[2].p, ovf[t - 1].p, sizeof(int) * (size_t)n_ovf[t - 1]);
+            int *fl = tierv.p; const int *ol = ovf[2].p; parallel_for(n_ovf[2], [=] DEV(i64 q) { fl[ol[q]] = 3; });
+          }
+          continue;
+        }
+        if (!counts3[t]) continue;
+        int *ol = first ? ovf[t].p : nullptr, *on = first ? novf.p + t : nullptr;
+        const int *tv = first ? nullptr : tierv.p;
+        if (t == 0)
+          k_spgemm_warp_bitmap<1024, 768, 4><<<(counts3[t] + 3) / 4, 128, 4 * (1024 * 12 + 768 * 6), c.stream>>>(
+              phase, cmv, spv, lists3[t], counts3[t], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, ol, on, tv, t, ar);
+        else if (t == 1)
+          k_spgemm_warp_bitmap<2048, 768, 2><<<(counts3[t] + 1) / 2, 64, 2 * (2048 * 12 + 768 * 6), c.stream>>>(
+              phase, cmv, spv, lists3[t], counts3[t], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, ol, on, tv, t, ar);
+        else
+          k_spgemm_warp_bitmap<4096, 768, 1><<<counts3[t], 32, 4096 * 12 + 768 * 6, c.stream>>>(
+              phase, cmv, spv, lists3[t], counts3[t], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, ol, on, tv, t, ar);
+        c.launches++; post_launch("spgemm_warp_optimistic");
+        if (first) {
+          std::vector<int> hn = novf.download();
+          n_ovf[t] = hn[(size_t)t];
+          counts3[t + 1] = n_ovf[t];
+          if (n_ovf[t]) { int *fl = tierv.p; const int *olist = ovf[t].p; const int tt = t + 1; parallel_for(n_ovf[t], [=] DEV(i64 q) { fl[olist[q]] = tt; }); }
+        }
+      }
+      if (n_ovf[2]) {
+        k_spgemm_dense<<<n_ovf[2], 256, (size_t)(hms[3] > 0 ? hms[3] : 1) * 8, c.stream>>>(phase, cmv, spv, ovf[2].p, n_ovf[2], aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, ar);
         c.launches++; post_launch("spgemm_dense");
       }
     }
     if (hc[6]) {
       const int mw = words(hms[6]);
-      k_spgemm_bitmap<<<hc[6], 128, 2048 * 12 + (size_t)mw * 8, c.stream>>>(phase, 2048, mw, cmv, spv, L(6), hc[6], nullptr, nullptr, nullptr, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+      k_spgemm_bitmap<<<hc[6], 128, 2048 * 12 + (size_t)mw * 8, c.stream>>>(phase, 2048, mw, cmv, spv, L(6), hc[6], nullptr, nullptr, nullptr, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, ar);
       c.launches++; post_launch("spgemm_bitmap2k");
     }
     if (hc[7]) {
       const int mw = words(hms[7]);
-      k_spgemm_bitmap<<<hc[7], 256, 8192 * 12 + (size_t)mw * 8, c.stream>>>(phase, 8192, mw, cmv, spv, L(7), hc[7], nullptr, nullptr, nullptr, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+      k_spgemm_bitmap<<<hc[7], 256, 8192 * 12 + (size_t)mw * 8, c.stream>>>(phase, 8192, mw, cmv, spv, L(7), hc[7], nullptr, nullptr, nullptr, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, ar);
       c.launches++; post_launch("spgemm_bitmap8k");
     }
     if (hc[8]) {
       const int mw = words(hms[8]);
-      k_spgemm_bitmap<<<hc[8], 256, (size_t)mw * 8 + 16, c.stream>>>(phase, 0, mw, cmv, spv, L(8), hc[8], toff5.p, gkeys5.p, gvals5.p, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+      k_spgemm_bitmap<<<hc[8], 256, (size_t)mw * 8 + 16, c.stream>>>(phase, 0, mw, cmv, spv, L(8), hc[8], toff5.p, gkeys5.p, gvals5.p, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, ar);
       c.launches++; post_launch("spgemm_bitmap_hbm");
     }
     if (hc[9]) {
-      k_spgemm_global<<<hc[9], 256, 0, c.stream>>>(phase, L(9), hc[9], toff6.p, gkeys6.p, gvals6.p, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa);
+      k_spgemm_global<<<hc[9], 256, 0, c.stream>>>(phase, L(9), hc[9], toff6.p, gkeys6.p, gvals6.p, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, ar);
       c.launches++; post_launch("spgemm_global");
     }
-    if (phase == 1) {
+    if (first) {
       CUDA_CHECK(cudaEventRecord(e1, c.stream));
       g_stats.ev.emplace_back(e0, e1);
       const i64 nnz = exclusive_scan(cnt.p, xro.p, rn);
@@ -583,6 +691,16 @@ Csr spgemm(const Csr &A, const Csr &B) {
       d2d(X.ro.p, xro.p, sizeof(int) * (size_t)(rn + 1));
       CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
       CUDA_CHECK(cudaEventRecord(e0, c.stream));
+      if (fused_on && aflag.get(0) == 0) {       // every row is in the arena: copy into place
+        if (nnz > 0) {
+          if ((double)nnz / (double)rn <= 12.0)
+            k_arena_copy<8><<<(rn + 31) / 32, 256, 0, c.stream>>>(rn, xro.p, aroff.p, acols.p, avals.p, X.col.p, X.a.p);
+          else
+            k_arena_copy<32><<<(rn + 7) / 8, 256, 0, c.stream>>>(rn, xro.p, aroff.p, acols.p, avals.p, X.col.p, X.a.p);
+          c.launches++; post_launch("spgemm_arena_copy");
+        }
+        done = true;
+      }
     }
   }
   CUDA_CHECK(cudaEventRecord(e1, c.stream));
@@ -598,7 +716,7 @@ Csr spgemm(const Csr &A, const Csr &B) {
       cudaEventElapsedTime(&m2, g_stats.ev[ne - 1].first, g_stats.ev[ne - 1].second);
       fprintf(stderr, "spgemm A %dx%d nnz %lld  B %dx%d nnz %lld  X nnz %lld | bins %d %d %d %d %d %d %d %d %d %d | phase1 %.3f ms phase2 %.3f ms | %.1f GB/s\n",
               A.rn, A.cn, (long long)A.nnz, B.rn, B.cn, (long long)B.nnz, (long long)X.nnz, hc[0], hc[1], hc[2], hc[3], hc[4],
-              n_ovf, hc[6], hc[7], hc[8], hc[9], m1, m2,
+              n_ovf[0] * 10000 + n_ovf[2], hc[6], hc[7], hc[8], hc[9], m1, m2,
               (12.0 * (A.nnz + B.nnz + X.nnz)) / ((m1 + m2) * 1e-3) / 1e9);
     }
   }
