@@ -392,18 +392,42 @@ __global__ void __launch_bounds__(EPS_T) k_eps_dot(const double *a, const double
       e.x = tie[k] ? 0 : (unsigned char)((fl[k] + up[k]) & 1);
       mine = par_compose(mine, e);
     }
-    // ---- exclusive scan of the parity functions over threads (Hillis-Steele in shared memory) ----
-    pf[t] = mine;
-    __syncthreads();
-    for (int off = 1; off < EPS_T; off <<= 1) {
-      ParFn v = pf[t];
-      if (t >= off) v = par_compose(pf[t - off], v);
+    // ---- inclusive scan of the parity functions over threads: shuffles inside a warp, the 32
+    // warp totals scanned by warp 0 ----
+    {
+      const int lane = t & 31, wid = t >> 5;
+      unsigned fr = mine.reset, fx = mine.x;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const unsigned pr = __shfl_up_sync(0xffffffffu, fr, off), px = __shfl_up_sync(0xffffffffu, fx, off);
+        if (lane >= off) { fx = fr ? fx : (px ^ fx); fr = fr | pr; }      // compose(prev, cur)
+      }
+      if (lane == 31) { pf[wid].reset = (unsigned char)fr; pf[wid].x = (unsigned char)fx; }
       __syncthreads();
-      pf[t] = v;
+      if (wid == 0) {
+        unsigned wr = pf[lane].reset, wx = pf[lane].x;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const unsigned pr = __shfl_up_sync(0xffffffffu, wr, off), px = __shfl_up_sync(0xffffffffu, wx, off);
+          if (lane >= off) { wx = wr ? wx : (px ^ wx); wr = wr | pr; }
+        }
+        pf[32 + lane].reset = (unsigned char)wr; pf[32 + lane].x = (unsigned char)wx;
+      }
       __syncthreads();
+      if (wid > 0) {                        // prepend everything before this warp
+        const unsigned pr = pf[32 + wid - 1].reset, px = pf[32 + wid - 1].x;
+        fx = fr ? fx : (px ^ fx); fr = fr | pr;
+      }
+      // exclusive value for this thread = inclusive of the previous thread
+      const unsigned er = __shfl_up_sync(0xffffffffu, fr, 1), ex = __shfl_up_sync(0xffffffffu, fx, 1);
+      unsigned qr, qx;
+      if (lane > 0) { qr = er; qx = ex; }
+      else if (wid > 0) { qr = pf[32 + wid - 1].reset; qx = pf[32 + wid - 1].x; }
+      else { qr = 0; qx = 0; }
+      mine.reset = (unsigned char)qr; mine.x = (unsigned char)qx;   // now: function of all earlier threads
     }
     int par = (int)(S0 & 1);
-    if (t > 0) { const ParFn f = pf[t - 1]; par = f.reset ? f.x : (par ^ f.x); }
+    par = mine.reset ? mine.x : (par ^ mine.x);
     // ---- increments with the tie decision, local sums ----
     long long c[EPS_E], lsum = 0;
 #pragma unroll
@@ -414,16 +438,31 @@ __global__ void __launch_bounds__(EPS_T) k_eps_dot(const double *a, const double
       if (bad[k]) ck = 0;
       c[k] = ck; lsum += ck;
     }
-    ls[t] = lsum;
-    __syncthreads();
-    for (int off = 1; off < EPS_T; off <<= 1) {
-      long long v = ls[t];
-      if (t >= off) v += ls[t - off];
+    long long Sexcl;
+    {
+      const int lane = t & 31, wid = t >> 5;
+      long long incl = lsum;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const long long pv = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += pv;
+      }
+      __syncthreads();                      // ls is free again
+      if (lane == 31) ls[wid] = incl;
       __syncthreads();
-      ls[t] = v;
+      if (wid == 0) {
+        long long wv = ls[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const long long pv = __shfl_up_sync(0xffffffffu, wv, off);
+          if (lane >= off) wv += pv;
+        }
+        ls[32 + lane] = wv;
+      }
       __syncthreads();
+      Sexcl = incl - lsum + (wid > 0 ? ls[32 + wid - 1] : 0);
     }
-    long long S = S0 + (t > 0 ? ls[t - 1] : 0);
+    long long S = S0 + Sexcl;
     // ---- first term that may leave the binade ----
     if (t == 0) vmin_sh = EPS_T * EPS_E;
     __syncthreads();

@@ -14,6 +14,55 @@ static double now_s() {
 // =======================================================================================
 // coarsen (:2737) with mat_max (:3535)
 // =======================================================================================
+#ifndef AMGB_EMU
+// warp-per-row variants of the three coarsening kernels for levels with long rows (maxima are
+// order-free, so the lanes reduce with shuffles)
+__global__ void __launch_bounds__(256) k_coarsen_thr(int n, const int *ro, const int *col, const double *sa,
+                                                     const double *vf, double mtol, double *thr) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const int lane = threadIdx.x & 31;
+  double amax = 0;
+  for (int j = ro[i] + lane; j < ro[i + 1]; j += 32)
+    if (vf[col[j]] != 0 && fabs(sa[j]) > amax) amax = fabs(sa[j]);
+  for (int off = 16; off >= 1; off >>= 1) amax = fmax(amax, __shfl_down_sync(0xffffffffu, amax, off));
+  if (lane == 0) thr[i] = amax * mtol;
+}
+template <int STAGE>
+__global__ void __launch_bounds__(256) k_coarsen_gather(int n, const int *tro, const int *tcol, const double *ta,
+                                                        const double *thr, const double *vf, const double *w,
+                                                        const double *g, double ctol2, double *mk, double *tp,
+                                                        double *vc, double *vfnext) {
+  const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (k >= n) return;
+  const int lane = threadIdx.x & 31;
+  double m = -DBL_MAX;
+  if (vf[k] != 0)
+    for (int p = tro[k] + lane; p < tro[k + 1]; p += 32) {
+      const int i = tcol[p];
+      if (fabs(ta[p]) < thr[i]) continue;
+      double x;
+      if (STAGE == 1) { const double mi0 = (w[i] > ctol2) ? 1. : 0.; x = g[i] * mi0; }
+      else x = tp[i];
+      if (x > m) m = x;
+    }
+  for (int off = 16; off >= 1; off >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, off));
+  if (lane != 0) return;
+  if (STAGE == 1) {
+    const double m0 = (w[k] > ctol2) ? 1. : 0.;
+    const double d = g[k] - m;
+    const double mv = (m0 != 0. && d >= 0.) ? 1. : 0.;
+    mk[k] = mv;
+    vfnext[k] = mv * ((double)k + 1.0);        // stage 1 writes the id vector into a scratch array
+  } else {
+    const double d = ((double)k + 1.0) - m;
+    const double mv = (mk[k] != 0. && d > 0.) ? 1. : 0.;
+    if (mv != 0.) vc[k] = 1.;
+    vfnext[k] = ((vf[k] == 0.) != (mv == 0.)) ? 1. : 0.;
+  }
+}
+#endif
+
 // mat_max (:3535): y[k] = max over rows i that hold k as a strong neighbour (|S_ik| >= thr_i,
 // thr_i = tol * max over F neighbours of |S_i.|, and f[k] != 0) of x[i].  The reference scatters
 // row by row; a maximum is order-free, so every k gathers from row k of S' (which lists exactly the
@@ -65,6 +114,26 @@ int coarsen(double *vc, const Csr &A, double ctol) {
       if (count_nonzero(vc, n) == 0) parallel_for(1, [=] DEV(i64) { vc[mi] = 1.; });
       break;
     }
+#ifndef AMGB_EMU
+    if ((double)S.nnz / (double)n > 16.0) {
+      Context &cx = ctx();
+      const int nb = (n + 7) / 8;
+      k_coarsen_thr<<<nb, 256, 0, cx.stream>>>(n, ro, col, sa, vfp, mtol, thp);
+      // stage 1 must not overwrite tmp while other warps may still read it as x: it does not read tp,
+      // so tp is its output; stage 2 reads tp and writes the next vf into w2
+      k_coarsen_gather<1><<<nb, 256, 0, cx.stream>>>(n, tro, tcol, ta, thp, vfp, wp, gp, ctol2, mk, nullptr, nullptr, tp);
+      k_coarsen_gather<2><<<nb, 256, 0, cx.stream>>>(n, tro, tcol, ta, thp, vfp, wp, gp, ctol2, mk, tp, vc, w2p);
+      cx.launches += 3; post_launch("coarsen_warp_kernels");
+      { double *t = vfp; vfp = w2p; w2p = t; }
+      if (ctx().trace_on) {
+        char t[64];
+        snprintf(t, sizeof t, "coarsen.vc.r%d", rounds);
+        trace_dev(t, vc, sizeof(double) * (size_t)n);
+      }
+      if (rounds > 100000) throw Error(-7, "coarsen: no convergence");
+      continue;
+    }
+#endif
     // thr_i of this round
     parallel_for(n, [=] DEV(i64 i) {
       double amax = 0;
@@ -661,7 +730,10 @@ Csr interpolation(const Csr &Af, const Csr &Ac, const Csr &Ar, double gamma2, do
     trace_csr("ip.W0", W0);
     trace_csr("ip.Wtmp", Wt);
     Csr R0, R;
-    { StageTimer t_("ip.AfW_spgemm+mpm"); Csr AfW = spgemm(Af, W0); R0 = mpm(1., AfW, 1., Ar); }
+    // R0 = Af*W0 + Ar is only read by expand_support; in the last round of a level it is never
+    // needed, so it is formed lazily (eagerly when tracing, to keep the trace order of the checker)
+    const bool eager_R0 = ctx().trace_on;
+    if (eager_R0) { StageTimer t_("ip.AfW_spgemm+mpm"); Csr AfW = spgemm(Af, W0); R0 = mpm(1., AfW, 1., Ar); }
     { StageTimer t_("ip.AfW_spgemm+mpm"); Csr AfW = spgemm(Af, Wt); R = mpm(1., AfW, 1., Ar); }
     {
       // dchat = sum(W .* (Arhat + Ar), 1): column c collects W_ic * Arr_ic over the rows i of its
@@ -674,11 +746,13 @@ Csr interpolation(const Csr &Af, const Csr &Ac, const Csr &Ar, double gamma2, do
     scale_rows(R, dfi);
     { double *a = R.a.p; parallel_for(R.nnz, [=] DEV(i64 e) { a[e] = fabs(a[e]); }); }
     scale_cols(R, dsq);
-    scale_rows(R0, dfi);
-    { double *a = R0.a.p; parallel_for(R0.nnz, [=] DEV(i64 e) { a[e] = fabs(a[e]); }); }
-    scale_cols(R0, dsq);
+    if (eager_R0) {
+      scale_rows(R0, dfi);
+      { double *a = R0.a.p; parallel_for(R0.nnz, [=] DEV(i64 e) { a[e] = fabs(a[e]); }); }
+      scale_cols(R0, dsq);
+    }
     trace_csr("ip.R", R);
-    trace_csr("ip.R0", R0);
+    if (eager_R0) trace_csr("ip.R0", R0);
     Csr Rt;
     Buf<int> rtpos;
     {
@@ -711,6 +785,12 @@ Csr interpolation(const Csr &Af, const Csr &Ac, const Csr &Ar, double gamma2, do
           if ((int)i == wcol[j]) { const double s = vp[i] / wu[i]; wa[j] = s * wa[j]; }
       });
       break;
+    }
+    if (!eager_R0) {
+      { StageTimer t_("ip.AfW_spgemm+mpm"); Csr AfW = spgemm(Af, W0); R0 = mpm(1., AfW, 1., Ar); }
+      scale_rows(R0, dfi);
+      { double *a = R0.a.p; parallel_for(R0.nnz, [=] DEV(i64 e) { a[e] = fabs(a[e]); }); }
+      scale_cols(R0, dsq);
     }
     parallel_for(nc, [=] DEV(i64 i) { const double x = w2p[i] > 1e-6 ? w2p[i] : 1e-6; alp[i] = dcp[i] / x; });
     Wsk = expand_support(Wsk, R, Rt, rtpos, R0, gamma2);
