@@ -232,15 +232,18 @@ void build_q_store(QStore &qs, const Csr &Wt, const Csr &At) {
   q_offsets(qs, Wt);
   const int n = Wt.rn;
   if (n == 0) return;
-  // bin the columns by support size: <=8 | <=32 | <=144 | larger
-  Buf<int> lists((i64)4 * n), cnt(4);
+  // bin the columns by support size: <=8 | <=32 | <=64 | <=144 | larger.  The block size and the
+  // shared-memory footprint follow the bin, so that small supports do not pay the occupancy of
+  // the largest one.
+  constexpr int NBIN = 5;
+  Buf<int> lists((i64)NBIN * n), cnt(NBIN);
   cnt.zero();
   const int *wro = Wt.ro.p;
   int *lp = lists.p, *cp = cnt.p;
   parallel_for(n, [=] DEV(i64 i) {
     const int nz = wro[i + 1] - wro[i];
     if (nz == 0) return;
-    const int bin = nz <= 8 ? 0 : nz <= 32 ? 1 : nz <= 144 ? 2 : 3;
+    const int bin = nz <= 8 ? 0 : nz <= 32 ? 1 : nz <= 64 ? 2 : nz <= 144 ? 3 : 4;
     const int p = atomic_add(&cp[bin], 1);
     lp[(i64)bin * n + p] = (int)i;
   });
@@ -248,27 +251,25 @@ void build_q_store(QStore &qs, const Csr &Wt, const Csr &At) {
   Context &c = ctx();
   const int *wcol = Wt.col.p, *aro = At.ro.p, *acol = At.col.p;
   const double *aa = At.a.p;
+  static bool attr = false;
+  if (!attr) { set_smem((const void *)k_build_q_block<true>, sizeof(double) * (2 * 144 + tri(144))); attr = true; }
   if (hc[0]) {
     k_build_q_tile8<8><<<(hc[0] + 31) / 32, 256, 0, c.stream>>>(lp, hc[0], wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
     c.launches++; post_launch("build_q_tile8");
   }
-  if (hc[1]) {
-    const size_t sm = sizeof(double) * (2 * 32 + tri(32));
-    k_build_q_block<true><<<hc[1], 32, sm, c.stream>>>(lp + n, hc[1], 32, wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
-    c.launches++; post_launch("build_q_block32");
+  const int caps[3] = {32, 64, 144}, threads[3] = {32, 64, 128};
+  for (int b = 0; b < 3; b++) {
+    if (!hc[b + 1]) continue;
+    const size_t sm = sizeof(double) * (2 * caps[b] + tri(caps[b]));
+    k_build_q_block<true><<<hc[b + 1], threads[b], sm, c.stream>>>(lp + (i64)(b + 1) * n, hc[b + 1], caps[b], wro, wcol, aro,
+                                                                   acol, aa, qs.Q.p, qs.qoff.p);
+    c.launches++; post_launch("build_q_block");
   }
-  if (hc[2]) {
-    const size_t sm = sizeof(double) * (2 * 144 + tri(144));
-    static bool attr = false;
-    if (!attr) { set_smem((const void *)k_build_q_block<true>, sizeof(double) * (2 * 144 + tri(144))); attr = true; }
-    k_build_q_block<true><<<hc[2], 128, sm, c.stream>>>(lp + 2 * (i64)n, hc[2], 144, wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
-    c.launches++; post_launch("build_q_block144");
-  }
-  if (hc[3]) {
+  if (hc[4]) {
     const size_t sm = sizeof(double) * (2 * (size_t)qs.maxnz);
     if (sm > 200 * 1024) throw Error(-12, "interpolation support of " + std::to_string(qs.maxnz) + " rows exceeds the kernel limit (12800)");
     if (sm > 48 * 1024) set_smem((const void *)k_build_q_block<false>, sm);
-    k_build_q_block<false><<<hc[3], 256, sm, c.stream>>>(lp + 3 * (i64)n, hc[3], qs.maxnz, wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
+    k_build_q_block<false><<<hc[4], 256, sm, c.stream>>>(lp + 4 * (i64)n, hc[4], qs.maxnz, wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
     c.launches++; post_launch("build_q_global");
   }
 }
