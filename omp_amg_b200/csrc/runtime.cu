@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(EPS_T) k_eps_dot(const double *a, const double
   __shared__ ParFn pf[EPS_T];
   __shared__ long long ls[EPS_T];
   const int t = threadIdx.x;
-  if (t == 0) { s_sh = 0.0; pos_sh = 0; burst_sh = 16; need_serial_sh = 1; }
+  if (t == 0) { s_sh = 0.0; pos_sh = 0; burst_sh = 16; need_serial_sh = 0; }
   __syncthreads();
   while (true) {
     const i64 pos = pos_sh;
@@ -359,8 +359,33 @@ __global__ void __launch_bounds__(EPS_T) k_eps_dot(const double *a, const double
     const unsigned long long sbits = (unsigned long long)__double_as_longlong(s);
     const int sex = (int)((sbits >> 52) & 0x7ff);
     const bool s_ok = (sex != 0 && sex != 0x7ff);           // normal, non-zero, finite
+    if (sbits == 0ULL && !need_serial_sh) {
+      // running sum is +0: zeros (of either sign) leave it +0 and the first non-zero term p gives
+      // 0 + p = p exactly, so leading zeros are skipped with a parallel search
+      if (t == 0) vmin_sh = EPS_T * EPS_E;
+      __syncthreads();
+      const i64 base0 = pos + (i64)t * EPS_E;
+      int first = -1;
+      for (int k = 0; k < EPS_E && first < 0; k++) {
+        const i64 j = base0 + k;
+        if (j >= n) { first = k; break; }
+        const double p = b ? __dmul_rn(a[j], b[j]) : a[j];
+        if (p != 0.0) first = k;              // NaN counts as non-zero
+      }
+      if (first >= 0) atomicMin(&vmin_sh, t * EPS_E + first);
+      __syncthreads();
+      if (t == 0) {
+        const i64 j = pos + vmin_sh;
+        if (vmin_sh == EPS_T * EPS_E || j >= n) pos_sh = (j < n) ? j : n;
+        else { s_sh = __dadd_rn(0.0, b ? __dmul_rn(a[j], b[j]) : a[j]); pos_sh = j + 1; }
+      }
+      __syncthreads();
+      continue;
+    }
     if (need_serial_sh || !s_ok) {
       // plain chain for a short burst: products staged by all threads, added by thread 0
+      if (!s_ok && !need_serial_sh && t == 0) burst_sh = min(burst_sh * 2, EPS_BURST_MAX);   // subnormal / non-finite sums
+      __syncthreads();
       const int cntb = (int)((n - pos < burst_sh) ? (n - pos) : burst_sh);
       for (int j = t; j < cntb; j += EPS_T) prod[j] = b ? __dmul_rn(a[pos + j], b[pos + j]) : a[pos + j];
       __syncthreads();

@@ -182,6 +182,10 @@ def test_sequential_reduction_kernel_is_exact(L):
         "palindrome": (lambda x: np.concatenate([x, -x[::-1]]))(rng.standard_normal(40000)),
         "denormals": rng.integers(-5, 6, 5000) * 5e-324,
         "tiny": np.array([3.0]), "empty_like": np.zeros(17),
+        "all_zero_large": np.zeros(1 << 20),
+        "zeros_then_values": np.concatenate([np.zeros(300000), rng.standard_normal(1000) ** 2]),
+        "sparse_nonzeros": np.where(rng.random(400000) < 1e-3, rng.standard_normal(400000), 0.0),
+        "negative_zero_start": np.concatenate([[-0.0, -0.0], np.zeros(10000), [-1.5, 2.5]]),
         "with_inf": np.concatenate([rng.standard_normal(100), [np.inf], rng.standard_normal(100)]),
     }
     for name, p in cases.items():
