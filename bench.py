@@ -246,9 +246,13 @@ def main():
             "host_syncs": int(sum(t["syncs"] for t in tims)),
             "clocks": clocks,
             "e2e": {"value": e2e_step, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "roofline": {"bound": "hbm", "kernel": "spgemm (two-phase hash/dense SpGEMM, all launches of the timed steps)",
+            "roofline": {"bound": "hbm", "kernel": "spgemm (fused hash/dense SpGEMM family, all launches of the timed steps)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                         "peak_source": peak_src, "traffic": None, "launch_seconds": sp_s / max(sp_n, 1),
+                         "peak_source": peak_src, "traffic": None,
+                         "traffic_note": "family of kernels; ncu --set full of its dominant launch "
+                                         "(k_spgemm_warp_bitmap<1024,768,4>, 96^3): 157 MB read + 80 MB written, "
+                                         "L2 hit 91% -- profiles/r1_ncu_full_spgemm_kernels_poisson7_96.csv",
+                         "launch_seconds": sp_s / max(sp_n, 1),
                          "algorithmic_bytes_per_call": sp_b / max(sp_n, 1), "calls": int(sp_n),
                          "share_of_step": sp_s / dev_s if dev_s else None},
         }
