@@ -341,16 +341,27 @@ __device__ __forceinline__ void eps_split(double p, int ssign, int se, long long
     if (G > half) up = 1; else if (G == half) tie = 1;
   }
 }
-__global__ void __launch_bounds__(EPS_T) k_eps_dot(const double *a, const double *b, i64 n, double *out) {
-  __shared__ double s_sh;
-  __shared__ i64 pos_sh;
-  __shared__ int burst_sh, need_serial_sh, vmin_sh;
-  __shared__ long long Sv_sh;
-  __shared__ double prod[EPS_BURST_MAX];
-  __shared__ ParFn pf[EPS_T];
-  __shared__ long long ls[EPS_T];
+struct EpsShared {
+  double s_sh;
+  i64 pos_sh;
+  int burst_sh, need_serial_sh, vmin_sh;
+  long long Sv_sh;
+  double prod[EPS_BURST_MAX];
+  ParFn pf[EPS_T];
+  long long ls[EPS_T];
+};
+// exact left-to-right accumulation of the terms [begin, n) onto s0 by one block; result in sh.s_sh
+__device__ void eps_run(const double *a, const double *b, i64 begin, i64 n, double s0, EpsShared &sh) {
+  double &s_sh = sh.s_sh;
+  i64 &pos_sh = sh.pos_sh;
+  int &burst_sh = sh.burst_sh, &need_serial_sh = sh.need_serial_sh, &vmin_sh = sh.vmin_sh;
+  long long &Sv_sh = sh.Sv_sh;
+  double *prod = sh.prod;
+  ParFn *pf = sh.pf;
+  long long *ls = sh.ls;
   const int t = threadIdx.x;
-  if (t == 0) { s_sh = 0.0; pos_sh = 0; burst_sh = 16; need_serial_sh = 0; }
+  __syncthreads();
+  if (t == 0) { s_sh = s0; pos_sh = begin; burst_sh = 16; need_serial_sh = 0; }
   __syncthreads();
   while (true) {
     const i64 pos = pos_sh;
@@ -519,7 +530,200 @@ __global__ void __launch_bounds__(EPS_T) k_eps_dot(const double *a, const double
     }
     __syncthreads();
   }
-  if (t == 0) *out = s_sh;
+}
+__global__ void __launch_bounds__(EPS_T) k_eps_dot(const double *a, const double *b, i64 n, double *out) {
+  __shared__ EpsShared sh;
+  eps_run(a, b, 0, n, 0.0, sh);
+  if (threadIdx.x == 0) *out = sh.s_sh;
+}
+
+// ---- many-block version for long vectors ----
+// Every chunk of 8192 terms is reduced speculatively by its own block, assuming the running sum
+// enters the chunk with the sign and exponent of an approximate (order-free) prefix sum.  A chunk
+// record holds the integer total for an even incoming mantissa, what changes for an odd one (only
+// the first tie of the chunk sees the incoming parity: delta), and the extreme values the running
+// mantissa takes before/after that tie, so that one thread can afterwards walk the chunks in
+// order, verify the assumption for the ACTUAL incoming sum (same sign, same exponent, mantissa
+// stays inside [2^52, 2^53)) and either accept the chunk in O(1) or hand it to eps_run.
+struct EpsChunk {
+  long long total0, lo_pre, hi_pre, lo_post, hi_post;
+  int delta, bad, gsign, gsex;
+};
+#define EPS_C (EPS_T * EPS_E)
+__global__ void __launch_bounds__(256) k_eps_chunk_sums(const double *a, const double *b, i64 n, double *sums) {
+  __shared__ double w[8];
+  const i64 base = (i64)blockIdx.x * EPS_C;
+  double x = 0.0;
+  for (int k = threadIdx.x; k < EPS_C; k += 256) { const i64 j = base + k; if (j < n) x += b ? a[j] * b[j] : a[j]; }
+  for (int off = 16; off >= 1; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+  if ((threadIdx.x & 31) == 0) w[threadIdx.x >> 5] = x;
+  __syncthreads();
+  if (threadIdx.x == 0) { double t = 0; for (int k = 0; k < 8; k++) t += w[k]; sums[blockIdx.x] = t; }
+}
+__global__ void k_eps_guess(const double *sums, int nchunks, EpsChunk *rec) {
+  double pre = 0.0;
+  for (int c = 0; c < nchunks; c++) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(pre);
+    rec[c].gsign = (bits >> 63) ? -1 : 1;
+    rec[c].gsex = (int)((bits >> 52) & 0x7ff);
+    pre += sums[c];
+  }
+}
+__global__ void __launch_bounds__(EPS_T) k_eps_chunk_stats(const double *a, const double *b, i64 n, EpsChunk *rec) {
+  __shared__ ParFn pf[64 + 32];
+  __shared__ long long ls[64 + 32];
+  __shared__ int first_tie, bad_sh, d0_sh;
+  __shared__ long long lo_pre, hi_pre, lo_post, hi_post;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  EpsChunk &R = rec[blockIdx.x];
+  const int sex = R.gsex, ssign = R.gsign;
+  if (t == 0) {
+    first_tie = EPS_C; bad_sh = (sex == 0 || sex == 0x7ff) ? 1 : 0; d0_sh = 0;
+    lo_pre = lo_post = (1LL << 62); hi_pre = hi_post = -(1LL << 62);
+  }
+  __syncthreads();
+  if (bad_sh) { if (t == 0) R.bad = 1; return; }
+  const int se = sex - 1075;
+  const i64 base = (i64)blockIdx.x * EPS_C + (i64)t * EPS_E;
+  long long fl[EPS_E];
+  int up[EPS_E], tie[EPS_E];
+  int anybad = 0;
+  unsigned fr = 0, fx = 0;
+#pragma unroll
+  for (int k = 0; k < EPS_E; k++) {
+    const i64 j = base + k;
+    int bd = 0;
+    if (j < n) {
+      const double p = b ? __dmul_rn(a[j], b[j]) : a[j];
+      eps_split(p, ssign, se, fl[k], up[k], tie[k], bd);
+    } else { fl[k] = 0; up[k] = 0; tie[k] = 0; }
+    anybad |= bd;
+    const unsigned er = (unsigned)tie[k], ex = tie[k] ? 0u : (unsigned)((fl[k] + up[k]) & 1);
+    fx = er ? ex : (fx ^ ex); fr = fr | er;
+  }
+  if (anybad) bad_sh = 1;
+  // scan of the parity functions (incoming parity 0)
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const unsigned pr = __shfl_up_sync(0xffffffffu, fr, off), px = __shfl_up_sync(0xffffffffu, fx, off);
+    if (lane >= off) { fx = fr ? fx : (px ^ fx); fr = fr | pr; }
+  }
+  if (lane == 31) { pf[wid].reset = (unsigned char)fr; pf[wid].x = (unsigned char)fx; }
+  __syncthreads();
+  if (wid == 0) {
+    unsigned wr = pf[lane].reset, wx = pf[lane].x;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned pr = __shfl_up_sync(0xffffffffu, wr, off), px = __shfl_up_sync(0xffffffffu, wx, off);
+      if (lane >= off) { wx = wr ? wx : (px ^ wx); wr = wr | pr; }
+    }
+    pf[32 + lane].reset = (unsigned char)wr; pf[32 + lane].x = (unsigned char)wx;
+  }
+  __syncthreads();
+  if (wid > 0) { const unsigned pr = pf[32 + wid - 1].reset, px = pf[32 + wid - 1].x; fx = fr ? fx : (px ^ fx); fr = fr | pr; }
+  const unsigned er = __shfl_up_sync(0xffffffffu, fr, 1), ex = __shfl_up_sync(0xffffffffu, fx, 1);
+  unsigned qr, qx;
+  if (lane > 0) { qr = er; qx = ex; }
+  else if (wid > 0) { qr = pf[32 + wid - 1].reset; qx = pf[32 + wid - 1].x; }
+  else { qr = 0; qx = 0; }
+  int par = qr ? (int)qx : (int)(0 ^ qx);          // parity before this thread's terms if the incoming one is even
+  // increments, first tie
+  long long c[EPS_E], lsum = 0;
+  int myfirst = -1, myd0 = 0;
+#pragma unroll
+  for (int k = 0; k < EPS_E; k++) {
+    long long ck = fl[k] + up[k];
+    if (tie[k]) {
+      const int d = (int)((par + fl[k]) & 1);
+      if (myfirst < 0) { myfirst = k; myd0 = d; }
+      ck += d; par = 0;
+    } else par ^= (int)(ck & 1);
+    c[k] = ck; lsum += ck;
+  }
+  if (myfirst >= 0) atomicMin(&first_tie, t * EPS_E + myfirst);
+  // prefix sums of the increments
+  long long incl = lsum;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) { const long long pv = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += pv; }
+  if (lane == 31) ls[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    long long wv = ls[lane];
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const long long pv = __shfl_up_sync(0xffffffffu, wv, off); if (lane >= off) wv += pv; }
+    ls[32 + lane] = wv;
+  }
+  __syncthreads();
+  long long P = incl - lsum + (wid > 0 ? ls[32 + wid - 1] : 0);      // prefix before this thread's terms
+  const int ft = first_tie;
+  if (ft / EPS_E == t && ft < EPS_C) d0_sh = myd0;
+  long long mlo_pre = (1LL << 62), mhi_pre = -(1LL << 62), mlo_post = (1LL << 62), mhi_post = -(1LL << 62);
+#pragma unroll
+  for (int k = 0; k < EPS_E; k++) {
+    const i64 j = base + k;
+    if (j < n) {
+      const long long v = P + fl[k];
+      if (t * EPS_E + k <= ft) { mlo_pre = min(mlo_pre, v); mhi_pre = max(mhi_pre, v + 1); }
+      else { mlo_post = min(mlo_post, v); mhi_post = max(mhi_post, v + 1); }
+    }
+    P += c[k];
+  }
+  for (int off = 16; off >= 1; off >>= 1) {
+    mlo_pre = min(mlo_pre, __shfl_down_sync(0xffffffffu, mlo_pre, off)); mhi_pre = max(mhi_pre, __shfl_down_sync(0xffffffffu, mhi_pre, off));
+    mlo_post = min(mlo_post, __shfl_down_sync(0xffffffffu, mlo_post, off)); mhi_post = max(mhi_post, __shfl_down_sync(0xffffffffu, mhi_post, off));
+  }
+  if (lane == 0) { atomicMin(&lo_pre, mlo_pre); atomicMax(&hi_pre, mhi_pre); atomicMin(&lo_post, mlo_post); atomicMax(&hi_post, mhi_post); }
+  __syncthreads();
+  if (t == EPS_T - 1) R.total0 = P;                                   // total of the chunk (incoming parity even)
+  if (t == 0) {
+    R.lo_pre = lo_pre; R.hi_pre = hi_pre; R.lo_post = lo_post; R.hi_post = hi_post;
+    R.delta = (ft < EPS_C) ? (1 - 2 * d0_sh) : 0;
+    R.bad = bad_sh;
+  }
+}
+__global__ void __launch_bounds__(EPS_T) k_eps_combine(const double *a, const double *b, i64 n, const EpsChunk *rec,
+                                                       int nchunks, double *out, int *nfallback) {
+  __shared__ EpsShared sh;
+  __shared__ int next_sh;
+  __shared__ double cur_sh;
+  __shared__ EpsChunk srec[160];                  // records of the first 160 chunks (1.3 M terms)
+  const int t = threadIdx.x;
+  if (t == 0) { cur_sh = 0.0; next_sh = 0; }
+  for (int q = t; q < nchunks && q < 160; q += EPS_T) srec[q] = rec[q];
+  __syncthreads();
+  int fb = 0;
+  while (true) {
+    if (t == 0) {
+      // accept as many consecutive chunks as the assumptions allow
+      double s = cur_sh;
+      int c = next_sh;
+      for (; c < nchunks; c++) {
+        const EpsChunk &R = (c < 160) ? srec[c] : rec[c];
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(s);
+        const int sex = (int)((bits >> 52) & 0x7ff), sg = (bits >> 63) ? -1 : 1;
+        if (R.bad || sex != R.gsex || sg != R.gsign || sex == 0 || sex == 0x7ff) break;
+        const long long S = (long long)((bits & 0xfffffffffffffULL) | (1ULL << 52));
+        const int odd = (int)(S & 1);
+        const long long d = odd ? R.delta : 0;
+        const long long lo = min(R.lo_pre, R.lo_post + d), hi = max(R.hi_pre, R.hi_post + d);
+        if (S + lo < (1LL << 52) || S + hi >= (1LL << 53)) break;
+        const long long So = S + R.total0 + d;
+        const unsigned long long nb = (bits & 0xfff0000000000000ULL) | ((unsigned long long)So & 0xfffffffffffffULL);
+        s = __longlong_as_double((long long)nb);
+      }
+      cur_sh = s; next_sh = c;
+    }
+    __syncthreads();
+    const int c = next_sh;
+    if (c >= nchunks) break;
+    const i64 b0 = (i64)c * EPS_C, b1 = (b0 + EPS_C < n) ? b0 + EPS_C : n;
+    eps_run(a, b, b0, b1, cur_sh, sh);                                // the whole block redoes this chunk exactly
+    fb++;
+    __syncthreads();
+    if (t == 0) { cur_sh = sh.s_sh; next_sh = c + 1; }
+    __syncthreads();
+  }
+  if (t == 0) { *out = cur_sh; if (nfallback) *nfallback = fb; }
 }
 static int g_eps = -1;
 
@@ -527,8 +731,17 @@ double seq_dot(const double *a, const double *b, i64 n) {
   if (n <= 0) return 0.0;
   StageTimer st_("prim.seq_dot");
   Buf<double> out(1);
-  if (g_eps < 0) { const char *e = getenv("AMGB_SEQDOT"); g_eps = (e && !strcmp(e, "chain")) ? 0 : 1; }
-  if (g_eps) k_eps_dot<<<1, EPS_T, 0, g_ctx.stream>>>(a, b, n, out.p);
+  if (g_eps < 0) { const char *e = getenv("AMGB_SEQDOT"); g_eps = (e && !strcmp(e, "chain")) ? 0 : (e && !strcmp(e, "block")) ? 1 : 2; }
+  if (g_eps == 2 && n >= 4 * (i64)EPS_C) {
+    const int nch = (int)((n + EPS_C - 1) / EPS_C);
+    Buf<double> sums(nch);
+    Buf<EpsChunk> rec(nch);
+    k_eps_chunk_sums<<<nch, 256, 0, g_ctx.stream>>>(a, b, n, sums.p);
+    k_eps_guess<<<1, 1, 0, g_ctx.stream>>>(sums.p, nch, rec.p);
+    k_eps_chunk_stats<<<nch, EPS_T, 0, g_ctx.stream>>>(a, b, n, rec.p);
+    k_eps_combine<<<1, EPS_T, 0, g_ctx.stream>>>(a, b, n, rec.p, nch, out.p, nullptr);
+    g_ctx.launches += 3;
+  } else if (g_eps) k_eps_dot<<<1, EPS_T, 0, g_ctx.stream>>>(a, b, n, out.p);
   else k_seq_dot<<<1, 1024, 0, g_ctx.stream>>>(a, b, n, out.p);
   g_ctx.launches++; post_launch(__func__);
   return out.get(0);
