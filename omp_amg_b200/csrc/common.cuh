@@ -240,6 +240,7 @@ struct StageTimer {
   ~StageTimer();
 };
 void stage_report();
+void stage_count(const char *name, long n);   // event counters shown by stage_report
 
 // trace: FNV-1a of a device array; the tests compare the tag/hash sequence with their checker
 void trace_dev(const char *tag, const void *dptr, size_t bytes);

@@ -962,6 +962,8 @@ StageTimer::~StageTimer() {
   auto &r = g_stage[name];
   r.first += wall_now() - t0; r.second++;
 }
+static std::map<std::string, long> g_counts;
+void stage_count(const char *name, long n) { if (g_stage_on > 0) g_counts[name] += n; }
 void stage_report() {
   if (g_stage_on <= 0) return;
   std::vector<std::pair<double, std::string>> v;
@@ -970,6 +972,8 @@ void stage_report() {
   fprintf(stderr, "---- stage profile (inclusive, synchronised) ----\n");
   for (auto it = v.rbegin(); it != v.rend(); ++it)
     fprintf(stderr, "%-28s %10.3f ms  calls %ld\n", it->second.c_str(), it->first * 1e3, g_stage[it->second].second);
+  for (auto &kv : g_counts) fprintf(stderr, "count %-24s %ld\n", kv.first.c_str(), kv.second);
+  g_counts.clear();
   g_stage.clear();
 }
 

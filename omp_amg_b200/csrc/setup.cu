@@ -93,6 +93,7 @@ int coarsen(double *vc, const Csr &A, double ctol) {
   const double ctol2 = ctol * ctol, mtol = 0.1;
   for (;;) {
     rounds++;
+    stage_count("coarsen.rounds", 1);
     // w1 = vf.*(S*(vf.*(S*vf))), w2 = vf.*(S*(vf.*(S*w1))), w = (1./w1).*w2 (0 where w1 == 0)
     spmv_vals(gp, 0, nullptr, 1., S, sa, vfp, vfp);
     spmv_vals(w1p, 0, nullptr, 1., S, sa, gp, vfp);
@@ -200,6 +201,7 @@ int pcg(double *x, const Csr &A, double *r, const double *M, double tol, const d
   double rho_old = 1;
   while (nmax > 0 && rho > rho_stop && k < nmax) {
     k++;
+    stage_count("pcg.iterations", 1);
     const double beta = rho / rho_old;
     parallel_for(n, [=] DEV(i64 i) { const double pb = pp[i] * beta; pp[i] = pb + zp[i]; });
     spmv(wp, 0, nullptr, 1, A, pp);
@@ -255,6 +257,7 @@ int lanczos(double *lambda, const Csr &A, hostmath::GlibcRand &rng, int *iters) 
   double *rp = r.p, *qp = qk.p, *qmp = qkm1.p, *Ap = Aqk.p;
   while (k < kmax && (change > 1e-5 || y[0] > 1e-3 || y[k - 1] > 1e-3)) {
     k++;
+    stage_count("lanczos.iterations", 1);
     const double ib = 1. / beta;
     parallel_for(rn, [=] DEV(i64 i) { qmp[i] = qp[i]; qp[i] = rp[i] * ib; });
     spmv(Ap, 0, nullptr, 1, A, qp);
@@ -529,6 +532,7 @@ Csr find_support(const Csr &R, Csr &Rt, Buf<int> &tpos, double goal) {   // Rt =
       cx.launches++; post_launch("find_support_cols");
     }
 #endif
+    stage_count("find_support.rounds", 1);
     if (++guard > 100000) throw Error(-8, "find_support: no convergence");
   }
   // Skel = sparse(skel_i, skel_j, 1): the flagged entries, in place

@@ -78,6 +78,55 @@ __device__ __forceinline__ void accumulate_row(const Group &g, int i, const int 
   }
 }
 
+// The same accumulation for a tile of G <= 32 threads with the loads taken off the critical path:
+// G entries of the row of A (a_ik and the bounds of row k of B) are read at once, one per thread,
+// and the first G entries of the NEXT row of B are already in registers while the current one is
+// accumulated.  Order of the additions: unchanged (k ascending, one k at a time).
+template <int G, class Tile>
+__device__ __forceinline__ void accumulate_row_tile(const Tile &g, int i, const int *aro, const int *acol,
+                                                    const double *aa, const int *bro, const int *bcol,
+                                                    const double *ba, int *keys, double *vals, int HS) {
+  const int r0 = g.thread_rank();
+  const unsigned mask = (unsigned)(HS - 1);
+  for (int h = r0; h < HS; h += G) keys[h] = EMPTY;
+  g.sync();
+  const int a0 = aro[i], a1 = aro[i + 1];
+  for (int jc = a0; jc < a1; jc += G) {
+    const int my = jc + r0;
+    int mb0 = 0, mb1 = 0;
+    double mav = 0.0;
+    if (my < a1) { const int mk = acol[my]; mav = aa[my]; mb0 = bro[mk]; mb1 = bro[mk + 1]; }
+    const int ns = min(G, a1 - jc);
+    int b0 = g.shfl(mb0, 0), b1 = g.shfl(mb1, 0);
+    int pc = EMPTY;
+    double pv = 0.0;
+    if (b0 + r0 < b1) { pc = bcol[b0 + r0]; pv = ba[b0 + r0]; }
+    for (int st = 0; st < ns; st++) {
+      const int cb0 = b0, cb1 = b1, cc = pc;
+      const double cv = pv;
+      const double av = g.shfl(mav, st);
+      if (st + 1 < ns) {
+        b0 = g.shfl(mb0, st + 1); b1 = g.shfl(mb1, st + 1);
+        pc = EMPTY;
+        if (b0 + r0 < b1) { pc = bcol[b0 + r0]; pv = ba[b0 + r0]; }
+      }
+      for (int jb = cb0 + r0; jb < cb1; jb += G) {
+        const bool first = (jb < cb0 + G);
+        const int c = first ? cc : bcol[jb];
+        const double p = (first ? cv : ba[jb]) * av;
+        unsigned h = hash_col(c) & mask;
+        for (;;) {
+          const int old = atomicCAS(&keys[h], EMPTY, c);
+          if (old == EMPTY) { double v = 0.0; v = v + p; vals[h] = v; break; }
+          if (old == c) { vals[h] = vals[h] + p; break; }
+          h = (h + 1) & mask;
+        }
+      }
+      g.sync();
+    }
+  }
+}
+
 // exact zeros leave the row (mxm stores y[ib] only if != 0); returns the survivor count
 template <class Group>
 __device__ __forceinline__ int drop_zeros_count(const Group &g, int *keys, const double *vals, int HS, int *red) {
@@ -157,7 +206,7 @@ __global__ void __launch_bounds__(256) k_spgemm_tile(int phase, const int *list,
   const int i = list[idx];
   int *keys = skeys + slot * HS;
   double *vals = svals + slot * HS;
-  accumulate_row(tile, i, aro, acol, aa, bro, bcol, ba, keys, vals, HS);
+  accumulate_row_tile<G>(tile, i, aro, acol, aa, bro, bcol, ba, keys, vals, HS);
   const int r0 = tile.thread_rank();
   if (phase == 1) {
     const int n = drop_zeros_count(tile, keys, vals, HS, sred + slot);
