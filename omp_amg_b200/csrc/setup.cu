@@ -691,6 +691,7 @@ void col_dot_transposed(double *s, const Csr &Tt, const Csr &M) {
 // interpolation (:598)
 Csr interpolation(const Csr &Af, const Csr &Ac, const Csr &Ar, double gamma2, double tol, int *rounds_out) {
   const int nf = Af.rn, nc = Ac.cn;
+  spgemm_cache_reset();
   Buf<double> Df(nf), Dfsqrti(nf), uc(nc), tmp(nf), v(nf), b(nf), Dc(nc), Dcinv(nc);
   diag_of(Df.p, Af);
   double *dfp = Df.p, *dfi = Dfsqrti.p;
@@ -937,6 +938,7 @@ void setup(i64 nnz, const int *dAi, const int *dAj, const double *dAv, Hierarchy
       parallel_for(rn, [=] DEV(i64 i) { if (cf[i]) ic[cp[i]] = il[i]; else jf[fp[i]] = il[i]; });
     }
     L.W = interpolation(L.Af, Ac, Afc, gamma2, itol, &L.interp_rounds);
+    spgemm_cache_reset();
     trace_csr("W", L.W);
     lap(H.t.interp);
 
@@ -973,6 +975,7 @@ void setup(i64 nnz, const int *dAi, const int *dAj, const double *dAv, Hierarchy
   H.t.device_total = H.t.total;
 #endif
   spgemm_stats_get(&H.t.spgemm, &H.t.spgemm_bytes, &H.t.spgemm_calls);
+  spgemm_cache_reset();
   stage_report();
   H.launches = c.launches - launches0;
   H.syncs = c.syncs - syncs0;

@@ -55,6 +55,7 @@ void trace_csr(const char *tag, const Csr &A);
 
 // device time / algorithmic bytes of the SpGEMM kernels since the last reset (spgemm.cu)
 void spgemm_stats_reset();
+void spgemm_cache_reset();      // drops the cached transpose of the last large left operand
 void spgemm_stats_get(double *seconds, i64 *bytes, i64 *calls);
 
 // element-wise helpers

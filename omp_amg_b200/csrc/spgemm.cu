@@ -538,11 +538,45 @@ void spgemm_stats_get(double *seconds, i64 *bytes, i64 *calls) {
 
 static int g_spgemm_impl = -1;
 
+static Csr spgemm_core(const Csr &A, const Csr &B);
+
+// X = A*B through the transposed product when that has the better shape.  Entry by entry,
+// (B'A')[c][i] = sum over k ascending of A'[k][i]*B'[c][k] has the same addends in the same
+// order as (AB)[i][c] = sum over k ascending of B[k][c]*A[i][k] (a product of two doubles does
+// not depend on the order of its factors), so X = (B'A')' bit for bit, exact zeros included.
+// Row-wise SpGEMM does one ordered step per entry of the row of A; long rows of A against short
+// rows of B (Af*W on the coarse levels: 500 against 50) are hundreds of nearly empty steps, while
+// the transposed product takes few steps that each fill the whole thread block.
+static Csr g_At_cache;
+static const void *g_At_key = nullptr;
+static i64 g_At_nnz = -1;
+static int g_At_rn = -1;
+void spgemm_cache_reset() { g_At_cache = Csr(); g_At_key = nullptr; g_At_nnz = -1; g_At_rn = -1; }
+
 Csr spgemm(const Csr &A, const Csr &B) {
   if (g_spgemm_impl < 0) { const char *e = getenv("AMGB_SPGEMM"); g_spgemm_impl = (e && !strcmp(e, "rowhash")) ? 0 : 1; }
   if (g_spgemm_impl == 0) return spgemm_rowhash(A, B);
-  StageTimer st_("prim.spgemm");
   if (A.cn != B.rn) throw Error(-4, "spgemm: dimension mismatch");
+  static int tr_on = -1;
+  if (tr_on < 0) { const char *e = getenv("AMGB_SPGEMM_TRANSPOSED"); tr_on = (e && *e == '0') ? 0 : 1; }
+  if (tr_on && A.rn > 0 && B.rn > 0 && A.nnz > (1 << 20) && B.nnz > 0) {
+    const double la = (double)A.nnz / A.rn, lb = (double)B.nnz / B.rn;
+    if (la > 64.0 && la > 4.0 * lb) {
+      StageTimer st_("prim.spgemm(transposed)");
+      if (g_At_key != (const void *)A.a.p || g_At_nnz != A.nnz || g_At_rn != A.rn) {   // A = Af recurs within a level
+        g_At_cache = transpose(A);
+        g_At_key = (const void *)A.a.p; g_At_nnz = A.nnz; g_At_rn = A.rn;
+      }
+      Csr Bt = transpose(B);
+      Csr Xt = spgemm_core(Bt, g_At_cache);
+      return transpose(Xt);
+    }
+  }
+  return spgemm_core(A, B);
+}
+
+static Csr spgemm_core(const Csr &A, const Csr &B) {
+  StageTimer st_("prim.spgemm");
   Context &c = ctx();
   const int rn = A.rn;
   if (rn == 0) { Csr X(0, B.cn, 0); X.ro.zero(); return X; }
@@ -776,6 +810,7 @@ Csr spgemm(const Csr &A, const Csr &B) {
 }
 #else
 void spgemm_stats_reset() {}
+void spgemm_cache_reset() {}
 void spgemm_stats_get(double *seconds, i64 *bytes, i64 *calls) { *seconds = 0; *bytes = 0; *calls = 0; }
 Csr spgemm(const Csr &A, const Csr &B) { return spgemm_rowhash(A, B); }
 #endif
