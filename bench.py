@@ -12,8 +12,11 @@ One "step" = one full hierarchy setup (amg_setup, amg_setup.c:60) of the workloa
           device time of those launches, both measured live inside the timed steps
   cpu_baseline  the CPU port of the reference (oracle/, sequential reductions) on a bounded
           sample of the same workload, scaled linearly in rows to the full size
-N > 1: the path does not shard yet ("replicas only", DESIGN.md section e): every rank sets up
-its own copy of the workload, no data-path collective; value stays the per-setup time.
+N > 1 (one process per GPU, torchrun): the ranks build ONE hierarchy together -- the SpGEMM rows
+and the local solves of the coarse columns are partitioned over the ranks and the blocks exchanged
+through the library's NCCL communicator (DESIGN.md row e); every rank ends with the same,
+bit-identical hierarchy.  Total work is fixed, so scaling is "strong" and value is the time of that
+one setup (max over ranks).  --parallel replicas runs N independent setups instead.
 """
 from __future__ import annotations
 
@@ -144,6 +147,9 @@ def main():
     ap.add_argument("--reduce", default="seq", choices=["seq", "tree"],
                     help="seq: reference-order dot products (bit-identical hierarchy); tree: fast mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parallel", default="partitioned", choices=["partitioned", "replicas"],
+                    help="N > 1: partitioned = one setup, stages row-partitioned over the ranks (NCCL); "
+                         "replicas = N independent setups")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -166,6 +172,19 @@ def main():
     L = amg.lib()
     api._check(L, L.amgb_init(local))
     api.set_reduce_mode(api.REDUCE_SEQUENTIAL if args.reduce == "seq" else api.REDUCE_TREE, L=L)
+    partitioned = False
+    if world > 1 and args.parallel == "partitioned":
+        ok = 1
+        try:
+            api.comm_init(L)
+        except Exception as e:          # no NCCL for the library: say so and run replicas
+            sys.stderr.write("rank %d: comm_init failed (%s); running replicas\n" % (rank, e))
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        partitioned = bool(int(flag[0]))
+        if not partitioned:
+            api.comm_finalize(L)
 
     Ai, Aj, Av = workload_matrix(args.workload, args.n)
     nnz = len(Av)
@@ -234,12 +253,16 @@ def main():
         last = tims[-1]
         line = {
             "metric": "amg_setup_time", "value": per_step, "unit": "s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": False, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": False,
+            "scaling": "strong" if partitioned else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s_%d^3_full_hierarchy_setup" % (args.workload, args.n), "rows": rows, "nnz": nnz,
                        "levels": nlev, "reduce_mode": args.reduce, "l2": "inputs_exceed_l2" if nnz * 16 > 126e6 else "small_input",
-                       "parallelism": "replicas_only_x%d" % world},
-            "rows_per_s": world * rows / per_step,
+                       "parallelism": ("row_partitioned_spgemm_and_local_solves_x%d" % world) if partitioned
+                       else ("replicas_x%d" % world if world > 1 else "single_gpu")},
+            "rows_per_s": (1 if partitioned else world) * rows / per_step,
+            "comm": {"exchanges_per_step": int(last["comm_calls"]), "bytes_received_per_rank_per_step": int(last["comm_bytes"]),
+                     "device_s_per_step": last["comm_device_s"], "transport": "nccl grouped broadcast (all-gather of row blocks)"},
             "wall_s_per_step": wall / args.steps,
             "stage_s": {k: last[k] for k in ("build_csr", "coarsen", "smoother", "lanczos", "interp", "galerkin")},
             "gpu_launches": int(sum(t["launches"] for t in tims)),
@@ -273,6 +296,8 @@ def main():
                           % (args.workload, ns, srows, ts, rows)}
         print(json.dumps(line), flush=True)
     if world > 1:
+        if partitioned:
+            api.comm_finalize(L)
         dist.destroy_process_group()
 
 

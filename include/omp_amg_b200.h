@@ -69,8 +69,29 @@ int amgb_solve_device(const amgb_hier *h, double *dx, const double *db);      /*
  * t[6]=galerkin (host seconds, stream synchronised at stage ends)
  * t[7]=device seconds inside SpGEMM kernels  t[8]=their algorithmic bytes  t[9]=SpGEMM calls
  * t[10]=kernel launches  t[11]=host syncs
- * t[12]=CUDA-event seconds from the first to the last kernel of the setup  t[13..15] reserved */
+ * t[12]=CUDA-event seconds from the first to the last kernel of the setup
+ * t[13]=exchanges of the row-partitioned stages  t[14]=bytes this rank received in them
+ * t[15]=device seconds inside the exchanges */
 int amgb_timing(const amgb_hier *h, double t[16]);
+
+/* ---- several GPUs: one process per GPU, row-partitioned stages ----
+ * The reference distributes the coarse problem over MPI ranks (struct comm, crs.h:14; the setup
+ * itself is serial, serial_amg.c).  Here every rank calls amgb_setup with the same matrix; the
+ * SpGEMM rows (mxm, amg_setup.c:1894) and the local solves of the coarse columns (interp,
+ * amg_setup.c:2053) are partitioned over the ranks and the blocks are exchanged through NCCL
+ * (NVLink), so that every rank ends with the same hierarchy, bit-identical to one GPU's.
+ * Rank 0 obtains an id (amgb_comm_unique_id), the host program hands it to the other ranks
+ * (MPI_Bcast / torch.distributed), then every rank calls amgb_comm_init on its own device.
+ * amgb_comm_init_host installs a host transport instead and exists only in the host-emulation
+ * build used by the CPU tests (the product build returns -112). */
+int amgb_comm_unique_id(uint8_t id[128]);
+int amgb_comm_init(int rank, int size, const uint8_t id[128]);
+/* in-place all-gather: rank r owns bytes [off[r], off[r+1]) of buf; returns 0 on success */
+typedef int (*amgb_allgatherv_fn)(void *buf, const long long *off, int size, void *user);
+int amgb_comm_init_host(int rank, int size, amgb_allgatherv_fn fn, void *user);
+int amgb_comm_finalize(void);
+int amgb_comm_rank(void);
+int amgb_comm_size(void);
 
 /* ---- device memory ----
  * Temporaries come from a caching allocator inside the library; amgb_release_memory() hands the

@@ -25,6 +25,10 @@ class AmgError(RuntimeError):
     pass
 
 
+# int fn(void *buf, const long long *off, int size, void *user): in-place all-gather of byte segments
+ALLGATHERV_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_longlong), C.c_int, C.c_void_p)
+
+
 def lib_path():
     return _LIB_PATH
 
@@ -71,6 +75,9 @@ def _declare(L):
     L.crs_amg_free.restype = None
     L.crs_amg_hierarchy.argtypes = [vp]
     L.crs_amg_hierarchy.restype = vp
+    L.amgb_comm_unique_id.argtypes = [C.c_char_p]
+    L.amgb_comm_init.argtypes = [C.c_int, C.c_int, C.c_char_p]
+    L.amgb_comm_init_host.argtypes = [C.c_int, C.c_int, ALLGATHERV_FN, vp]
     return L
 
 
@@ -120,6 +127,63 @@ def device_count(L=None):
 def _check(L, rc):
     if rc != 0:
         raise AmgError("omp_amg_b200 error %d: %s" % (rc, L.amgb_last_error().decode()))
+
+
+def comm_init(L=None, device=None):
+    """Join the ranks of the current ``torch.distributed`` job (one process per GPU) so that
+    ``amg_setup`` partitions its SpGEMM rows and local solves over them and exchanges the blocks
+    through NCCL.  torch.distributed only carries the 128-byte NCCL id from rank 0 to the others;
+    the data path is the library's own communicator.  Every rank must then call ``amg_setup`` with
+    the same matrix."""
+    import torch
+    import torch.distributed as dist
+    L = L or lib()
+    rank, size = dist.get_rank(), dist.get_world_size()
+    if device is not None:
+        _check(L, L.amgb_init(int(device)))
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        _check(L, L.amgb_comm_unique_id(buf))
+    on_gpu = dist.get_backend() == "nccl"
+    t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+    if on_gpu:
+        t = t.cuda()
+    dist.broadcast(t, src=0)
+    ident = bytes(t.cpu().numpy().tobytes())
+    _check(L, L.amgb_comm_init(rank, size, ident))
+    return rank, size
+
+
+def comm_init_host_gloo(L):
+    """Host transport over the current (gloo) process group for the host-emulation build -- a test
+    tool for the partitioning logic on CPU.  The product build refuses it (error -112)."""
+    import torch
+    import torch.distributed as dist
+    rank, size = dist.get_rank(), dist.get_world_size()
+
+    def gather(buf, off, n, user):
+        try:
+            for r in range(n):
+                nb = off[r + 1] - off[r]
+                if nb <= 0:
+                    continue
+                seg = np.ctypeslib.as_array((C.c_ubyte * nb).from_address(buf + off[r]))
+                dist.broadcast(torch.from_numpy(seg), src=r)
+            return 0
+        except Exception:           # never unwind through the C frames
+            import traceback
+            traceback.print_exc()
+            return 1
+
+    cb = ALLGATHERV_FN(gather)
+    L._amgb_host_cb = cb            # keep the trampoline alive as long as the library handle
+    _check(L, L.amgb_comm_init_host(rank, size, cb, None))
+    return rank, size
+
+
+def comm_finalize(L=None):
+    L = L or lib()
+    _check(L, L.amgb_comm_finalize())
 
 
 class Hierarchy:
@@ -186,7 +250,8 @@ class Hierarchy:
         t = (C.c_double * 16)()
         _check(self._L, self._L.amgb_timing(self._h, t))
         keys = ("total", "build_csr", "coarsen", "smoother", "lanczos", "interp", "galerkin",
-                "spgemm_device_s", "spgemm_bytes", "spgemm_calls", "launches", "syncs", "device_total_s")
+                "spgemm_device_s", "spgemm_bytes", "spgemm_calls", "launches", "syncs", "device_total_s",
+                "comm_calls", "comm_bytes", "comm_device_s")
         return dict(zip(keys, list(t)))
 
     def free(self):

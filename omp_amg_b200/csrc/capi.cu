@@ -1,6 +1,7 @@
 // capi.cu -- the C ABI declared in include/omp_amg_b200.h.
 #include "../../include/omp_amg_b200.h"
 #include "setup.cuh"
+#include "comm.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -280,9 +281,40 @@ int amgb_timing(const amgb_hier *h, double t[16]) {
   t[0] = s.total; t[1] = s.build; t[2] = s.coarsen; t[3] = s.smoother; t[4] = s.lanczos;
   t[5] = s.interp; t[6] = s.galerkin; t[7] = s.spgemm; t[8] = (double)s.spgemm_bytes;
   t[9] = (double)s.spgemm_calls; t[10] = (double)h->H.launches; t[11] = (double)h->H.syncs;
-  t[12] = s.device_total; t[13] = t[14] = t[15] = 0;
+  t[12] = s.device_total; t[13] = (double)s.comm_calls; t[14] = (double)s.comm_bytes; t[15] = s.comm;
   return 0;
 }
+
+// ---- ranks (one process per GPU) ----
+int amgb_comm_unique_id(uint8_t id[128]) {
+  API_BEGIN
+  if (!id) return fail(-2, "null id");
+  comm_unique_id(id);
+  return 0;
+  API_END
+}
+int amgb_comm_init(int rank, int size, const uint8_t id[128]) {
+  API_BEGIN
+  ctx_init(-1);
+  if (size > 1 && !id) return fail(-2, "null id");
+  comm_init_nccl(rank, size, id);
+  return 0;
+  API_END
+}
+int amgb_comm_init_host(int rank, int size, amgb_allgatherv_fn fn, void *user) {
+  API_BEGIN
+  comm_init_host(rank, size, (host_allgatherv_fn)fn, user);
+  return 0;
+  API_END
+}
+int amgb_comm_finalize(void) {
+  API_BEGIN
+  comm_finalize();
+  return 0;
+  API_END
+}
+int amgb_comm_rank(void) { return comm_rank(); }
+int amgb_comm_size(void) { return comm_size(); }
 
 void amgb_release_memory(void) { dev_release_cache(); }
 int64_t amgb_peak_device_bytes(void) { return (int64_t)dev_peak_bytes(); }

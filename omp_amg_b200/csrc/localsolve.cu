@@ -6,6 +6,7 @@
 // multiply and add (the library is compiled with --fmad=false).  Parallelism is only ever over
 // independent outputs, never inside one sum.
 #include "localsolve.cuh"
+#include "comm.cuh"
 
 #ifndef AMGB_EMU
 #include <cooperative_groups.h>
@@ -48,6 +49,29 @@ void qq_offsets(QQStore &qq, const Csr &Wt) {
   qq.QQ.alloc(total);
 }
 
+// Partition of the coarse columns over the ranks (one process per GPU): contiguous column
+// ranges holding equal shares of the Q store (its size stands in for the work).  cs[r] is the
+// first column of rank r, off[r] the byte offset of its Q blocks; false = not partitioned.
+static bool q_partition(const QStore &qs, int n, std::vector<int> &cs, std::vector<i64> &off) {
+  const int P = comm_size();
+  if (P <= 1 || n < P || qs.total < comm_min_work()) return false;
+  Buf<i64> sb(2 * ((i64)P + 1));
+  i64 *sp = sb.p;
+  const i64 *qo = qs.qoff.p;
+  const i64 total = qs.total;
+  parallel_for((i64)P + 1, [=] DEV(i64 r) {
+    const i64 target = total / P * r;
+    int lo = 0, hi = n;
+    if (r == P) lo = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (qo[mid] < target) lo = mid + 1; else hi = mid; }
+    sp[2 * r] = lo; sp[2 * r + 1] = qo[lo];
+  });
+  std::vector<i64> h = sb.download();
+  cs.resize((size_t)P + 1); off.resize((size_t)P + 1);
+  for (int r = 0; r <= P; r++) { cs[(size_t)r] = (int)h[2 * (size_t)r]; off[(size_t)r] = (i64)sizeof(double) * h[2 * (size_t)r + 1]; }
+  return true;
+}
+
 #ifdef AMGB_EMU
 // =======================================================================================
 // host emulation: straight restatement, one logical thread per column / row
@@ -60,7 +84,12 @@ void build_q_store(QStore &qs, const Csr &Wt, const Csr &At) {
   double *Qall = qs.Q.p, *sc = scratch.p;
   const i64 *qo = qs.qoff.p;
   const int mx = qs.maxnz + 1;
-  parallel_for(Wt.rn, [=] DEV(i64 i) {
+  std::vector<int> cs;
+  std::vector<i64> off;
+  const bool part = q_partition(qs, Wt.rn, cs, off);
+  const int c0 = part ? cs[(size_t)comm_rank()] : 0, c1 = part ? cs[(size_t)comm_rank() + 1] : Wt.rn;
+  parallel_for(c1 - c0, [=] DEV(i64 ii) {
+    const i64 i = c0 + ii;
     const int b = wro[i], nz = wro[i + 1] - b;
     const int *Qj = wcol + b;
     double *Q = Qall + qo[i], *sqv1 = sc, *sqv2 = sc + mx;
@@ -77,6 +106,7 @@ void build_q_store(QStore &qs, const Csr &Wt, const Csr &At) {
       qk[k] = -alpha;
     }
   });
+  if (part) comm_allgatherv(qs.Q.p, off.data());
 }
 void apply_q(const QStore &qs, Csr &Wt, const Csr &Bt, const double *u, const double *lambda) {
   Buf<double> scratch((i64)2 * (qs.maxnz + 1));
@@ -224,6 +254,56 @@ __global__ void k_build_q_block(const int *list, int nlist, int nzcap, const int
   }
 }
 
+// Very large supports (the reference piles every F row without a coupling into column 0, :2229):
+// one column is worked on by a CLUSTER of 8 blocks (2048 threads, 8 SMs' worth of L2 bandwidth);
+// Q and the two work vectors live in HBM/L2 and the k-steps are separated by cluster barriers.
+// The arithmetic per output is the same as in build_q_coop.
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(256)
+k_build_q_cluster(const int *list, int nlist, int maxnz, const int *wro, const int *wcol, const int *aro,
+                  const int *acol, const double *aa, double *Qall, const i64 *qoff, double *scratch) {
+  cg::cluster_group cl = cg::this_cluster();
+  __shared__ double alpha_sh;
+  const int cidx = blockIdx.x / 8;
+  if (cidx >= nlist) return;                      // whole cluster leaves together
+  const int i = list[cidx];
+  const int b = wro[i], nz = wro[i + 1] - b;
+  const int *Qj = wcol + b;
+  double *Q = Qall + qoff[i];
+  double *sqv1 = scratch + (size_t)cidx * 2 * maxnz, *sqv2 = sqv1 + maxnz;
+  const int tid = (int)cl.block_rank() * 256 + threadIdx.x, T = 8 * 256;
+  for (int k = 0; k < nz; k++) {
+    const int s = Qj[k];
+    const int ab = aro[s], an = aro[s + 1] - ab;
+    double *qk = Q + tri(k);
+    for (int m = tid; m <= k; m += T) sqv1[m] = row_at(acol + ab, aa + ab, an, Qj[m]);
+    cl.sync();
+    for (int r = tid; r < k; r += T) {
+      double v = 0;
+      const double *u = Q + tri(r);
+      for (int j = 0; j <= r; j++) v = v + u[j] * sqv1[j];
+      sqv2[r] = v;
+    }
+    cl.sync();
+    for (int r = tid; r < k; r += T) {
+      double y = 0;
+      for (int j = r; j < k; j++) y = y + Q[tri(j) + r] * sqv2[j];
+      qk[r] = y;
+    }
+    cl.sync();
+    if (threadIdx.x == 0) {                       // one thread per block forms the recurrence
+      double alpha = sqv1[k];
+      for (int m = 0; m < k; m++) alpha = alpha - sqv1[m] * qk[m];
+      alpha_sh = -1.0 / sqrt(alpha);
+    }
+    __syncthreads();
+    const double alpha = alpha_sh;
+    cl.sync();                                     // every block has read q_k before it is scaled
+    for (int m = tid; m < k; m += T) qk[m] = qk[m] * alpha;
+    if (tid == 0) qk[k] = -alpha;
+    cl.sync();
+  }
+}
+
 static void set_smem(const void *fn, size_t bytes) {
   CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
 }
@@ -235,15 +315,21 @@ void build_q_store(QStore &qs, const Csr &Wt, const Csr &At) {
   // bin the columns by support size: <=8 | <=32 | <=64 | <=144 | larger.  The block size and the
   // shared-memory footprint follow the bin, so that small supports do not pay the occupancy of
   // the largest one.
-  constexpr int NBIN = 5;
+  constexpr int NBIN = 6;
   Buf<int> lists((i64)NBIN * n), cnt(NBIN);
   cnt.zero();
   const int *wro = Wt.ro.p;
   int *lp = lists.p, *cp = cnt.p;
-  parallel_for(n, [=] DEV(i64 i) {
+  // several ranks: this rank builds the Q blocks of its column range, the blocks are exchanged
+  std::vector<int> cs;
+  std::vector<i64> off;
+  const bool part = q_partition(qs, n, cs, off);
+  const int c0 = part ? cs[(size_t)comm_rank()] : 0, c1 = part ? cs[(size_t)comm_rank() + 1] : n;
+  parallel_for(c1 - c0, [=] DEV(i64 ii) {
+    const i64 i = c0 + ii;
     const int nz = wro[i + 1] - wro[i];
     if (nz == 0) return;
-    const int bin = nz <= 8 ? 0 : nz <= 32 ? 1 : nz <= 64 ? 2 : nz <= 144 ? 3 : 4;
+    const int bin = nz <= 8 ? 0 : nz <= 32 ? 1 : nz <= 64 ? 2 : nz <= 144 ? 3 : nz <= 256 ? 4 : 5;
     const int p = atomic_add(&cp[bin], 1);
     lp[(i64)bin * n + p] = (int)i;
   });
@@ -265,13 +351,18 @@ void build_q_store(QStore &qs, const Csr &Wt, const Csr &At) {
                                                                    acol, aa, qs.Q.p, qs.qoff.p);
     c.launches++; post_launch("build_q_block");
   }
+  if (hc[5]) {
+    if (qs.maxnz > 12800) throw Error(-12, "interpolation support of " + std::to_string(qs.maxnz) + " rows exceeds the kernel limit (12800)");
+    Buf<double> scratch((i64)hc[5] * 2 * qs.maxnz);
+    k_build_q_cluster<<<hc[5] * 8, 256, 0, c.stream>>>(lp + 5 * (i64)n, hc[5], qs.maxnz, wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p, scratch.p);
+    c.launches++; post_launch("build_q_cluster");
+  }
   if (hc[4]) {
-    const size_t sm = sizeof(double) * (2 * (size_t)qs.maxnz);
-    if (sm > 200 * 1024) throw Error(-12, "interpolation support of " + std::to_string(qs.maxnz) + " rows exceeds the kernel limit (12800)");
-    if (sm > 48 * 1024) set_smem((const void *)k_build_q_block<false>, sm);
-    k_build_q_block<false><<<hc[4], 256, sm, c.stream>>>(lp + 4 * (i64)n, hc[4], qs.maxnz, wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
+    const size_t sm = sizeof(double) * (2 * (size_t)256);
+    k_build_q_block<false><<<hc[4], 256, sm, c.stream>>>(lp + 4 * (i64)n, hc[4], 256, wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
     c.launches++; post_launch("build_q_global");
   }
+  if (part) comm_allgatherv(qs.Q.p, off.data());
 }
 
 // ---- apply: W row := Q (Q^t (R(B e_i + u_i lambda))) ----
@@ -340,6 +431,7 @@ __global__ void __launch_bounds__(128) k_form_qq(int n, const int *wro, const do
   const int i = blockIdx.x;
   if (i >= n) return;
   const int nz = wro[i + 1] - wro[i];
+  if (nz > 192) return;                       // done by k_form_qq_big
   const double *Q = Qall + qoff[i];
   double *out = QQ + qqoff[i];
   for (int idx = threadIdx.x; idx < nz * nz; idx += blockDim.x) {
@@ -368,11 +460,43 @@ __global__ void __launch_bounds__(256) k_form_qq_small(int n, const int *wro, co
     out[(i64)j * nz + m] = acc;
   }
 }
+// columns with a large support: the pairs (m <= j) of one column are spread over gridDim.x blocks
+__global__ void __launch_bounds__(256) k_form_qq_big(const int *list, const int *wro, const double *Qall,
+                                                     const i64 *qoff, double *QQ, const i64 *qqoff) {
+  const int i = list[blockIdx.y];
+  const int nz = wro[i + 1] - wro[i];
+  const double *Q = Qall + qoff[i];
+  double *out = QQ + qqoff[i];
+  const i64 total = (i64)nz * nz;
+  for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (i64)gridDim.x * blockDim.x) {
+    const int m = (int)(idx / nz), j = (int)(idx - (i64)m * nz);
+    if (m > j) continue;
+    double acc = 0;
+    for (int k = j; k < nz; k++) acc = acc + Q[tri(k) + m] * Q[tri(k) + j];
+    out[(i64)m * nz + j] = acc;
+    out[(i64)j * nz + m] = acc;
+  }
+}
+#define QQ_BIG 192
 void form_qq(QQStore &qq, const QStore &qs, const Csr &Wt) {
   qq_offsets(qq, Wt);
   const int n = Wt.rn;
   if (n == 0) return;
   Context &c = ctx();
+  if (qs.maxnz > QQ_BIG) {
+    // the few columns with a very large support (the reference piles every F row without a
+    // coupling into column 0, :2229) would otherwise be one block each and set the run time
+    Buf<int> big(n), nbig(1);
+    nbig.zero();
+    const int *wro = Wt.ro.p;
+    int *bp = big.p, *np_ = nbig.p;
+    parallel_for(n, [=] DEV(i64 i) { if (wro[i + 1] - wro[i] > QQ_BIG) bp[atomic_add(np_, 1)] = (int)i; });
+    const int nb = nbig.get(0);
+    if (nb) {
+      k_form_qq_big<<<dim3(96, nb), 256, 0, c.stream>>>(big.p, Wt.ro.p, qs.Q.p, qs.qoff.p, qq.QQ.p, qq.qqoff.p);
+      c.launches++; post_launch("form_qq_big");
+    }
+  }
   if (qs.maxnz <= 12)
     k_form_qq_small<<<(n + 31) / 32, 256, 0, c.stream>>>(n, Wt.ro.p, qs.Q.p, qs.qoff.p, qq.QQ.p, qq.qqoff.p);
   else

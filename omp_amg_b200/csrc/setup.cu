@@ -2,6 +2,7 @@
 // Host code only orchestrates: every matrix- or vector-sized operation is a kernel.
 // All citations are amg_setup.c lines of the reference unless another file is named.
 #include "setup.cuh"
+#include "comm.cuh"
 #include "localsolve.cuh"
 #include <chrono>
 
@@ -839,6 +840,7 @@ void setup(i64 nnz, const int *dAi, const int *dAj, const double *dAv, Hierarchy
   const double t_begin = now_s();
   double t0 = t_begin;
   spgemm_stats_reset();
+  comm_stats_reset();
 #ifndef AMGB_EMU
   cudaEvent_t ev0, ev1;
   CUDA_CHECK(cudaEventCreate(&ev0)); CUDA_CHECK(cudaEventCreate(&ev1));
@@ -975,6 +977,7 @@ void setup(i64 nnz, const int *dAi, const int *dAj, const double *dAv, Hierarchy
   H.t.device_total = H.t.total;
 #endif
   spgemm_stats_get(&H.t.spgemm, &H.t.spgemm_bytes, &H.t.spgemm_calls);
+  comm_stats_get(&H.t.comm_calls, &H.t.comm_bytes, &H.t.comm);
   spgemm_cache_reset();
   stage_report();
   H.launches = c.launches - launches0;

@@ -1,6 +1,7 @@
 // sparse.cu -- sparse primitives (first generation: one logical thread per row; the hot ones
 // have warp-cooperative replacements in spgemm.cu / spmv kernels below).
 #include "sparse.cuh"
+#include "comm.cuh"
 
 namespace amgb {
 
@@ -409,6 +410,69 @@ int max_row_len(const Csr &A) {
 // SpGEMM, generation 1 (reference semantics of mxm :1894): one logical thread per row, an
 // open-addressing table per row in HBM.  Every X[i][c] is accumulated over k ascending.
 // ---------------------------------------------------------------------------------------
+// Row-partitioned X = A*B (one process per GPU): rank r forms the rows [row_split(r),
+// row_split(r+1)) of X from its row block of A with the single-GPU kernel `local`; the row
+// lengths and then the entries of the blocks are exchanged in place (comm_allgatherv), so every
+// rank ends with the whole X.  Each row is computed by exactly one rank with the same kernel as
+// on one GPU, hence X is bit-identical to local(A, B).
+Csr spgemm_partitioned(const Csr &A, const Csr &B, Csr (*local)(const Csr &, const Csr &)) {
+  const int P = comm_size(), me = comm_rank();
+  const int rn = A.rn;
+  const int r0 = (int)row_split(rn, me), r1 = (int)row_split(rn, me + 1), ln = r1 - r0;
+  Csr Xl;
+  {
+    // the row block of A (offsets rebased); its entries are one contiguous range of A
+    Buf<int> span(2);
+    const int *aro = A.ro.p;
+    int *sp = span.p;
+    parallel_for(1, [=] DEV(i64) { sp[0] = aro[r0]; sp[1] = aro[r1]; });
+    std::vector<int> hs = span.download();
+    Csr Al(ln, A.cn, (i64)hs[1] - hs[0]);
+    int *lro = Al.ro.p;
+    const int base = hs[0];
+    parallel_for((i64)ln + 1, [=] DEV(i64 i) { lro[i] = aro[r0 + i] - base; });
+    if (Al.nnz) {
+      d2d(Al.col.p, A.col.p + base, sizeof(int) * (size_t)Al.nnz);
+      d2d(Al.a.p, A.a.p + base, sizeof(double) * (size_t)Al.nnz);
+    }
+    Xl = local(Al, B);
+  }
+  // row lengths of all blocks, then the global offsets
+  Buf<int> cnt((i64)rn + 1), xro((i64)rn + 1);
+  {
+    int *cp = cnt.p;
+    const int *lro = Xl.ro.p;
+    parallel_for(ln, [=] DEV(i64 i) { cp[r0 + i] = lro[i + 1] - lro[i]; });
+    std::vector<i64> off((size_t)P + 1);
+    for (int r = 0; r <= P; r++) off[(size_t)r] = (i64)sizeof(int) * row_split(rn, r);
+    comm_allgatherv(cnt.p, off.data());
+  }
+  const i64 nnz = exclusive_scan(cnt.p, xro.p, rn);
+  Csr X(rn, B.cn, nnz);
+  X.ro = std::move(xro);
+  std::vector<i64> seg((size_t)P + 1);
+  {
+    Buf<int> sb((i64)P + 1);
+    int *sp = sb.p;
+    const int *xr = X.ro.p;
+    const i64 rnl = rn;
+    parallel_for((i64)P + 1, [=] DEV(i64 r) { sp[r] = xr[rnl * r / P]; });
+    std::vector<int> hs = sb.download();
+    for (int r = 0; r <= P; r++) seg[(size_t)r] = hs[(size_t)r];
+  }
+  if (seg[(size_t)me + 1] - seg[(size_t)me] != Xl.nnz) throw Error(-114, "spgemm_partitioned: block size mismatch");
+  if (Xl.nnz) {
+    d2d(X.col.p + seg[(size_t)me], Xl.col.p, sizeof(int) * (size_t)Xl.nnz);
+    d2d(X.a.p + seg[(size_t)me], Xl.a.p, sizeof(double) * (size_t)Xl.nnz);
+  }
+  std::vector<i64> off((size_t)P + 1);
+  for (int r = 0; r <= P; r++) off[(size_t)r] = (i64)sizeof(int) * seg[(size_t)r];
+  comm_allgatherv(X.col.p, off.data());
+  for (int r = 0; r <= P; r++) off[(size_t)r] = (i64)sizeof(double) * seg[(size_t)r];
+  comm_allgatherv(X.a.p, off.data());
+  return X;
+}
+
 Csr spgemm_rowhash(const Csr &A, const Csr &B) {
   if (A.cn != B.rn) throw Error(-4, "spgemm: dimension mismatch");
   const int rn = A.rn;

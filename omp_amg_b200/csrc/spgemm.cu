@@ -12,6 +12,7 @@
 // entries per row, a scan turns counts into row offsets, phase 2 recomputes, sorts the table
 // (bitonic, zeros and empty slots pushed to the end) and writes the row.
 #include "sparse.cuh"
+#include "comm.cuh"
 
 #ifndef AMGB_EMU
 #include <cooperative_groups.h>
@@ -21,6 +22,7 @@ namespace cg = cooperative_groups;
 namespace amgb {
 
 Csr spgemm_rowhash(const Csr &A, const Csr &B);
+Csr spgemm_partitioned(const Csr &A, const Csr &B, Csr (*local)(const Csr &, const Csr &));
 
 #ifndef AMGB_EMU
 namespace {
@@ -538,7 +540,13 @@ void spgemm_stats_get(double *seconds, i64 *bytes, i64 *calls) {
 
 static int g_spgemm_impl = -1;
 
-static Csr spgemm_core(const Csr &A, const Csr &B);
+static Csr spgemm_core_local(const Csr &A, const Csr &B);
+// one GPU: the kernels below; several ranks: the rows of X are partitioned (sparse.cu)
+static Csr spgemm_core(const Csr &A, const Csr &B) {
+  if (comm_active() && A.rn >= comm_size() && A.nnz + B.nnz >= comm_min_work())
+    return spgemm_partitioned(A, B, spgemm_core_local);
+  return spgemm_core_local(A, B);
+}
 
 // X = A*B through the transposed product when that has the better shape.  Entry by entry,
 // (B'A')[c][i] = sum over k ascending of A'[k][i]*B'[c][k] has the same addends in the same
@@ -575,7 +583,7 @@ Csr spgemm(const Csr &A, const Csr &B) {
   return spgemm_core(A, B);
 }
 
-static Csr spgemm_core(const Csr &A, const Csr &B) {
+static Csr spgemm_core_local(const Csr &A, const Csr &B) {
   StageTimer st_("prim.spgemm");
   Context &c = ctx();
   const int rn = A.rn;
@@ -812,7 +820,11 @@ static Csr spgemm_core(const Csr &A, const Csr &B) {
 void spgemm_stats_reset() {}
 void spgemm_cache_reset() {}
 void spgemm_stats_get(double *seconds, i64 *bytes, i64 *calls) { *seconds = 0; *bytes = 0; *calls = 0; }
-Csr spgemm(const Csr &A, const Csr &B) { return spgemm_rowhash(A, B); }
+Csr spgemm(const Csr &A, const Csr &B) {
+  if (comm_active() && A.rn >= comm_size() && A.nnz + B.nnz >= comm_min_work())
+    return spgemm_partitioned(A, B, spgemm_rowhash);
+  return spgemm_rowhash(A, B);
+}
 #endif
 
 }  // namespace amgb

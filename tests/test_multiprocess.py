@@ -52,3 +52,52 @@ def test_max_over_ranks_reduction_gloo_world2():
         p.join(60)
         assert p.exitcode == 0
     assert out[0][1] == [2.0, 10.0] and out[1][1] == [2.0, 10.0]
+
+
+# ---------------------------------------------------------------------------------------
+# Row-partitioned setup on 2 and 3 ranks (DESIGN.md row e).  The host-emulation build runs the same
+# partitioning code as the product (spgemm_partitioned, q_partition) with a gloo transport in
+# place of NCCL; every rank must end with the hierarchy one rank builds, bit for bit.
+# ---------------------------------------------------------------------------------------
+def _dist_worker(rank, world, port, q, case):
+    import numpy as np
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      AMGB_DIST_MIN_NNZ="0")     # partition every product, however small
+    from util import EMU_SO, api, amg, fetch, orc
+    from omp_amg_b200 import matrices
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        L = api.lib(EMU_SO)
+        mat = {"poisson7_8": lambda: matrices.poisson7(8), "aniso_6": lambda: matrices.aniso7(6),
+               "amgdmp": lambda: matrices.read_amgdmp(os.path.join(ROOT, "tests", "golden"))}[case]()
+        single = fetch(amg.amg_setup(*mat, L=L))             # before joining: one rank, no exchange
+        api.comm_init_host_gloo(L)
+        assert L.amgb_comm_size() == world and L.amgb_comm_rank() == rank
+        H = amg.amg_setup(*mat, L=L)
+        t = H.timing()
+        got = fetch(H)
+        bad = orc.compare(got, single)
+        api.comm_finalize(L)
+        q.put((rank, bad[:3], int(t["comm_calls"]), int(t["comm_bytes"])))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case,world,port", [("poisson7_8", 2, 29641), ("aniso_6", 3, 29642), ("amgdmp", 2, 29643)])
+def test_row_partitioned_setup_matches_single_rank(case, world, port):
+    import torch.multiprocessing as mp
+    subprocess.run(["make", "-j4", "-C", os.path.join(ROOT, "omp_amg_b200", "csrc"), "emu"], check=True,
+                   stdout=subprocess.DEVNULL)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_dist_worker, args=(r, world, port, q, case)) for r in range(world)]
+    for p in ps:
+        p.start()
+    out = sorted(q.get(timeout=600) for _ in ps)
+    for p in ps:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, bad, calls, nbytes in out:
+        assert not bad, "rank %d differs from the single-rank hierarchy: %s" % (rank, bad)
+        assert calls > 0 and nbytes > 0, "rank %d exchanged nothing: the stages were not partitioned" % rank
