@@ -133,9 +133,10 @@ void comm_init_host(int rank, int size, host_allgatherv_fn fn, void *user) {
 #endif
 }
 
-void comm_allgatherv(void *buf, const i64 *off) {
+void comm_allgatherv(void *buf, const i64 *off, const char *what) {
   const int P = g_comm.size;
   if (P <= 1) return;
+  StageTimer st_(what);      // AMGB_STAGE_LOG: time waiting for + inside the exchange, per call site
   g_comm.calls++;
   g_comm.bytes += (off[P] - off[0]) - (off[g_comm.rank + 1] - off[g_comm.rank]);
 #ifndef AMGB_EMU

@@ -106,7 +106,7 @@ void build_q_store(QStore &qs, const Csr &Wt, const Csr &At) {
       qk[k] = -alpha;
     }
   });
-  if (part) comm_allgatherv(qs.Q.p, off.data());
+  if (part) comm_allgatherv(qs.Q.p, off.data(), "comm.q_blocks");
 }
 void apply_q(const QStore &qs, Csr &Wt, const Csr &Bt, const double *u, const double *lambda) {
   Buf<double> scratch((i64)2 * (qs.maxnz + 1));
@@ -173,32 +173,89 @@ void lmop_accumulate(Csr &S, const QQStore &qq, const double *u, const Csr &Wskt
 // =======================================================================================
 // CUDA: G cooperating threads per coarse column (G = 8, 32, or a whole block)
 // =======================================================================================
-template <class Group>
-__device__ __forceinline__ void build_q_coop(const Group &g, int nz, const int *Qj, const int *aro,
-                                             const int *acol, const double *aa, double *Q,
-                                             double *sqv1, double *sqv2) {
+// Ordered sums whose left operand streams from HBM/L2: v (+|-)= a[j]*b[j] for j ascending, one add
+// after the other as in the reference, while the loads of a run one batch of U ahead of the adds
+// (the sum is a dependent chain; without the explicit batches every add waits for its own load).
+template <int U, bool SUB>
+__device__ __forceinline__ double chain_dot(double v, const double *a, const double *b, int n) {
+  double cur[U], nxt[U];
+  int j = 0;
+  if (n >= U) {
+#pragma unroll
+    for (int t = 0; t < U; t++) cur[t] = a[t];
+  }
+  while (j + U <= n) {
+    if (j + 2 * U <= n) {
+#pragma unroll
+      for (int t = 0; t < U; t++) nxt[t] = a[j + U + t];
+    }
+#pragma unroll
+    for (int t = 0; t < U; t++) { const double p = cur[t] * b[j + t]; v = SUB ? v - p : v + p; }
+#pragma unroll
+    for (int t = 0; t < U; t++) cur[t] = nxt[t];
+    j += U;
+  }
+  for (; j < n; j++) { const double p = a[j] * b[j]; v = SUB ? v - p : v + p; }
+  return v;
+}
+// the same for a column of the packed triangle: sum over j in [j0, j1) of Q[tri(j) + r] * s[j]
+template <int U>
+__device__ __forceinline__ double chain_col(const double *Q, int r, int j0, int j1, const double *s) {
+  double v = 0, cur[U], nxt[U];
+  int j = j0;
+  i64 o = tri(j0) + r;                    // offset of (j, r); the next row starts j + 1 further
+  if (j1 - j0 >= U) {
+    i64 q = o;
+#pragma unroll
+    for (int t = 0; t < U; t++) { cur[t] = Q[q]; q += j + t + 1; }
+  }
+  while (j + U <= j1) {
+    i64 on = o;
+#pragma unroll
+    for (int t = 0; t < U; t++) on += j + t + 1;
+    if (j + 2 * U <= j1) {
+      i64 q = on;
+#pragma unroll
+      for (int t = 0; t < U; t++) { nxt[t] = Q[q]; q += j + U + t + 1; }
+    }
+#pragma unroll
+    for (int t = 0; t < U; t++) v = v + cur[t] * s[j + t];
+#pragma unroll
+    for (int t = 0; t < U; t++) cur[t] = nxt[t];
+    j += U; o = on;
+  }
+  for (; j < j1; j++) { v = v + Q[o] * s[j]; o += j + 1; }
+  return v;
+}
+
+// On entry Q holds the Gram rows: Q[tri(k) + m] = A[Qj[k]][Qj[m]], m <= k (k_gram_fill) -- the
+// slot of column k of Q is exactly the restricted row of A that step k starts from, so the serial
+// k loop below touches no matrix data at all.  PIPE: Q lives in HBM/L2 (batched loads).
+template <bool PIPE, class Group>
+__device__ __forceinline__ void build_q_coop(const Group &g, int nz, double *Q, double *sqv1, double *sqv2) {
   const int r0 = g.thread_rank(), G = g.size();
   for (int k = 0; k < nz; k++) {
-    const int s = Qj[k];
-    const int ab = aro[s], an = aro[s + 1] - ab;
     double *qk = Q + tri(k);
-    for (int m = r0; m <= k; m += G) sqv1[m] = row_at(acol + ab, aa + ab, an, Qj[m]);
+    for (int m = r0; m <= k; m += G) sqv1[m] = qk[m];
     g.sync();
     for (int r = r0; r < k; r += G) {                 // mv_utt: row r of Q^t, left to right
-      double v = 0;
       const double *u = Q + tri(r);
-      for (int j = 0; j <= r; j++) v = v + u[j] * sqv1[j];
+      double v = 0;
+      if (PIPE) v = chain_dot<8, false>(0.0, u, sqv1, r + 1);
+      else for (int j = 0; j <= r; j++) v = v + u[j] * sqv1[j];
       sqv2[r] = v;
     }
     g.sync();
     for (int r = r0; r < k; r += G) {                 // mv_ut: ascending j, starting from 0
       double y = 0;
-      for (int j = r; j < k; j++) y = y + Q[tri(j) + r] * sqv2[j];
+      if (PIPE) y = chain_col<8>(Q, r, r, k, sqv2);
+      else for (int j = r; j < k; j++) y = y + Q[tri(j) + r] * sqv2[j];
       qk[r] = y;
     }
     g.sync();
     double alpha = sqv1[k];                           // every thread forms the same recurrence
-    for (int m = 0; m < k; m++) alpha = alpha - sqv1[m] * qk[m];
+    if (PIPE) alpha = chain_dot<8, true>(alpha, qk, sqv1, k);
+    else for (int m = 0; m < k; m++) alpha = alpha - sqv1[m] * qk[m];
     alpha = -1.0 / sqrt(alpha);
     g.sync();
     for (int m = r0; m < k; m += G) qk[m] = qk[m] * alpha;
@@ -227,9 +284,11 @@ __global__ void __launch_bounds__(256) k_build_q_tile8(const int *list, int nlis
   const int i = list[idx];
   const int b = wro[i], nz = wro[i + 1] - b;
   double *sqv1 = sm + slot * PER, *sqv2 = sqv1 + NZCAP, *Q = sqv2 + NZCAP;
-  build_q_coop(tile, nz, wcol + b, aro, acol, aa, Q, sqv1, sqv2);
   double *out = Qall + qoff[i];
   const int nq = (int)tri(nz);
+  for (int t = tile.thread_rank(); t < nq; t += 8) Q[t] = out[t];
+  tile.sync();
+  build_q_coop<false>(tile, nz, Q, sqv1, sqv2);
   for (int t = tile.thread_rank(); t < nq; t += 8) out[t] = Q[t];
 }
 
@@ -247,58 +306,90 @@ __global__ void k_build_q_block(const int *list, int nlist, int nzcap, const int
   double *Qg = Qall + qoff[i];
   double *Q = QSMEM ? (sm + 2 * nzcap) : Qg;
   BlockGroup g;
-  build_q_coop(g, nz, wcol + b, aro, acol, aa, Q, sqv1, sqv2);
+  const int nq = (int)tri(nz);
   if (QSMEM) {
-    const int nq = (int)tri(nz);
+    for (int t = threadIdx.x; t < nq; t += blockDim.x) Q[t] = Qg[t];
+    __syncthreads();
+  }
+  build_q_coop<!QSMEM>(g, nz, Q, sqv1, sqv2);
+  if (QSMEM) {
     for (int t = threadIdx.x; t < nq; t += blockDim.x) Qg[t] = Q[t];
   }
 }
 
-// Very large supports (the reference piles every F row without a coupling into column 0, :2229):
-// one column is worked on by a CLUSTER of 8 blocks (2048 threads, 8 SMs' worth of L2 bandwidth);
-// Q and the two work vectors live in HBM/L2 and the k-steps are separated by cluster barriers.
-// The arithmetic per output is the same as in build_q_coop.
+// Gram rows of the columns list[0..nlist): one warp per column, the lanes take the entries
+// (k, m <= k) side by side.  No barriers and no serial dependence: the searches of all columns
+// overlap, which is what hides their latency.
+__global__ void __launch_bounds__(256) k_gram_fill(const int *list, int nlist, const int *wro, const int *wcol,
+                                                   const int *aro, const int *acol, const double *aa,
+                                                   double *Qall, const i64 *qoff) {
+  const int w = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (w >= nlist) return;
+  const int i = list[w];
+  const int b = wro[i], nz = wro[i + 1] - b;
+  const int *Qj = wcol + b;
+  double *Q = Qall + qoff[i];
+  for (int k = 0; k < nz; k++) {
+    const int s = Qj[k];
+    const int ab = aro[s], an = aro[s + 1] - ab;
+    double *qk = Q + tri(k);
+    for (int m = lane; m <= k; m += 32) qk[m] = row_at(acol + ab, aa + ab, an, Qj[m]);
+  }
+}
+
+// Gram rows of columns with a very large support: blockIdx.y = column, the pairs (k, m <= k) are
+// spread over gridDim.x blocks
+__global__ void __launch_bounds__(256) k_gram_fill_big(const int *list, const int *wro, const int *wcol, const int *aro,
+                                                       const int *acol, const double *aa, double *Qall, const i64 *qoff) {
+  const int i = list[blockIdx.y];
+  const int b = wro[i], nz = wro[i + 1] - b;
+  const int *Qj = wcol + b;
+  double *Q = Qall + qoff[i];
+  for (int k = blockIdx.x * 8 + (threadIdx.x >> 5); k < nz; k += gridDim.x * 8) {
+    const int s = Qj[k];
+    const int ab = aro[s], an = aro[s + 1] - ab;
+    double *qk = Q + tri(k);
+    for (int m = threadIdx.x & 31; m <= k; m += 32) qk[m] = row_at(acol + ab, aa + ab, an, Qj[m]);
+  }
+}
+
+// Very large supports (the reference piles every F row without a coupling into column 0, :2229;
+// 1050 rows at 128^3): one column is worked on by a CLUSTER of 8 blocks (2048 threads, 8 SMs'
+// worth of L2 bandwidth -- every step re-reads the whole triangle built so far).  Q lives in
+// HBM/L2; the vectors of a step are exchanged through L2 and copied into every block's shared
+// memory; three cluster barriers per step.  The arithmetic per output is that of build_q_coop.
 __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(256)
-k_build_q_cluster(const int *list, int nlist, int maxnz, const int *wro, const int *wcol, const int *aro,
-                  const int *acol, const double *aa, double *Qall, const i64 *qoff, double *scratch) {
+k_build_q_cluster(const int *list, int nlist, int maxnz, const int *wro, double *Qall, const i64 *qoff, double *scratch) {
+  extern __shared__ double sm[];
   cg::cluster_group cl = cg::this_cluster();
   __shared__ double alpha_sh;
   const int cidx = blockIdx.x / 8;
   if (cidx >= nlist) return;                      // whole cluster leaves together
   const int i = list[cidx];
-  const int b = wro[i], nz = wro[i + 1] - b;
-  const int *Qj = wcol + b;
+  const int nz = wro[i + 1] - wro[i];
   double *Q = Qall + qoff[i];
-  double *sqv1 = scratch + (size_t)cidx * 2 * maxnz, *sqv2 = sqv1 + maxnz;
+  double *g2 = scratch + (size_t)cidx * 2 * maxnz, *gy = g2 + maxnz;
+  double *sqv1 = sm, *sqv2 = sm + maxnz;
   const int tid = (int)cl.block_rank() * 256 + threadIdx.x, T = 8 * 256;
   for (int k = 0; k < nz; k++) {
-    const int s = Qj[k];
-    const int ab = aro[s], an = aro[s + 1] - ab;
     double *qk = Q + tri(k);
-    for (int m = tid; m <= k; m += T) sqv1[m] = row_at(acol + ab, aa + ab, an, Qj[m]);
+    for (int m = threadIdx.x; m <= k; m += 256) sqv1[m] = qk[m];          // Gram row k
+    __syncthreads();
+    for (int r = tid; r < k; r += T) g2[r] = chain_dot<16, false>(0.0, Q + tri(r), sqv1, r + 1);
     cl.sync();
-    for (int r = tid; r < k; r += T) {
-      double v = 0;
-      const double *u = Q + tri(r);
-      for (int j = 0; j <= r; j++) v = v + u[j] * sqv1[j];
-      sqv2[r] = v;
-    }
+    for (int m = threadIdx.x; m < k; m += 256) sqv2[m] = __ldcg(g2 + m);
+    __syncthreads();
+    for (int r = tid; r < k; r += T) gy[r] = chain_col<16>(Q, r, r, k, sqv2);
     cl.sync();
-    for (int r = tid; r < k; r += T) {
-      double y = 0;
-      for (int j = r; j < k; j++) y = y + Q[tri(j) + r] * sqv2[j];
-      qk[r] = y;
-    }
-    cl.sync();
+    for (int m = threadIdx.x; m < k; m += 256) sqv2[m] = __ldcg(gy + m);  // unscaled q_k
+    __syncthreads();
     if (threadIdx.x == 0) {                       // one thread per block forms the recurrence
-      double alpha = sqv1[k];
-      for (int m = 0; m < k; m++) alpha = alpha - sqv1[m] * qk[m];
+      const double alpha = chain_dot<16, true>(sqv1[k], sqv1, sqv2, k);
       alpha_sh = -1.0 / sqrt(alpha);
     }
     __syncthreads();
     const double alpha = alpha_sh;
-    cl.sync();                                     // every block has read q_k before it is scaled
-    for (int m = tid; m < k; m += T) qk[m] = qk[m] * alpha;
+    for (int m = tid; m < k; m += T) qk[m] = sqv2[m] * alpha;
     if (tid == 0) qk[k] = -alpha;
     cl.sync();
   }
@@ -339,6 +430,51 @@ void build_q_store(QStore &qs, const Csr &Wt, const Csr &At) {
   const double *aa = At.a.p;
   static bool attr = false;
   if (!attr) { set_smem((const void *)k_build_q_block<true>, sizeof(double) * (2 * 144 + tri(144))); attr = true; }
+  {
+    static int logit = -1;
+    if (logit < 0) { const char *e = getenv("AMGB_Q_LOG"); logit = (e && *e && *e != '0') ? 1 : 0; }
+    if (logit) fprintf(stderr, "build_q: columns %d  maxnz %d  Q entries %lld | bins(<=8,32,64,144,256,more) %d %d %d %d %d %d\n",
+                       n, qs.maxnz, (long long)qs.total, hc[0], hc[1], hc[2], hc[3], hc[4], hc[5]);
+  }
+  // columns with more than 256 rows: a handful (the column-0 pile of the reference) goes to the
+  // cluster kernel on a second stream, next to the other bins; many of them are better off as one
+  // block each, like the bin below
+  const bool big_cluster = hc[5] > 0 && hc[5] <= 32;
+  static cudaStream_t aux = nullptr;
+  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  Buf<double> scratch;
+  if (hc[5] && qs.maxnz > 12800) throw Error(-12, "interpolation support of " + std::to_string(qs.maxnz) + " rows exceeds the kernel limit (12800)");
+  if (hc[5]) {
+    k_gram_fill_big<<<dim3(64, hc[5]), 256, 0, c.stream>>>(lp + 5 * (i64)n, wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
+    c.launches++; post_launch("gram_fill_big");
+  }
+  if (big_cluster) {
+    if (!aux) {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+      CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+      CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
+    scratch.alloc((i64)hc[5] * 2 * qs.maxnz);
+    const size_t sm = sizeof(double) * 2 * (size_t)qs.maxnz;
+    static size_t sm_set = 48 * 1024;
+    if (sm > sm_set) { set_smem((const void *)k_build_q_cluster, sm); sm_set = sm; }
+    CUDA_CHECK(cudaEventRecord(ev_fork, c.stream));
+    CUDA_CHECK(cudaStreamWaitEvent(aux, ev_fork, 0));
+    k_build_q_cluster<<<hc[5] * 8, 256, sm, aux>>>(lp + 5 * (i64)n, hc[5], qs.maxnz, wro, qs.Q.p, qs.qoff.p, scratch.p);
+    c.launches++; post_launch("build_q_cluster");
+    CUDA_CHECK(cudaEventRecord(ev_join, aux));
+  } else if (hc[5]) {
+    const size_t sm = sizeof(double) * 2 * (size_t)qs.maxnz;
+    static size_t sm_set = 48 * 1024;
+    if (sm > sm_set) { set_smem((const void *)k_build_q_block<false>, sm); sm_set = sm; }
+    k_build_q_block<false><<<hc[5], 256, sm, c.stream>>>(lp + 5 * (i64)n, hc[5], qs.maxnz, wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
+    c.launches++; post_launch("build_q_global_big");
+  }
+  for (int b = 0; b < 5; b++) {
+    if (!hc[b]) continue;
+    k_gram_fill<<<(hc[b] + 7) / 8, 256, 0, c.stream>>>(lp + (i64)b * n, hc[b], wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
+    c.launches++; post_launch("gram_fill");
+  }
   if (hc[0]) {
     k_build_q_tile8<8><<<(hc[0] + 31) / 32, 256, 0, c.stream>>>(lp, hc[0], wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
     c.launches++; post_launch("build_q_tile8");
@@ -351,18 +487,13 @@ void build_q_store(QStore &qs, const Csr &Wt, const Csr &At) {
                                                                    acol, aa, qs.Q.p, qs.qoff.p);
     c.launches++; post_launch("build_q_block");
   }
-  if (hc[5]) {
-    if (qs.maxnz > 12800) throw Error(-12, "interpolation support of " + std::to_string(qs.maxnz) + " rows exceeds the kernel limit (12800)");
-    Buf<double> scratch((i64)hc[5] * 2 * qs.maxnz);
-    k_build_q_cluster<<<hc[5] * 8, 256, 0, c.stream>>>(lp + 5 * (i64)n, hc[5], qs.maxnz, wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p, scratch.p);
-    c.launches++; post_launch("build_q_cluster");
-  }
   if (hc[4]) {
     const size_t sm = sizeof(double) * (2 * (size_t)256);
     k_build_q_block<false><<<hc[4], 256, sm, c.stream>>>(lp + 4 * (i64)n, hc[4], 256, wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
     c.launches++; post_launch("build_q_global");
   }
-  if (part) comm_allgatherv(qs.Q.p, off.data());
+  if (big_cluster) CUDA_CHECK(cudaStreamWaitEvent(c.stream, ev_join, 0));   // join before anything reads Q
+  if (part) comm_allgatherv(qs.Q.p, off.data(), "comm.q_blocks");
 }
 
 // ---- apply: W row := Q (Q^t (R(B e_i + u_i lambda))) ----

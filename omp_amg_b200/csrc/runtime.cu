@@ -1,5 +1,6 @@
 // runtime.cu -- context, stream-ordered memory, prefix scans, deterministic reductions.
 #include "common.cuh"
+#include "comm.cuh"
 #include <algorithm>
 #include <chrono>
 #include <map>
@@ -969,7 +970,7 @@ void stage_report() {
   std::vector<std::pair<double, std::string>> v;
   for (auto &kv : g_stage) v.push_back({kv.second.first, kv.first});
   std::sort(v.begin(), v.end());
-  fprintf(stderr, "---- stage profile (inclusive, synchronised) ----\n");
+  fprintf(stderr, "---- stage profile (inclusive, synchronised) rank %d ----\n", comm_rank());
   for (auto it = v.rbegin(); it != v.rend(); ++it)
     fprintf(stderr, "%-28s %10.3f ms  calls %ld\n", it->second.c_str(), it->first * 1e3, g_stage[it->second].second);
   for (auto &kv : g_counts) fprintf(stderr, "count %-24s %ld\n", kv.first.c_str(), kv.second);

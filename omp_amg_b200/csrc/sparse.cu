@@ -445,7 +445,7 @@ Csr spgemm_partitioned(const Csr &A, const Csr &B, Csr (*local)(const Csr &, con
     parallel_for(ln, [=] DEV(i64 i) { cp[r0 + i] = lro[i + 1] - lro[i]; });
     std::vector<i64> off((size_t)P + 1);
     for (int r = 0; r <= P; r++) off[(size_t)r] = (i64)sizeof(int) * row_split(rn, r);
-    comm_allgatherv(cnt.p, off.data());
+    comm_allgatherv(cnt.p, off.data(), "comm.spgemm_counts");
   }
   const i64 nnz = exclusive_scan(cnt.p, xro.p, rn);
   Csr X(rn, B.cn, nnz);
@@ -467,9 +467,9 @@ Csr spgemm_partitioned(const Csr &A, const Csr &B, Csr (*local)(const Csr &, con
   }
   std::vector<i64> off((size_t)P + 1);
   for (int r = 0; r <= P; r++) off[(size_t)r] = (i64)sizeof(int) * seg[(size_t)r];
-  comm_allgatherv(X.col.p, off.data());
+  comm_allgatherv(X.col.p, off.data(), "comm.spgemm_cols");
   for (int r = 0; r <= P; r++) off[(size_t)r] = (i64)sizeof(double) * seg[(size_t)r];
-  comm_allgatherv(X.a.p, off.data());
+  comm_allgatherv(X.a.p, off.data(), "comm.spgemm_vals");
   return X;
 }
 
