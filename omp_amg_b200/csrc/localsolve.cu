@@ -176,47 +176,53 @@ void lmop_accumulate(Csr &S, const QQStore &qq, const double *u, const Csr &Wskt
 // Ordered sums whose left operand streams from HBM/L2: v (+|-)= a[j]*b[j] for j ascending, one add
 // after the other as in the reference, while the loads of a run one batch of U ahead of the adds
 // (the sum is a dependent chain; without the explicit batches every add waits for its own load).
+// The prefetch is unconditional (indices clamped to the last element) so that it stays a straight
+// line of loads ahead of the adds.
 template <int U, bool SUB>
 __device__ __forceinline__ double chain_dot(double v, const double *a, const double *b, int n) {
+  if (n <= 0) return v;
   double cur[U], nxt[U];
+  const int last = n - 1;
+#pragma unroll
+  for (int t = 0; t < U; t++) cur[t] = a[min(t, last)];
   int j = 0;
-  if (n >= U) {
-#pragma unroll
-    for (int t = 0; t < U; t++) cur[t] = a[t];
-  }
   while (j + U <= n) {
-    if (j + 2 * U <= n) {
 #pragma unroll
-      for (int t = 0; t < U; t++) nxt[t] = a[j + U + t];
-    }
+    for (int t = 0; t < U; t++) nxt[t] = a[min(j + U + t, last)];
 #pragma unroll
     for (int t = 0; t < U; t++) { const double p = cur[t] * b[j + t]; v = SUB ? v - p : v + p; }
 #pragma unroll
     for (int t = 0; t < U; t++) cur[t] = nxt[t];
     j += U;
   }
-  for (; j < n; j++) { const double p = a[j] * b[j]; v = SUB ? v - p : v + p; }
+#pragma unroll
+  for (int t = 0; t < U; t++)
+    if (j + t < n) { const double p = cur[t] * b[j + t]; v = SUB ? v - p : v + p; }
   return v;
 }
-// the same for a column of the packed triangle: sum over j in [j0, j1) of Q[tri(j) + r] * s[j]
-template <int U>
-__device__ __forceinline__ double chain_col(const double *Q, int r, int j0, int j1, const double *s) {
-  double v = 0, cur[U], nxt[U];
+// the same for a strided walk: element j sits at offset o_j with o_{j+1} = o_j + inc(j);
+// sum over j in [j0, j1) of Q[o_j] * s[j], o_{j0} = o0.  Offsets past the end are clamped to the
+// last element's (never used in the sum).
+template <int U, class Inc>
+__device__ __forceinline__ double chain_walk(const double *Q, i64 o0, int j0, int j1, const double *s, Inc inc) {
+  double v = 0;
+  if (j1 <= j0) return v;
+  double cur[U], nxt[U];
   int j = j0;
-  i64 o = tri(j0) + r;                    // offset of (j, r); the next row starts j + 1 further
-  if (j1 - j0 >= U) {
+  i64 o = o0;                      // offset of element j
+  {
     i64 q = o;
 #pragma unroll
-    for (int t = 0; t < U; t++) { cur[t] = Q[q]; q += j + t + 1; }
+    for (int t = 0; t < U; t++) { cur[t] = Q[q]; if (j + t + 1 < j1) q += inc(j + t); }
   }
   while (j + U <= j1) {
     i64 on = o;
 #pragma unroll
-    for (int t = 0; t < U; t++) on += j + t + 1;
-    if (j + 2 * U <= j1) {
+    for (int t = 0; t < U; t++) if (j + t + 1 < j1) on += inc(j + t);      // offset of element j + U (clamped)
+    {
       i64 q = on;
 #pragma unroll
-      for (int t = 0; t < U; t++) { nxt[t] = Q[q]; q += j + U + t + 1; }
+      for (int t = 0; t < U; t++) { nxt[t] = Q[q]; if (j + U + t + 1 < j1) q += inc(j + U + t); }
     }
 #pragma unroll
     for (int t = 0; t < U; t++) v = v + cur[t] * s[j + t];
@@ -224,8 +230,15 @@ __device__ __forceinline__ double chain_col(const double *Q, int r, int j0, int 
     for (int t = 0; t < U; t++) cur[t] = nxt[t];
     j += U; o = on;
   }
-  for (; j < j1; j++) { v = v + Q[o] * s[j]; o += j + 1; }
+#pragma unroll
+  for (int t = 0; t < U; t++)
+    if (j + t < j1) v = v + cur[t] * s[j + t];
   return v;
+}
+// a column of the packed triangle: sum over j in [j0, j1) of Q[tri(j) + r] * s[j]
+template <int U>
+__device__ __forceinline__ double chain_col(const double *Q, int r, int j0, int j1, const double *s) {
+  return chain_walk<U>(Q, tri(j0) + r, j0, j1, s, [](int j) { return (i64)(j + 1); });
 }
 
 // On entry Q holds the Gram rows: Q[tri(k) + m] = A[Qj[k]][Qj[m]], m <= k (k_gram_fill) -- the
@@ -368,14 +381,20 @@ k_build_q_cluster(const int *list, int nlist, int maxnz, const int *wro, double 
   const int i = list[cidx];
   const int nz = wro[i + 1] - wro[i];
   double *Q = Qall + qoff[i];
-  double *g2 = scratch + (size_t)cidx * 2 * maxnz, *gy = g2 + maxnz;
+  // per column: the two exchange vectors and a second copy Q2 of the triangle in the other
+  // packing (element (k, m) at m*nz - m(m-1)/2 + k - m), so that the threads r = 0,1,2.. of the
+  // row sums below read neighbouring addresses as well -- rows of the packed Q are tri(r) apart,
+  // which costs one L1 wavefront per thread and load
+  double *g2 = scratch + (size_t)cidx * (2 * (size_t)maxnz + (size_t)tri(maxnz)), *gy = g2 + maxnz, *Q2 = gy + maxnz;
   double *sqv1 = sm, *sqv2 = sm + maxnz;
+  const i64 nzl = nz;
   const int tid = (int)cl.block_rank() * 256 + threadIdx.x, T = 8 * 256;
   for (int k = 0; k < nz; k++) {
     double *qk = Q + tri(k);
     for (int m = threadIdx.x; m <= k; m += 256) sqv1[m] = qk[m];          // Gram row k
     __syncthreads();
-    for (int r = tid; r < k; r += T) g2[r] = chain_dot<16, false>(0.0, Q + tri(r), sqv1, r + 1);
+    for (int r = tid; r < k; r += T)             // sum over j <= r of Q(r, j) * sqv1[j]
+      g2[r] = chain_walk<16>(Q2, (i64)r, 0, r + 1, sqv1, [nzl](int j) { return nzl - j - 1; });
     cl.sync();
     for (int m = threadIdx.x; m < k; m += 256) sqv2[m] = __ldcg(g2 + m);
     __syncthreads();
@@ -389,8 +408,11 @@ k_build_q_cluster(const int *list, int nlist, int maxnz, const int *wro, double 
     }
     __syncthreads();
     const double alpha = alpha_sh;
-    for (int m = tid; m < k; m += T) qk[m] = sqv2[m] * alpha;
-    if (tid == 0) qk[k] = -alpha;
+    for (int m = tid; m <= k; m += T) {
+      const double q = m < k ? sqv2[m] * alpha : -alpha;
+      qk[m] = q;
+      Q2[(i64)m * nzl - (i64)m * (m - 1) / 2 + (k - m)] = q;
+    }
     cl.sync();
   }
 }
@@ -454,7 +476,7 @@ void build_q_store(QStore &qs, const Csr &Wt, const Csr &At) {
       CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
       CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     }
-    scratch.alloc((i64)hc[5] * 2 * qs.maxnz);
+    scratch.alloc((i64)hc[5] * (2 * (i64)qs.maxnz + tri(qs.maxnz)));
     const size_t sm = sizeof(double) * 2 * (size_t)qs.maxnz;
     static size_t sm_set = 48 * 1024;
     if (sm > sm_set) { set_smem((const void *)k_build_q_cluster, sm); sm_set = sm; }
