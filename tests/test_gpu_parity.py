@@ -195,3 +195,19 @@ def test_sequential_reduction_kernel_is_exact(L):
     a = rng.standard_normal(1 << 20); b = a * rng.uniform(0.5, 1.5, 1 << 20)
     assert api.debug_dot(a, b, api.REDUCE_SEQUENTIAL, L=L) == _seq(a * b)
     assert api.debug_dot(a, a, api.REDUCE_SEQUENTIAL, L=L) == _seq(a * a)
+
+
+def test_two_rank_partitioned_setup_identical_to_one_gpu(L):
+    """Row-partitioned setup over NCCL (DESIGN.md row e): on a box with >= 2 GPUs, two ranks build
+    the hierarchy together (SpGEMM rows and local solves partitioned, every product however small)
+    and each rank's result must equal the single-GPU hierarchy bit for bit (tools/dist_check.py)."""
+    import subprocess
+    import sys
+    if amg.device_count(L) < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, AMGB_DIST_MIN_NNZ="0", MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29711", os.path.join(ROOT, "tools", "dist_check.py"), "poisson7:14",
+           "aniso7:10", "sem_hex:8"]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "DIST ALL OK" in r.stdout, r.stdout[-3000:]
