@@ -16,30 +16,35 @@ static double now_s() {
 // coarsen (:2737) with mat_max (:3535)
 // =======================================================================================
 #ifndef AMGB_EMU
-// warp-per-row variants of the three coarsening kernels for levels with long rows (maxima are
-// order-free, so the lanes reduce with shuffles)
+// G-lanes-per-row variants of the three coarsening kernels for levels with longer rows (maxima
+// are order-free, so the lanes reduce with shuffles).  G = 8 for rows of a few dozen entries: the
+// kernels are chains of dependent gathers (row offsets -> column index -> thr/w/g of that row),
+// so what matters is how many rows are in flight, and a warp holds four of them.
+template <int G>
 __global__ void __launch_bounds__(256) k_coarsen_thr(int n, const int *ro, const int *col, const double *sa,
                                                      const double *vf, double mtol, double *thr) {
-  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int i = blockIdx.x * (256 / G) + threadIdx.x / G;
   if (i >= n) return;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x % G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
   double amax = 0;
-  for (int j = ro[i] + lane; j < ro[i + 1]; j += 32)
+  for (int j = ro[i] + lane; j < ro[i + 1]; j += G)
     if (vf[col[j]] != 0 && fabs(sa[j]) > amax) amax = fabs(sa[j]);
-  for (int off = 16; off >= 1; off >>= 1) amax = fmax(amax, __shfl_down_sync(0xffffffffu, amax, off));
+  for (int off = G / 2; off >= 1; off >>= 1) amax = fmax(amax, __shfl_down_sync(gmask, amax, off, G));
   if (lane == 0) thr[i] = amax * mtol;
 }
-template <int STAGE>
+template <int STAGE, int G>
 __global__ void __launch_bounds__(256) k_coarsen_gather(int n, const int *tro, const int *tcol, const double *ta,
                                                         const double *thr, const double *vf, const double *w,
                                                         const double *g, double ctol2, double *mk, double *tp,
                                                         double *vc, double *vfnext) {
-  const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int k = blockIdx.x * (256 / G) + threadIdx.x / G;
   if (k >= n) return;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x % G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
   double m = -DBL_MAX;
   if (vf[k] != 0)
-    for (int p = tro[k] + lane; p < tro[k + 1]; p += 32) {
+    for (int p = tro[k] + lane; p < tro[k + 1]; p += G) {
       const int i = tcol[p];
       if (fabs(ta[p]) < thr[i]) continue;
       double x;
@@ -47,7 +52,7 @@ __global__ void __launch_bounds__(256) k_coarsen_gather(int n, const int *tro, c
       else x = tp[i];
       if (x > m) m = x;
     }
-  for (int off = 16; off >= 1; off >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, off));
+  for (int off = G / 2; off >= 1; off >>= 1) m = fmax(m, __shfl_down_sync(gmask, m, off, G));
   if (lane != 0) return;
   if (STAGE == 1) {
     const double m0 = (w[k] > ctol2) ? 1. : 0.;
@@ -119,12 +124,19 @@ int coarsen(double *vc, const Csr &A, double ctol) {
 #ifndef AMGB_EMU
     if ((double)S.nnz / (double)n > 16.0) {
       Context &cx = ctx();
-      const int nb = (n + 7) / 8;
-      k_coarsen_thr<<<nb, 256, 0, cx.stream>>>(n, ro, col, sa, vfp, mtol, thp);
       // stage 1 must not overwrite tmp while other warps may still read it as x: it does not read tp,
       // so tp is its output; stage 2 reads tp and writes the next vf into w2
-      k_coarsen_gather<1><<<nb, 256, 0, cx.stream>>>(n, tro, tcol, ta, thp, vfp, wp, gp, ctol2, mk, nullptr, nullptr, tp);
-      k_coarsen_gather<2><<<nb, 256, 0, cx.stream>>>(n, tro, tcol, ta, thp, vfp, wp, gp, ctol2, mk, tp, vc, w2p);
+      if ((double)S.nnz / (double)n <= 64.0) {
+        const int nb = (n + 31) / 32;
+        k_coarsen_thr<8><<<nb, 256, 0, cx.stream>>>(n, ro, col, sa, vfp, mtol, thp);
+        k_coarsen_gather<1, 8><<<nb, 256, 0, cx.stream>>>(n, tro, tcol, ta, thp, vfp, wp, gp, ctol2, mk, nullptr, nullptr, tp);
+        k_coarsen_gather<2, 8><<<nb, 256, 0, cx.stream>>>(n, tro, tcol, ta, thp, vfp, wp, gp, ctol2, mk, tp, vc, w2p);
+      } else {
+        const int nb = (n + 7) / 8;
+        k_coarsen_thr<32><<<nb, 256, 0, cx.stream>>>(n, ro, col, sa, vfp, mtol, thp);
+        k_coarsen_gather<1, 32><<<nb, 256, 0, cx.stream>>>(n, tro, tcol, ta, thp, vfp, wp, gp, ctol2, mk, nullptr, nullptr, tp);
+        k_coarsen_gather<2, 32><<<nb, 256, 0, cx.stream>>>(n, tro, tcol, ta, thp, vfp, wp, gp, ctol2, mk, tp, vc, w2p);
+      }
       cx.launches += 3; post_launch("coarsen_warp_kernels");
       { double *t = vfp; vfp = w2p; w2p = t; }
       if (ctx().trace_on) {
@@ -432,6 +444,53 @@ __global__ void __launch_bounds__(256) k_find_support_cols(int nc, const int *tr
   }
 }
 
+// The same with one block of 256 threads per column, for the coarse levels where R has few, long
+// columns (1400 columns of 3000 entries): a warp per column leaves most of the GPU idle and walks
+// ~100 dependent gather rounds.
+__global__ void __launch_bounds__(256) k_find_support_cols_block(int nc, const int *tro, const int *tcol, double *rtv,
+                                                                 const double *rs, const double *w, double thr,
+                                                                 int *alive, double *rv, const int *src, int *skel) {
+  __shared__ double sbest[8];
+  __shared__ int sarg[8], sany[8];
+  const int c = blockIdx.x;
+  if (c >= nc) return;
+  if (!(w[c] > thr)) return;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int b = tro[c], e = tro[c + 1];
+  int any = 0;
+  double best = -DBL_MAX;
+  int arg = 0x7fffffff;
+  for (int p = b + threadIdx.x; p < e; p += 256) {
+    const double v = rtv[p];
+    any |= (v != 0.);
+    if (!alive[p]) continue;
+    const double x = v * rs[tcol[p]];
+    if (x > best) { best = x; arg = p; }          // p ascending per thread: first maximum kept
+  }
+  any = __any_sync(0xffffffffu, any);
+  for (int off = 16; off >= 1; off >>= 1) {
+    const double ob = __shfl_down_sync(0xffffffffu, best, off);
+    const int oa = __shfl_down_sync(0xffffffffu, arg, off);
+    if (oa != 0x7fffffff && (arg == 0x7fffffff || ob > best || (ob == best && oa < arg))) { best = ob; arg = oa; }
+  }
+  if (lane == 0) { sbest[wid] = best; sarg[wid] = arg; sany[wid] = any; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int a_any = 0;
+    for (int q = 0; q < 8; q++) {
+      a_any |= sany[q];
+      const double ob = sbest[q];
+      const int oa = sarg[q];
+      if (q == 0) { best = ob; arg = oa; }
+      else if (oa != 0x7fffffff && (arg == 0x7fffffff || ob > best || (ob == best && oa < arg))) { best = ob; arg = oa; }
+    }
+    if (a_any && arg != 0x7fffffff) {
+      alive[arg] = 0; rtv[arg] = 0.0;
+      rv[src[arg]] = 0.0; skel[src[arg]] = 1;
+    }
+  }
+}
+
 // expand_support (:965-1114) for one bad row per warp: |X| ranked descending (stable: ties keep
 // column order), the shortest prefix whose running sum reaches half of the row sum is taken (the
 // two sums run left to right over the ranking, as sum()/cumsum() do), and the chosen columns are
@@ -529,7 +588,10 @@ Csr find_support(const Csr &R, Csr &Rt, Buf<int> &tpos, double goal) {   // Rt =
 #else
     {
       Context &cx = ctx();
-      k_find_support_cols<<<(nc + 7) / 8, 256, 0, cx.stream>>>(nc, tro, tcol, rtv, rsp, wp, thr, alp, rvp, srcp, skp);
+      if (R.nnz > 512 * (i64)nc)
+        k_find_support_cols_block<<<nc, 256, 0, cx.stream>>>(nc, tro, tcol, rtv, rsp, wp, thr, alp, rvp, srcp, skp);
+      else
+        k_find_support_cols<<<(nc + 7) / 8, 256, 0, cx.stream>>>(nc, tro, tcol, rtv, rsp, wp, thr, alp, rvp, srcp, skp);
       cx.launches++; post_launch("find_support_cols");
     }
 #endif

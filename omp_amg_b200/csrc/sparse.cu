@@ -36,8 +36,52 @@ __global__ void __launch_bounds__(256) k_spmv_tile(int rn, const int *ro, const 
   for (int base = ro[i]; base < end; base += G) {
     const int j = base + lane;
     const double p = (j < end) ? vals[j] * x[col[j]] : 0.0;
-    const int m = min(G, end - base);
-    for (int l = 0; l < m; l++) t = t + __shfl_sync(gmask, p, l, G);
+    const int m = end - base;
+    if (m >= G) {                          // full batch: straight line of G shuffles and adds
+#pragma unroll
+      for (int l = 0; l < G; l++) t = t + __shfl_sync(gmask, p, l, G);
+    } else {
+      for (int l = 0; l < m; l++) t = t + __shfl_sync(gmask, p, l, G);
+    }
+  }
+  if (lane == 0) {
+    double r = plain ? beta * t : alpha * y[i] + beta * t;
+    if (post) r = r * post[i];
+    z[i] = r;
+  }
+}
+// Long rows: one warp per row as above, but the 32 products of a batch travel through shared
+// memory instead of shuffles.  A 64-bit shuffle is two SHFL instructions and the SM issues one per
+// clock, which capped k_spmv_tile<32> at 1.37 TB/s whatever the matrix (per-call log, 128^3);
+// here every lane parks its product (one STS) and reads the batch back as 16 broadcast LDS.128,
+// then adds the 32 values in entry order.
+__global__ void __launch_bounds__(256) k_spmv_row32(int rn, const int *ro, const int *col, const double *vals,
+                                                    const double *x, double *z, double alpha, const double *y,
+                                                    double beta, bool plain, const double *post) {
+  __shared__ __align__(16) double buf[8][2][32];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + w;
+  if (i >= rn) return;
+  const int end = ro[i + 1];
+  double t = 0;
+  int par = 0;
+  for (int base = ro[i]; base < end; base += 32, par ^= 1) {
+    const int j = base + lane;
+    const double p = (j < end) ? vals[j] * x[col[j]] : 0.0;
+    double *b = buf[w][par];
+    b[lane] = p;
+    __syncwarp();
+    const int m = end - base;
+    if (m >= 32) {
+#pragma unroll
+      for (int l = 0; l < 32; l += 2) {
+        const double2 q = *reinterpret_cast<const double2 *>(b + l);
+        t = t + q.x;
+        t = t + q.y;
+      }
+    } else {
+      for (int l = 0; l < m; l++) t = t + b[l];
+    }
   }
   if (lane == 0) {
     double r = plain ? beta * t : alpha * y[i] + beta * t;
@@ -47,8 +91,33 @@ __global__ void __launch_bounds__(256) k_spmv_tile(int rn, const int *ro, const 
 }
 #endif
 
+static void spmv_vals_run(double *z, double alpha, const double *y, double beta, const Csr &M, const double *vals,
+                          const double *x, const double *post);
 void spmv_vals(double *z, double alpha, const double *y, double beta, const Csr &M, const double *vals,
                const double *x, const double *post) {
+#ifndef AMGB_EMU
+  static int logit = -1;
+  if (logit < 0) { const char *e = getenv("AMGB_SPMV_LOG"); logit = (e && *e && *e != '0') ? 1 : 0; }
+  if (logit) {                      // per-call device time (diagnostics; synchronises)
+    Context &c = ctx();
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, c.stream);
+    spmv_vals_run(z, alpha, y, beta, M, vals, x, post);
+    cudaEventRecord(e1, c.stream);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    fprintf(stderr, "spmv %d x %d nnz %lld  %.4f ms  %.1f GB/s\n", M.rn, M.cn, (long long)M.nnz, ms,
+            (12.0 * M.nnz + 16.0 * M.rn) / (ms * 1e-3) / 1e9);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return;
+  }
+#endif
+  spmv_vals_run(z, alpha, y, beta, M, vals, x, post);
+}
+static void spmv_vals_run(double *z, double alpha, const double *y, double beta, const Csr &M, const double *vals,
+                          const double *x, const double *post) {
   StageTimer st_("prim.spmv");
   const int *ro = M.ro.p, *col = M.col.p;
   const bool plain = (alpha == 0. || y == nullptr);
@@ -58,7 +127,7 @@ void spmv_vals(double *z, double alpha, const double *y, double beta, const Csr 
     if ((double)M.nnz / (double)M.rn <= 64.0)
       k_spmv_tile<8><<<(M.rn + 31) / 32, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post);
     else
-      k_spmv_tile<32><<<(M.rn + 7) / 8, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post);
+      k_spmv_row32<<<(M.rn + 7) / 8, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post);
     c.launches++; post_launch("spmv_tile");
     return;
   }
