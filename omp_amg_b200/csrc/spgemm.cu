@@ -80,6 +80,56 @@ __device__ __forceinline__ void accumulate_row(const Group &g, int i, const int 
   }
 }
 
+// Block version with the loads taken off the critical path (blockDim.x <= 256): the entries of the
+// row of A are staged 256 at a time in shared memory together with the bounds of their rows of B,
+// and every thread holds its first TWO entries of the next row of B in registers while the current
+// one is accumulated.  accumulate_row pays the chain acol -> bro -> bcol/ba of dependent loads
+// inside every k step; here only the barrier separates consecutive k.
+struct BlockStage { int b0[256], b1[256]; double av[256]; };
+__device__ __forceinline__ void accumulate_row_block(BlockStage &sg, int i, const int *aro, const int *acol,
+                                                     const double *aa, const int *bro, const int *bcol,
+                                                     const double *ba, int *keys, double *vals, int HS) {
+  const int t = threadIdx.x, T = blockDim.x;
+  const unsigned mask = (unsigned)(HS - 1);
+  for (int h = t; h < HS; h += T) keys[h] = EMPTY;
+  const int a0 = aro[i], a1 = aro[i + 1];
+  for (int jc = a0; jc < a1; jc += T) {
+    __syncthreads();
+    const int my = jc + t;
+    if (my < a1) { const int mk = acol[my]; sg.av[t] = aa[my]; sg.b0[t] = bro[mk]; sg.b1[t] = bro[mk + 1]; }
+    __syncthreads();
+    const int ns = min(T, a1 - jc);
+    int b0 = sg.b0[0], b1 = sg.b1[0];
+    int pc0 = EMPTY, pc1 = EMPTY;
+    double pv0 = 0.0, pv1 = 0.0;
+    if (b0 + t < b1) { pc0 = bcol[b0 + t]; pv0 = ba[b0 + t]; }
+    if (b0 + T + t < b1) { pc1 = bcol[b0 + T + t]; pv1 = ba[b0 + T + t]; }
+    for (int st = 0; st < ns; st++) {
+      const int cb0 = b0, cb1 = b1, cc0 = pc0, cc1 = pc1;
+      const double cv0 = pv0, cv1 = pv1, av = sg.av[st];
+      if (st + 1 < ns) {
+        b0 = sg.b0[st + 1]; b1 = sg.b1[st + 1];
+        if (b0 + t < b1) { pc0 = bcol[b0 + t]; pv0 = ba[b0 + t]; }
+        if (b0 + T + t < b1) { pc1 = bcol[b0 + T + t]; pv1 = ba[b0 + T + t]; }
+      }
+      int it = 0;
+      for (int jb = cb0 + t; jb < cb1; jb += T, it++) {
+        const int c = it == 0 ? cc0 : it == 1 ? cc1 : bcol[jb];
+        const double p = (it == 0 ? cv0 : it == 1 ? cv1 : ba[jb]) * av;
+        unsigned h = hash_col(c) & mask;
+        for (;;) {
+          const int old = atomicCAS(&keys[h], EMPTY, c);
+          if (old == EMPTY) { double v = 0.0; v = v + p; vals[h] = v; break; }
+          if (old == c) { vals[h] = vals[h] + p; break; }
+          h = (h + 1) & mask;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+}
+
 // The same accumulation for a tile of G <= 32 threads with the loads taken off the critical path:
 // G entries of the row of A (a_ik and the bounds of row k of B) are read at once, one per thread,
 // and the first G entries of the NEXT row of B are already in registers while the current one is
@@ -480,7 +530,8 @@ __global__ void __launch_bounds__(256) k_spgemm_bitmap(int phase, int HS_smem, i
   }
   int *wpre = (int *)(bits + maxwords);
   BlockGroup g;
-  accumulate_row(g, i, aro, acol, aa, bro, bcol, ba, skeys, svals, HS);
+  __shared__ BlockStage stage;
+  accumulate_row_block(stage, i, aro, acol, aa, bro, bcol, ba, skeys, svals, HS);
   const int n = drop_zeros_count(g, skeys, svals, HS, &sred);
   if (phase == 1) { if (threadIdx.x == 0) cnt[i] = n; return; }
   long long base = xro ? xro[i] : 0;
@@ -606,7 +657,9 @@ static Csr spgemm_core_local(const Csr &A, const Csr &B) {
   constexpr int BM6_SPAN = 700000, BM7_SPAN = 400000, BM8_SPAN = 800000;   // bitmap = span/4 bytes
   const int bcn = B.cn;
   Buf<int> lists((i64)NB * rn), bcnt(NB), need(rn), cminv(rn), spanv(rn), maxspan(NB);
-  bcnt.zero(); maxspan.zero();
+  Buf<unsigned long long> needsum(1);      // sum of the per-row bounds: an upper bound of nnz(X)
+  bcnt.zero(); maxspan.zero(); needsum.zero();
+  unsigned long long *nsum = needsum.p;
   int *lp = lists.p, *bc = bcnt.p, *nd = need.p, *cmv = cminv.p, *spv = spanv.p, *mxs = maxspan.p;
   parallel_for(rn, [=] DEV(i64 i) {
     i64 ub = 0;
@@ -632,8 +685,10 @@ static Csr spgemm_core_local(const Csr &A, const Csr &B) {
     const int p = atomic_add(&bc[bin], 1);
     lp[(i64)bin * rn + p] = (int)i;
     atomic_max_i32(&mxs[bin], span);
+    if (ub) atomic_add(nsum, (unsigned long long)ub);
   });
   std::vector<int> hc = bcnt.download();
+  const i64 need_total = (i64)needsum.get(0);
   std::vector<int> hms = maxspan.download();
   // rows of bins 8 and 9 get tables in HBM
   Buf<i64> tsz5, toff5, tsz6, toff6;
@@ -679,8 +734,13 @@ static Csr spgemm_core_local(const Csr &A, const Csr &B) {
   Buf<unsigned long long> atop;
   Buf<i64> aroff;
   if (fused_on) {
+    // the arena holds every row of X: sum of the per-row bounds when that is affordable (the
+    // pattern products W_skel*W_skel' expand 15x), else a multiple of the operands -- a too small
+    // arena costs a second pass over all rows
     i64 cap = 6 * (A.nnz + B.nnz) + rn;
     if (cap < (1 << 20)) cap = 1 << 20;
+    const i64 cap_hi = (i64)400 << 20;             // 400 Mi entries = 4.8 GB
+    if (need_total > cap) cap = need_total < cap_hi ? need_total : (cap > cap_hi ? cap : cap_hi);
     acols.alloc(cap); avals.alloc(cap); atop.alloc(1); aflag.alloc(1); aroff.alloc(rn);
     atop.zero(); aflag.zero();
     ar = Arena{acols.p, avals.p, atop.p, cap, aroff.p, aflag.p};
