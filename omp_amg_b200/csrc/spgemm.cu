@@ -85,13 +85,18 @@ __device__ __forceinline__ void accumulate_row(const Group &g, int i, const int 
 // and every thread holds its first TWO entries of the next row of B in registers while the current
 // one is accumulated.  accumulate_row pays the chain acol -> bro -> bcol/ba of dependent loads
 // inside every k step; here only the barrier separates consecutive k.
-struct BlockStage { int b0[256], b1[256]; double av[256]; };
-__device__ __forceinline__ void accumulate_row_block(BlockStage &sg, int i, const int *aro, const int *acol,
+// OPT (optimistic use): the table may be too small for the row.  New keys are counted; once the
+// count passes `limit` no further key is inserted and the row is given up at the next barrier
+// (returns false; the caller hands the row to a kernel with a larger table).
+struct BlockStage { int b0[256], b1[256]; double av[256]; int fill, full; };
+template <bool OPT>
+__device__ __forceinline__ bool accumulate_row_block(BlockStage &sg, int i, const int *aro, const int *acol,
                                                      const double *aa, const int *bro, const int *bcol,
-                                                     const double *ba, int *keys, double *vals, int HS) {
+                                                     const double *ba, int *keys, double *vals, int HS, int limit) {
   const int t = threadIdx.x, T = blockDim.x;
   const unsigned mask = (unsigned)(HS - 1);
   for (int h = t; h < HS; h += T) keys[h] = EMPTY;
+  if (OPT && t == 0) { sg.fill = 0; sg.full = 0; }
   const int a0 = aro[i], a1 = aro[i + 1];
   for (int jc = a0; jc < a1; jc += T) {
     __syncthreads();
@@ -118,16 +123,32 @@ __device__ __forceinline__ void accumulate_row_block(BlockStage &sg, int i, cons
         const double p = (it == 0 ? cv0 : it == 1 ? cv1 : ba[jb]) * av;
         unsigned h = hash_col(c) & mask;
         for (;;) {
-          const int old = atomicCAS(&keys[h], EMPTY, c);
-          if (old == EMPTY) { double v = 0.0; v = v + p; vals[h] = v; break; }
-          if (old == c) { vals[h] = vals[h] + p; break; }
-          h = (h + 1) & mask;
+          if (OPT) {                       // look before claiming a slot: a full table takes no new key
+            const int cur = keys[h];
+            if (cur == EMPTY) {
+              if (atomicAdd(&sg.fill, 1) >= limit) { sg.full = 1; break; }
+              const int old = atomicCAS(&keys[h], EMPTY, c);
+              if (old == EMPTY) { double v = 0.0; v = v + p; vals[h] = v; break; }
+              atomicSub(&sg.fill, 1);      // another thread took the slot (a different column): go on
+              h = (h + 1) & mask;
+              continue;
+            }
+            if (cur == c) { vals[h] = vals[h] + p; break; }
+            h = (h + 1) & mask;
+          } else {
+            const int old = atomicCAS(&keys[h], EMPTY, c);
+            if (old == EMPTY) { double v = 0.0; v = v + p; vals[h] = v; break; }
+            if (old == c) { vals[h] = vals[h] + p; break; }
+            h = (h + 1) & mask;
+          }
         }
       }
       __syncthreads();
+      if (OPT && sg.full) return false;    // uniform: read after the barrier
     }
   }
   __syncthreads();
+  return true;
 }
 
 // The same accumulation for a tile of G <= 32 threads with the loads taken off the critical path:
@@ -506,18 +527,22 @@ __global__ void __launch_bounds__(WPB * 32) k_spgemm_warp_bitmap(int phase, cons
 // Hash table (shared memory, or HBM for rows that do not fit) plus a bitmap over the row's column
 // span in shared memory: the rank of a column is the number of set bits below it, so the row is
 // written in column order without sorting.
+// sel != null: the block works on list position sel[blockIdx.x] (rows given up by the optimistic
+// launch); ovf != null: optimistic launch, rows whose table fills up are appended to ovf.
 __global__ void __launch_bounds__(256) k_spgemm_bitmap(int phase, int HS_smem, int maxwords, const int *cminv,
                                                        const int *spanv, const int *list, int nlist,
                                                        const i64 *toff, int *gkeys, double *gvals,
                                                        const int *aro, const int *acol, const double *aa,
                                                        const int *bro, const int *bcol, const double *ba,
-                                                       int *cnt, const int *xro, int *xcol, double *xa, Arena ar) {
+                                                       int *cnt, const int *xro, int *xcol, double *xa, Arena ar,
+                                                       const int *sel, int *ovf, int *novf) {
   extern __shared__ double dsm[];
   __shared__ int sred;
   __shared__ int stmp[256];
   __shared__ long long sbase;
   if ((int)blockIdx.x >= nlist) return;
-  const int i = list[blockIdx.x];
+  const int q = sel ? sel[blockIdx.x] : (int)blockIdx.x;
+  const int i = list[q];
   int HS;
   double *svals;
   int *skeys;
@@ -525,13 +550,20 @@ __global__ void __launch_bounds__(256) k_spgemm_bitmap(int phase, int HS_smem, i
   if (HS_smem > 0) {
     HS = HS_smem; svals = dsm; skeys = (int *)(dsm + HS); bits = (unsigned *)(skeys + HS);
   } else {
-    const i64 base = toff[blockIdx.x];
+    const i64 base = toff[blockIdx.x];       // tables are laid out in launch order
     HS = (int)(toff[blockIdx.x + 1] - base); svals = gvals + base; skeys = gkeys + base; bits = (unsigned *)dsm;
   }
   int *wpre = (int *)(bits + maxwords);
   BlockGroup g;
   __shared__ BlockStage stage;
-  accumulate_row_block(stage, i, aro, acol, aa, bro, bcol, ba, skeys, svals, HS);
+  if (ovf) {
+    if (!accumulate_row_block<true>(stage, i, aro, acol, aa, bro, bcol, ba, skeys, svals, HS, HS / 4 * 3)) {
+      if (threadIdx.x == 0) ovf[atomicAdd(novf, 1)] = q;
+      return;
+    }
+  } else {
+    accumulate_row_block<false>(stage, i, aro, acol, aa, bro, bcol, ba, skeys, svals, HS, 0);
+  }
   const int n = drop_zeros_count(g, skeys, svals, HS, &sred);
   if (phase == 1) { if (threadIdx.x == 0) cnt[i] = n; return; }
   long long base = xro ? xro[i] : 0;
@@ -694,7 +726,10 @@ static Csr spgemm_core_local(const Csr &A, const Csr &B) {
   Buf<i64> tsz5, toff5, tsz6, toff6;
   Buf<int> gkeys5, gkeys6;
   Buf<double> gvals5, gvals6;
-  for (int bin = 8; bin <= 9; bin++) {
+  Buf<int> ovf8, novf8;
+  int n_ovf8 = 0;
+  bool sel8 = false;       // the HBM launch of bin 8 works on the positions listed in ovf8
+  for (int bin = 9; bin <= 9; bin++) {     // bin 8 gets its tables after the optimistic launch
     if (!hc[bin]) continue;
     Buf<i64> &tsz = bin == 8 ? tsz5 : tsz6, &toff = bin == 8 ? toff5 : toff6;
     tsz.alloc(hc[bin] + 1); toff.alloc(hc[bin] + 1);
@@ -817,18 +852,56 @@ static Csr spgemm_core_local(const Csr &A, const Csr &B) {
     }
     if (hc[6]) {
       const int mw = words(hms[6]);
-      k_spgemm_bitmap<<<hc[6], 128, 2048 * 12 + (size_t)mw * 8, c.stream>>>(phase, 2048, mw, cmv, spv, L(6), hc[6], nullptr, nullptr, nullptr, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, ar);
+      k_spgemm_bitmap<<<hc[6], 128, 2048 * 12 + (size_t)mw * 8, c.stream>>>(phase, 2048, mw, cmv, spv, L(6), hc[6], nullptr, nullptr, nullptr, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, ar, nullptr, nullptr, nullptr);
       c.launches++; post_launch("spgemm_bitmap2k");
     }
     if (hc[7]) {
       const int mw = words(hms[7]);
-      k_spgemm_bitmap<<<hc[7], 256, 8192 * 12 + (size_t)mw * 8, c.stream>>>(phase, 8192, mw, cmv, spv, L(7), hc[7], nullptr, nullptr, nullptr, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, ar);
+      k_spgemm_bitmap<<<hc[7], 256, 8192 * 12 + (size_t)mw * 8, c.stream>>>(phase, 8192, mw, cmv, spv, L(7), hc[7], nullptr, nullptr, nullptr, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, ar, nullptr, nullptr, nullptr);
       c.launches++; post_launch("spgemm_bitmap8k");
     }
     if (hc[8]) {
+      // The bound of these rows (sum of the B row lengths) exceeds every shared-memory table, but
+      // the number of DISTINCT columns usually does not (Af*W on the coarse levels compresses 15
+      // products into one entry): first an optimistic launch with the 8192-slot table in shared
+      // memory; rows that fill it are collected and redone with a table in HBM sized by the bound.
       const int mw = words(hms[8]);
-      k_spgemm_bitmap<<<hc[8], 256, (size_t)mw * 8 + 16, c.stream>>>(phase, 0, mw, cmv, spv, L(8), hc[8], toff5.p, gkeys5.p, gvals5.p, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, ar);
-      c.launches++; post_launch("spgemm_bitmap_hbm");
+      const size_t opt_sm = 8192 * 12 + (size_t)mw * 8;
+      const char *o8 = getenv("AMGB_SPGEMM_OPT8");      // =0: straight to the HBM tables (A/B checks)
+      const bool optimistic = opt_sm <= 200 * 1024 && !(o8 && *o8 == '0');
+      if (first) {
+        n_ovf8 = hc[8];
+        if (optimistic) {
+          ovf8.alloc(hc[8]); novf8.alloc(1); novf8.zero();
+          k_spgemm_bitmap<<<hc[8], 256, opt_sm, c.stream>>>(phase, 8192, mw, cmv, spv, L(8), hc[8], nullptr, nullptr, nullptr, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, ar, nullptr, ovf8.p, novf8.p);
+          c.launches++; post_launch("spgemm_bitmap_optimistic");
+          n_ovf8 = novf8.get(0);
+          sel8 = true;
+        }
+        if (n_ovf8) {                      // HBM tables for the rows that are left, in launch order
+          tsz5.alloc(n_ovf8 + 1); toff5.alloc(n_ovf8 + 1);
+          i64 *ts = tsz5.p;
+          const int *lb = L(8), *sl = optimistic ? ovf8.p : nullptr;
+          parallel_for(n_ovf8, [=] DEV(i64 q) { i64 sz = 256; const int row = lb[sl ? sl[q] : (int)q]; while (sz < 2 * (i64)nd[row]) sz <<= 1; ts[q] = sz; });
+          const i64 total = exclusive_scan64(tsz5.p, toff5.p, n_ovf8);
+          gkeys5.alloc(total); gvals5.alloc(total);
+        }
+      } else if (optimistic && (n_ovf8 < hc[8] || sel8)) {
+        // second pass (the arena was too small, rare): every row through the HBM kernel; which rows
+        // the optimistic launch gives up can differ by a few between two runs (the fill count is
+        // transiently high while threads race for a slot), so its list is not reused
+        n_ovf8 = hc[8]; sel8 = false;
+        tsz5.alloc(n_ovf8 + 1); toff5.alloc(n_ovf8 + 1);
+        i64 *ts = tsz5.p;
+        const int *lb = L(8);
+        parallel_for(n_ovf8, [=] DEV(i64 q) { i64 sz = 256; while (sz < 2 * (i64)nd[lb[q]]) sz <<= 1; ts[q] = sz; });
+        const i64 total = exclusive_scan64(tsz5.p, toff5.p, n_ovf8);
+        gkeys5.alloc(total); gvals5.alloc(total);
+      }
+      if (n_ovf8) {
+        k_spgemm_bitmap<<<n_ovf8, 256, (size_t)mw * 8 + 16, c.stream>>>(phase, 0, mw, cmv, spv, L(8), n_ovf8, toff5.p, gkeys5.p, gvals5.p, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, ar, sel8 ? ovf8.p : nullptr, nullptr, nullptr);
+        c.launches++; post_launch("spgemm_bitmap_hbm");
+      }
     }
     if (hc[9]) {
       k_spgemm_global<<<hc[9], 256, 0, c.stream>>>(phase, L(9), hc[9], toff6.p, gkeys6.p, gvals6.p, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, ar);
