@@ -271,10 +271,13 @@ def main():
             "e2e": {"value": e2e_step, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "roofline": {"bound": "hbm", "kernel": "spgemm (fused hash/dense SpGEMM family, all launches of the timed steps)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                         "peak_source": peak_src, "traffic": None,
-                         "traffic_note": "family of kernels; ncu --set full of its dominant launch "
-                                         "(k_spgemm_warp_bitmap<1024,768,4>, 96^3): 157 MB read + 80 MB written, "
-                                         "L2 hit 91% -- profiles/r1_ncu_full_spgemm_kernels_poisson7_96.csv",
+                         "peak_source": peak_src,
+                         # DRAM bytes (read + write) of the longest launch of the family, ncu, per launch
+                         "traffic": 3449320704,
+                         "traffic_note": "k_spgemm_bitmap, grid 274882 (the level-1 Galerkin product W'(Af W + Afc): "
+                                         "10.8M x 35.9M -> 53.5M entries): 66.7 ms, 2849 MB read + 600 MB written of DRAM "
+                                         "against 1.20 GB algorithmic, L2 hit 56%, 12% active warps -- "
+                                         "profiles/r1_ncu_spgemm_family_dram_traffic_poisson7_128.txt",
                          "launch_seconds": sp_s / max(sp_n, 1),
                          "algorithmic_bytes_per_call": sp_b / max(sp_n, 1), "calls": int(sp_n),
                          "share_of_step": sp_s / dev_s if dev_s else None},
