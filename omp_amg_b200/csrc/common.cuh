@@ -242,6 +242,12 @@ struct StageTimer {
 void stage_report();
 void stage_count(const char *name, long n);   // event counters shown by stage_report
 
+// Test hook (env AMGB_TEST_SMALL_BINS=1, read at every call): the kernels meant for the large
+// levels (long-row SpMV, block-per-column find_support, cluster / HBM Q builders, the optimistic
+// block SpGEMM with its overflow path) take over at tiny sizes, so that the parity tests against
+// the oracle, which only finishes small problems, run through them.  Never set in production.
+bool test_small_bins();
+
 // trace: FNV-1a of a device array; the tests compare the tag/hash sequence with their checker
 void trace_dev(const char *tag, const void *dptr, size_t bytes);
 

@@ -438,11 +438,12 @@ void build_q_store(QStore &qs, const Csr &Wt, const Csr &At) {
   std::vector<i64> off;
   const bool part = q_partition(qs, n, cs, off);
   const int c0 = part ? cs[(size_t)comm_rank()] : 0, c1 = part ? cs[(size_t)comm_rank() + 1] : n;
+  const bool small = test_small_bins();     // test hook: the HBM and cluster builders from 9 rows on
   parallel_for(c1 - c0, [=] DEV(i64 ii) {
     const i64 i = c0 + ii;
     const int nz = wro[i + 1] - wro[i];
     if (nz == 0) return;
-    const int bin = nz <= 8 ? 0 : nz <= 32 ? 1 : nz <= 64 ? 2 : nz <= 144 ? 3 : nz <= 256 ? 4 : 5;
+    const int bin = nz <= 8 ? 0 : small ? (nz <= 12 ? 4 : 5) : nz <= 32 ? 1 : nz <= 64 ? 2 : nz <= 144 ? 3 : nz <= 256 ? 4 : 5;
     const int p = atomic_add(&cp[bin], 1);
     lp[(i64)bin * n + p] = (int)i;
   });

@@ -948,6 +948,8 @@ void max_first2(const double *a, const double *b, i64 n, double *amax, i64 *aidx
 }
 #endif
 
+bool test_small_bins() { const char *e = getenv("AMGB_TEST_SMALL_BINS"); return e && *e == '1'; }
+
 // ---- sub-stage profile ----
 static std::map<std::string, std::pair<double, long>> g_stage;
 static int g_stage_on = -1;

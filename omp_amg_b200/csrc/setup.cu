@@ -588,7 +588,7 @@ Csr find_support(const Csr &R, Csr &Rt, Buf<int> &tpos, double goal) {   // Rt =
 #else
     {
       Context &cx = ctx();
-      if (R.nnz > 512 * (i64)nc)
+      if (R.nnz > 512 * (i64)nc || test_small_bins())
         k_find_support_cols_block<<<nc, 256, 0, cx.stream>>>(nc, tro, tcol, rtv, rsp, wp, thr, alp, rvp, srcp, skp);
       else
         k_find_support_cols<<<(nc + 7) / 8, 256, 0, cx.stream>>>(nc, tro, tcol, rtv, rsp, wp, thr, alp, rvp, srcp, skp);

@@ -124,7 +124,7 @@ static void spmv_vals_run(double *z, double alpha, const double *y, double beta,
 #ifndef AMGB_EMU
   if (M.rn > 0 && (double)M.nnz / (double)M.rn > 8.0) {
     Context &c = ctx();
-    if ((double)M.nnz / (double)M.rn <= 64.0)
+    if ((double)M.nnz / (double)M.rn <= 64.0 && !test_small_bins())
       k_spmv_tile<8><<<(M.rn + 31) / 32, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post);
     else
       k_spmv_row32<<<(M.rn + 7) / 8, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post);

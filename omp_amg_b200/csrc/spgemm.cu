@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(256) k_spgemm_bitmap(int phase, int HS_smem, i
                                                        const int *aro, const int *acol, const double *aa,
                                                        const int *bro, const int *bcol, const double *ba,
                                                        int *cnt, const int *xro, int *xcol, double *xa, Arena ar,
-                                                       const int *sel, int *ovf, int *novf) {
+                                                       const int *sel, int *ovf, int *novf, int optlimit) {
   extern __shared__ double dsm[];
   __shared__ int sred;
   __shared__ int stmp[256];
@@ -557,7 +557,7 @@ __global__ void __launch_bounds__(256) k_spgemm_bitmap(int phase, int HS_smem, i
   BlockGroup g;
   __shared__ BlockStage stage;
   if (ovf) {
-    if (!accumulate_row_block<true>(stage, i, aro, acol, aa, bro, bcol, ba, skeys, svals, HS, HS / 4 * 3)) {
+    if (!accumulate_row_block<true>(stage, i, aro, acol, aa, bro, bcol, ba, skeys, svals, HS, optlimit)) {
       if (threadIdx.x == 0) ovf[atomicAdd(novf, 1)] = q;
       return;
     }
@@ -693,6 +693,7 @@ static Csr spgemm_core_local(const Csr &A, const Csr &B) {
   bcnt.zero(); maxspan.zero(); needsum.zero();
   unsigned long long *nsum = needsum.p;
   int *lp = lists.p, *bc = bcnt.p, *nd = need.p, *cmv = cminv.p, *spv = spanv.p, *mxs = maxspan.p;
+  const bool small = test_small_bins();
   parallel_for(rn, [=] DEV(i64 i) {
     i64 ub = 0;
     int lo = 0x7fffffff, hi = -1;
@@ -706,7 +707,8 @@ static Csr spgemm_core_local(const Csr &A, const Csr &B) {
     if (ub > span) ub = span;
     nd[i] = (int)ub; cmv[i] = hi >= lo ? lo : 0; spv[i] = span;
     int bin;
-    if (ub <= 24) bin = 0;
+    if (small && ub > 24 && span <= BM8_SPAN) bin = 8;      // test hook: block kernel + overflow path
+    else if (ub <= 24) bin = 0;
     else if (ub <= 96) bin = 1;
     else if (ub <= 256 && span <= 32512) bin = 2;
     else if (span <= 24576) bin = 3;          // optimistic warp kernel first, dense fallback (bins 4,5 unused)
@@ -852,12 +854,12 @@ static Csr spgemm_core_local(const Csr &A, const Csr &B) {
     }
     if (hc[6]) {
       const int mw = words(hms[6]);
-      k_spgemm_bitmap<<<hc[6], 128, 2048 * 12 + (size_t)mw * 8, c.stream>>>(phase, 2048, mw, cmv, spv, L(6), hc[6], nullptr, nullptr, nullptr, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, ar, nullptr, nullptr, nullptr);
+      k_spgemm_bitmap<<<hc[6], 128, 2048 * 12 + (size_t)mw * 8, c.stream>>>(phase, 2048, mw, cmv, spv, L(6), hc[6], nullptr, nullptr, nullptr, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, ar, nullptr, nullptr, nullptr, 0);
       c.launches++; post_launch("spgemm_bitmap2k");
     }
     if (hc[7]) {
       const int mw = words(hms[7]);
-      k_spgemm_bitmap<<<hc[7], 256, 8192 * 12 + (size_t)mw * 8, c.stream>>>(phase, 8192, mw, cmv, spv, L(7), hc[7], nullptr, nullptr, nullptr, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, ar, nullptr, nullptr, nullptr);
+      k_spgemm_bitmap<<<hc[7], 256, 8192 * 12 + (size_t)mw * 8, c.stream>>>(phase, 8192, mw, cmv, spv, L(7), hc[7], nullptr, nullptr, nullptr, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, ar, nullptr, nullptr, nullptr, 0);
       c.launches++; post_launch("spgemm_bitmap8k");
     }
     if (hc[8]) {
@@ -873,7 +875,7 @@ static Csr spgemm_core_local(const Csr &A, const Csr &B) {
         n_ovf8 = hc[8];
         if (optimistic) {
           ovf8.alloc(hc[8]); novf8.alloc(1); novf8.zero();
-          k_spgemm_bitmap<<<hc[8], 256, opt_sm, c.stream>>>(phase, 8192, mw, cmv, spv, L(8), hc[8], nullptr, nullptr, nullptr, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, ar, nullptr, ovf8.p, novf8.p);
+          k_spgemm_bitmap<<<hc[8], 256, opt_sm, c.stream>>>(phase, 8192, mw, cmv, spv, L(8), hc[8], nullptr, nullptr, nullptr, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, ar, nullptr, ovf8.p, novf8.p, small ? 40 : 8192 / 4 * 3);
           c.launches++; post_launch("spgemm_bitmap_optimistic");
           n_ovf8 = novf8.get(0);
           sel8 = true;
@@ -899,7 +901,7 @@ static Csr spgemm_core_local(const Csr &A, const Csr &B) {
         gkeys5.alloc(total); gvals5.alloc(total);
       }
       if (n_ovf8) {
-        k_spgemm_bitmap<<<n_ovf8, 256, (size_t)mw * 8 + 16, c.stream>>>(phase, 0, mw, cmv, spv, L(8), n_ovf8, toff5.p, gkeys5.p, gvals5.p, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, ar, sel8 ? ovf8.p : nullptr, nullptr, nullptr);
+        k_spgemm_bitmap<<<n_ovf8, 256, (size_t)mw * 8 + 16, c.stream>>>(phase, 0, mw, cmv, spv, L(8), n_ovf8, toff5.p, gkeys5.p, gvals5.p, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, ar, sel8 ? ovf8.p : nullptr, nullptr, nullptr, 0);
         c.launches++; post_launch("spgemm_bitmap_hbm");
       }
     }

@@ -55,6 +55,27 @@ def test_hierarchy_bit_identical_to_oracle(L, O, name, n, mode):
     assert H.timing()["launches"] > 0
 
 
+@pytest.mark.parametrize("name,n", [("poisson7", 13), ("poisson7", 20), ("poisson27", 10), ("aniso7", 14), ("sem_hex", 12)])
+def test_large_level_kernels_bit_identical_to_oracle(L, O, name, n, monkeypatch):
+    """The kernels that take over on the large levels of a 128^3 setup -- the long-row SpMV through
+    shared memory, block-per-column find_support, the Q builders that keep Q in HBM (one block, and
+    the 8-CTA cluster kernel on a second stream), the optimistic block SpGEMM and its HBM overflow
+    path -- never run on problems small enough for the oracle.  AMGB_TEST_SMALL_BINS=1 lowers their
+    thresholds; every traced intermediate array and the hierarchy must still equal the oracle's."""
+    monkeypatch.setenv("AMGB_TEST_SMALL_BINS", "1")
+    mat = M.by_name(name, n)
+    h = O.setup_raw(*mat, orc.SEQ, trace=True)
+    want = O.fetch(h); twant = O.trace(); O.free(h)
+    L.amgb_trace_enable(1)
+    try:
+        H = amg.amg_setup(*mat, L=L)
+        tgot = product_trace(L)
+    finally:
+        L.amgb_trace_enable(0)
+    assert first_trace_mismatch(tgot, twant) is None
+    assert orc.compare(fetch(H), want) == []
+
+
 @pytest.mark.parametrize("fixture", ["ref_dump", "ref_sem_hex4", "ref_sem_hex6", "ref_sem_hex_3x4x5"])
 def test_identical_to_reference_fixtures(L, fixture):
     """Against struct amg_setup_data produced by the unmodified reference (tests/golden/

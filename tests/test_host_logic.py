@@ -193,3 +193,22 @@ def test_amgdmp_round_trip(tmp_path):
     M.write_amgdmp(str(tmp_path), Ai, Aj, Av)
     Bi, Bj, Bv = M.read_amgdmp(str(tmp_path))
     assert np.array_equal(Ai, Bi) and np.array_equal(Aj, Bj) and np.array_equal(Av, Bv)
+
+
+def test_transports_are_not_interchangeable(emu):
+    """The product build exchanges through NCCL only: it refuses a host transport (-112), so the
+    CPU tests of the partitioning logic can never be mistaken for the product path; the
+    host-emulation build in turn has no NCCL."""
+    import ctypes as C
+    L = amg.lib()
+    cb = api.ALLGATHERV_FN(lambda buf, off, n, user: 0)
+    assert L.amgb_comm_init_host(0, 2, cb, None) == -112
+    assert b"NCCL" in L.amgb_last_error()
+    assert L.amgb_comm_size() == 1 and L.amgb_comm_rank() == 0
+    buf = C.create_string_buffer(128)
+    assert emu.amgb_comm_unique_id(buf) == -112
+    assert emu.amgb_comm_init(0, 2, buf) == -112
+    # a one-rank host communicator is a no-op and must leave the setup untouched
+    assert emu.amgb_comm_init_host(0, 1, api.ALLGATHERV_FN(0), None) == 0
+    assert emu.amgb_comm_size() == 1
+    assert emu.amgb_comm_finalize() == 0
