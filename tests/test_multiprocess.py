@@ -84,7 +84,8 @@ def _dist_worker(rank, world, port, q, case):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case,world,port", [("poisson7_8", 2, 29641), ("aniso_6", 3, 29642), ("amgdmp", 2, 29643)])
+@pytest.mark.parametrize("case,world,port", [("poisson7_8", 2, 29641), ("aniso_6", 3, 29642), ("amgdmp", 2, 29643),
+                                             ("amgdmp", 4, 29644)])     # 49 rows over 4 ranks: blocks of 1-4 rows on the coarse levels
 def test_row_partitioned_setup_matches_single_rank(case, world, port):
     import torch.multiprocessing as mp
     subprocess.run(["make", "-j4", "-C", os.path.join(ROOT, "omp_amg_b200", "csrc"), "emu"], check=True,
@@ -101,3 +102,36 @@ def test_row_partitioned_setup_matches_single_rank(case, world, port):
     for rank, bad, calls, nbytes in out:
         assert not bad, "rank %d differs from the single-rank hierarchy: %s" % (rank, bad)
         assert calls > 0 and nbytes > 0, "rank %d exchanged nothing: the stages were not partitioned" % rank
+
+
+def _threshold_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    os.environ.pop("AMGB_DIST_MIN_NNZ", None)          # default threshold: 2^20 entries
+    from util import EMU_SO, api, amg
+    from omp_amg_b200 import matrices
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        L = api.lib(EMU_SO)
+        api.comm_init_host_gloo(L)
+        H = amg.amg_setup(*matrices.poisson7(6), L=L)
+        q.put((rank, int(H.timing()["comm_calls"])))
+        api.comm_finalize(L)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_small_products_stay_replicated_gloo_world2():
+    """Below the work threshold (AMGB_DIST_MIN_NNZ, default 2^20 entries) a stage is not worth an
+    exchange: every rank computes it whole and nothing is sent."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_threshold_worker, args=(r, 2, 29645, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    out = sorted(q.get(timeout=300) for _ in ps)
+    for p in ps:
+        p.join(60)
+        assert p.exitcode == 0
+    assert out == [(0, 0), (1, 0)]
