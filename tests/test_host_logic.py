@@ -212,3 +212,40 @@ def test_transports_are_not_interchangeable(emu):
     assert emu.amgb_comm_init_host(0, 1, api.ALLGATHERV_FN(0), None) == 0
     assert emu.amgb_comm_size() == 1
     assert emu.amgb_comm_finalize() == 0
+
+
+def test_c_host_program_links_against_the_abi(tmp_path):
+    """the C drop-in for serial_amg.c compiles against include/ and links
+    against the shared library with plain gcc; without a GPU it reports the error and exits 1
+    (there is no CPU fallback), with one it writes the four amg*.dat files."""
+    import shutil
+    import torch
+    src = tmp_path / "serial_amg_b200.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "omp_amg_b200.h"
+int main(void)
+{
+  amgb_hier *h;
+  if (amgb_setup_from_dump(".", &h)) {
+    fprintf(stderr, "amg setup failed: %s\n", amgb_last_error());
+    return 1;
+  }
+  if (amgb_export(h, ".")) return 1;
+  printf("levels %d\n", amgb_nlevels(h));
+  amgb_free(h);
+  return 0;
+}
+''')
+    libdir = os.path.join(ROOT, "omp_amg_b200")
+    exe = tmp_path / "serial_amg_b200"
+    subprocess.run(["gcc", str(src), "-I" + os.path.join(ROOT, "include"), "-L" + libdir, "-lomp_amg_b200",
+                    "-Wl,-rpath," + libdir, "-o", str(exe)], check=True)
+    for f in ("amgdmp_i.dat", "amgdmp_j.dat", "amgdmp_p.dat"):
+        shutil.copy(os.path.join(ROOT, "tests", "golden", f), tmp_path / f)
+    r = subprocess.run([str(exe)], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "levels 4" in r.stdout
+        assert all((tmp_path / f).exists() for f in ("amg.dat", "amg_W.dat", "amg_AfP.dat", "amg_Aff.dat"))
+    else:
+        assert r.returncode == 1 and "amg setup failed" in r.stderr
