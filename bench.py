@@ -168,6 +168,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device; omp_amg_b200 has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own messages (its version banner at
+        # NCCL_DEBUG=WARN) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = amg.lib()
     api._check(L, L.amgb_init(local))
