@@ -114,6 +114,14 @@ int amgb_get_reduce_mode(void);
  * reduction kernels; mode as above.  Mode 1 equals the plain left-to-right loop bit for bit. */
 int amgb_debug_dot(const double *a, const double *b, int64_t n, int mode, double *out);
 
+/* diagnostics: X = A*B with the library's SpGEMM on HOST CSR arrays (columns ascending in every
+ * row).  Semantics of mxm (amg_setup.c:1894): X[i][c] = sum over k ascending of B[k][c]*A[i][k],
+ * separate multiply and add, entries whose sum is exactly 0 are not stored.  xro has arn+1
+ * entries; xcol/xa hold up to cap entries (-30 and *xnnz set if X is larger). */
+int amgb_debug_spgemm(int32_t arn, int32_t acn, const int32_t *aro, const int32_t *acol, const double *aa,
+                      int32_t brn, int32_t bcn, const int32_t *bro, const int32_t *bcol, const double *ba,
+                      int64_t cap, int64_t *xnnz, int32_t *xro, int32_t *xcol, double *xa);
+
 /* ---- stage trace (debug): FNV-1a hashes of intermediate arrays, in stage order ---- */
 void amgb_trace_enable(int on);
 int amgb_trace_count(void);

@@ -60,6 +60,8 @@ def _declare(L):
     L.amgb_release_memory.restype = None
     L.amgb_peak_device_bytes.restype = C.c_int64
     L.amgb_debug_dot.argtypes = [f64p, C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_double)]
+    L.amgb_debug_spgemm.argtypes = [C.c_int32, C.c_int32, i32p, i32p, f64p, C.c_int32, C.c_int32, i32p, i32p, f64p,
+                                    C.c_int64, C.POINTER(C.c_int64), i32p, i32p, f64p]
     L.amgb_trace_enable.argtypes = [C.c_int]
     L.amgb_trace_enable.restype = None
     L.amgb_trace_get.argtypes = [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]
@@ -114,6 +116,23 @@ def debug_dot(a, b=None, mode=REDUCE_SEQUENTIAL, L=None):
         b = np.ascontiguousarray(b, np.float64)
         _check(L, L.amgb_debug_dot(a, b.ctypes.data, len(a), mode, C.byref(out)))
     return out.value
+
+
+def debug_spgemm(A, B, L=None):
+    """The library's SpGEMM on host CSR operands ``(ro, col, a, (rn, cn))`` -> the same tuple for X
+    (diagnostics / tests of the ``mxm`` primitive in isolation)."""
+    L = L or lib()
+    aro, acol, aa, (arn, acn) = A
+    bro, bcol, ba, (brn, bcn) = B
+    c32 = lambda v: np.ascontiguousarray(v, np.int32) if len(v) else np.zeros(1, np.int32)
+    c64 = lambda v: np.ascontiguousarray(v, np.float64) if len(v) else np.zeros(1, np.float64)
+    aro, acol, aa, bro, bcol, ba = c32(aro), c32(acol), c64(aa), c32(bro), c32(bcol), c64(ba)
+    # every product could survive: bound of the output size
+    cap = int(sum(int(bro[k + 1] - bro[k]) for k in acol[:int(aro[arn])])) + 1
+    xro = np.zeros(arn + 1, np.int32); xcol = np.zeros(cap, np.int32); xa = np.zeros(cap, np.float64)
+    nnz = C.c_int64()
+    _check(L, L.amgb_debug_spgemm(arn, acn, aro, acol, aa, brn, bcn, bro, bcol, ba, cap, C.byref(nnz), xro, xcol, xa))
+    return xro, xcol[:nnz.value], xa[:nnz.value], (arn, bcn)
 
 
 def build_info(L=None):

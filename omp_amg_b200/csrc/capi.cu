@@ -338,6 +338,32 @@ int amgb_debug_dot(const double *a, const double *b, int64_t n, int mode, double
   API_END
 }
 
+// diagnostics: X = A*B with the library's SpGEMM (mxm semantics) on HOST CSR arrays
+int amgb_debug_spgemm(int32_t arn, int32_t acn, const int32_t *aro, const int32_t *acol, const double *aa,
+                      int32_t brn, int32_t bcn, const int32_t *bro, const int32_t *bcol, const double *ba,
+                      int64_t cap, int64_t *xnnz, int32_t *xro, int32_t *xcol, double *xa) {
+  API_BEGIN
+  ctx_init(-1);
+  if (arn < 0 || brn < 0 || acn != brn || !aro || !bro || !xnnz || !xro) return fail(-2, "bad arguments");
+  const i64 annz = aro[arn], bnnz = bro[brn];
+  Csr A(arn, acn, annz), B(brn, bcn, bnnz);
+  A.ro.upload(aro, (i64)arn + 1); B.ro.upload(bro, (i64)brn + 1);
+  if (annz) { A.col.upload(acol, annz); A.a.upload(aa, annz); }
+  if (bnnz) { B.col.upload(bcol, bnnz); B.a.upload(ba, bnnz); }
+  spgemm_cache_reset();
+  Csr X = spgemm(A, B);
+  spgemm_cache_reset();
+  *xnnz = X.nnz;
+  d2h(xro, X.ro.p, sizeof(int) * (size_t)(arn + 1));
+  if (X.nnz > cap) return fail(-30, "output arrays too small");
+  if (X.nnz) {
+    d2h(xcol, X.col.p, sizeof(int) * (size_t)X.nnz);
+    d2h(xa, X.a.p, sizeof(double) * (size_t)X.nnz);
+  }
+  return 0;
+  API_END
+}
+
 void amgb_trace_enable(int on) { ctx().trace_on = on != 0; ctx().trace.clear(); }
 int amgb_trace_count(void) { return (int)ctx().trace.size(); }
 int amgb_trace_get(int i, char *tag, int taglen, uint64_t *hash, int64_t *bytes) {

@@ -232,3 +232,18 @@ def test_two_rank_partitioned_setup_identical_to_one_gpu(L):
            "aniso7:10", "sem_hex:8"]
     r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0 and "DIST ALL OK" in r.stdout, r.stdout[-3000:]
+
+
+@pytest.mark.parametrize("small_bins", ["0", "1"])
+def test_spgemm_primitive_every_bin(L, small_bins, monkeypatch):
+    """mxm in isolation through the C ABI on operands whose rows fall into every SpGEMM bin (tile,
+    warp hash, warp bitmap, optimistic warp + dense fallback, block bitmap, optimistic block table +
+    HBM overflow, global hash): bit-identical to the exact-order reference, exact-zero drops
+    included.  With the test hook on, every row with more than 24 products goes through the
+    optimistic block kernel with a 40-key limit and its overflow path."""
+    from util import spgemm_adversarial_operands, spgemm_reference, same_csr_bits
+    monkeypatch.setenv("AMGB_TEST_SMALL_BINS", small_bins)
+    A, B = spgemm_adversarial_operands(0)
+    want = spgemm_reference(A, B)
+    got = api.debug_spgemm(A, B, L=L)
+    assert got[3] == want[3] and same_csr_bits(got, want)

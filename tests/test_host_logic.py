@@ -249,3 +249,16 @@ int main(void)
         assert all((tmp_path / f).exists() for f in ("amg.dat", "amg_W.dat", "amg_AfP.dat", "amg_Aff.dat"))
     else:
         assert r.returncode == 1 and "amg setup failed" in r.stderr
+
+
+def test_spgemm_primitive_against_exact_order_reference(emu):
+    """amgb_debug_spgemm (the mxm primitive in isolation) on operands that reach every SpGEMM bin:
+    the host-emulation build must reproduce the exact-order reference bit for bit, zero drops
+    included.  (The GPU suite runs the same operands through the CUDA kernels.)"""
+    from util import spgemm_adversarial_operands, spgemm_reference, same_csr_bits
+    A, B = spgemm_adversarial_operands(0)
+    want = spgemm_reference(A, B)
+    got = api.debug_spgemm(A, B, L=emu)
+    assert got[3] == want[3] and same_csr_bits(got, want)
+    dropped = sum(int(B[0][k + 1] - B[0][k]) for k in A[1]) - len(want[1])
+    assert dropped > 0 and len(want[1]) > 100000
