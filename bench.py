@@ -1,17 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- AMG hierarchy setup time on B200 (BASELINE.json's headline metric).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload poisson7 --size 128]
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+                    [--workload poisson7|poisson27|aniso7|sem_hex --size 128] [--metric setup|solve]
 
 One "step" = one full hierarchy setup (amg_setup, amg_setup.c:60) of the workload.
   value   seconds per setup with the COO input already resident in HBM (device CUDA events
           around the whole setup, max over ranks)
   e2e     the same through the host-buffer entry point amgb_setup(): pinned host COO in,
-          H2D inside the timed region, per-level metadata read back (D2H)
+          H2D inside the timed region, per-level metadata and the hierarchy fingerprint read back
   roofline  the SpGEMM kernels (the dominant HBM-bound kernel family): algorithmic bytes /
           device time of those launches, both measured live inside the timed steps
-  cpu_baseline  the CPU port of the reference (oracle/, sequential reductions) on a bounded
-          sample of the same workload, scaled linearly in rows to the full size
+  hierarchy_hash  fingerprint of the hierarchy this run built (amgb_hierarchy_hash): equal on every
+          GPU count, and equal to tests/golden/trace_<workload>_<size>.json.gz where that exists
+  cpu_baseline / same_config_sample  the CPU port of the reference (oracle/, sequential, one core
+          like the reference) and this GPU path timed on the SAME bounded sample; nothing is scaled
+--metric solve: a step is one V-cycle (crs_amg_solve's amg_exec, amg.c:114) on the resident
+  hierarchy; value = V-cycles per second, roofline = the bytes of the matrices one cycle streams.
 N > 1 (one process per GPU, torchrun): the ranks build ONE hierarchy together -- the SpGEMM rows
 and the local solves of the coarse columns are partitioned over the ranks and the blocks exchanged
 through the library's NCCL communicator (DESIGN.md row e); every rank ends with the same,
@@ -99,40 +104,137 @@ def workload_matrix(name, n):
     return matrices.by_name(name, n)
 
 
-def run_reference(args, rank, world):
-    """The reference's own CPU implementation of the path on the host cores.  oracle/_ref (the
-    unmodified reference) cannot run this workload: its mxm is O(rows^2) and its unchecked
-    sp_add leaves its arrays on finite-difference Poisson matrices (DESIGN.md "sp_add"), so the
-    CPU port in oracle/ is timed, on a bounded sample, single-threaded like the reference."""
-    if rank != 0:
-        return
+def grid_rows(workload, n):
+    return (n + 1) ** 3 if workload == "sem_hex" else n ** 3
+
+
+def time_cpu_port(workload, n, steps=1):
+    """Seconds per setup of the CPU port (oracle/, reference order, one core) on workload/n."""
     from oracle import oracle as orc
     orc.build(ref=False)
     O = orc.Oracle()
-    ns = args.sample_n
-    mat = workload_matrix(args.workload, ns)
-    rows_s = int(mat[0].max()) + 1
-    rows_full = args.n ** 3 if args.workload != "sem_hex" else (args.n + 1) ** 3
-    for _ in range(min(args.warmup, 1)):
-        O.setup(*workload_matrix(args.workload, max(8, ns // 3)), orc.SEQ)
+    mat = workload_matrix(workload, n)
     ts = []
-    for _ in range(args.steps):
+    for _ in range(max(1, steps)):
         t0 = time.perf_counter()
         h = O.setup_raw(*mat, orc.SEQ)
         ts.append(time.perf_counter() - t0)
         O.free(h)
-    t = sum(ts) / len(ts)
-    scaled = t * rows_full / rows_s
-    sample = ("%s %d^3 (%d rows) measured %.3f s per setup; scaled linearly in rows to %d rows "
-              "(flatters the CPU: its cost grows faster than linearly)" % (args.workload, ns, rows_s, t, rows_full))
-    line = {"impl": "reference", "metric": "amg_setup_time", "value": scaled, "unit": "s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": False,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s_%d^3_full_hierarchy_setup" % (args.workload, args.n), "rows": rows_full,
-                       "sample_rows": rows_s},
-            "cpu_baseline": {"value": scaled, "unit": "s", "cores": 1, "kind": "port", "sample": sample},
-            "e2e": {"value": scaled, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    return sum(ts) / len(ts), int(mat[0].max()) + 1
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path on the host cores.  oracle/_ref (the
+    unmodified reference) cannot run these workloads: its mxm is O(rows^2) and its unchecked
+    sp_add leaves its arrays on finite-difference Poisson matrices (DESIGN.md "sp_add"), so the
+    CPU port in oracle/ is timed, single-threaded like the reference (its only OpenMP pragmas are
+    commented out).  Nothing is extrapolated: `value` is the measured time of a setup of the config
+    named in `config.workload`.  A 128^3 setup of the port takes about half an hour, so by default
+    each step is the bounded sample --sample-n (the GPU arm times the same sample, key
+    same_config_sample); --ref-size N (or AMGB_REF_SIZE) times another size, e.g. the full one, with
+    the step count capped so that the run stays inside --ref-budget seconds."""
+    if rank != 0:
+        return
+    n = int(os.environ.get("AMGB_REF_SIZE", args.ref_size or args.sample_n))
+    t1, rows = time_cpu_port(args.workload, n, 1)
+    budget = args.ref_budget
+    steps = max(1, min(args.steps, int(budget / max(t1, 1e-3)) - 1))
+    warm = 1
+    if steps > 1:
+        t, _ = time_cpu_port(args.workload, n, steps)
+    else:
+        t, warm = t1, 0
+    sample = "%s %d^3 (%d rows): %.3f s per setup measured over %d step(s), 1 core, nothing scaled" % (
+        args.workload, n, rows, t, steps)
+    line = {"impl": "reference", "metric": "amg_setup_time", "value": t, "unit": "s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": False,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s_%d^3_full_hierarchy_setup" % (args.workload, n), "rows": rows,
+                       "steps_requested": args.steps, "steps_capped_to": steps,
+                       "same_config_as_gpu_arm": n == args.n,
+                       "note": "bounded sample of %s_%d^3; compare with the GPU arm's same_config_sample" % (args.workload, args.n)
+                       if n != args.n else "the benchmark's own config"},
+            "cpu_baseline": {"value": t, "unit": "s", "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": t, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def load_traffic(key):
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(key)
+    except Exception:
+        return None
+
+
+def golden_hash(workload, n):
+    """Hierarchy fingerprint the oracle produced for this workload/size, if a fixture is committed."""
+    import gzip
+    path = os.path.join(ROOT, "tests", "golden", "trace_%s_%d.json.gz" % (workload, n))
+    try:
+        with gzip.open(path, "rb") as f:
+            return json.loads(f.read().decode())["hierarchy_hash"]
+    except Exception:
+        return None
+
+
+def run_solve(args, L, api, torch, dist, rank, world, local, dev, barrier):
+    """--metric solve: V-cycles per second on the resident hierarchy (amg_exec, amg.c:114).  Every
+    rank holds the hierarchy and applies the cycle to its own right-hand sides, so
+    N ranks are N independent solve streams (weak scaling); value = cycles/s over all ranks."""
+    dAi, dAj, dAv, nnz, rows = dev
+    H = api.amg_setup(dAi.data_ptr(), dAj.data_ptr(), dAv.data_ptr(), L=L, device_ptrs=True, nnz=nnz)
+    n0 = H.level_info(0)["n"]
+    b = torch.sin(torch.arange(n0, dtype=torch.float64, device="cuda") * 0.37) + 0.1
+    x = torch.zeros(n0, dtype=torch.float64, device="cuda")
+    # bytes one cycle streams: W' and W, AfP, Af (m-1 times), D and the vectors of every level
+    bytes_cycle = 0
+    for l in range(H.nlevels - 1):
+        info, par = H.level_info(l), H.level_params(l)
+        m = int(par["m"])
+        mats = 2 * info["nnzw"] + info["nnzfp"] + max(m - 1, 0) * info["nnzf"]
+        bytes_cycle += 12 * mats + 8 * (6 * info["n"] + (4 + 3 * max(m - 1, 0)) * info["nf"])
+    reps = 20
+    for _ in range(max(args.warmup, 3)):
+        H.solve_device_repeat(x.data_ptr(), b.data_ptr(), reps)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    l0 = L.amgb_launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        H.solve_device_repeat(x.data_ptr(), b.data_ptr(), reps)
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = L.amgb_launch_count() - l0
+    clocks = sampler.stop()
+    # e2e: host right-hand side in, host solution out, every cycle (crs_amg_solve's traffic)
+    hb = b.cpu().numpy(); hx = None
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        hx = H.solve(hb)
+    e2e = (time.perf_counter() - t0) / args.steps
+    tt = torch.tensor([wall, e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    wall, e2e = float(tt[0]), float(tt[1])
+    cyc = wall / (args.steps * reps)
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        ach = bytes_cycle / cyc / 1e9
+        line = {"metric": "amg_vcycles_per_s", "value": world / cyc, "unit": "cycles/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": cyc * reps * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "%s_%d^3_vcycle" % (args.workload, args.n), "rows": rows, "levels": H.nlevels,
+                           "cycles_per_step": reps, "l2": "hierarchy_exceeds_l2" if bytes_cycle > 126e6 else "fits_l2",
+                           "parallelism": "independent_solve_streams_x%d" % world},
+                "ms_per_cycle": cyc * 1e3, "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": {"value": world / e2e, "unit": "cycles/s", "h2d_bytes_per_step": 8 * n0, "d2h_bytes_per_step": 8 * n0},
+                "roofline": {"bound": "hbm", "kernel": "V-cycle (SpMV with W', W, AfP, Af and the vector updates of every level)",
+                             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
+                             "traffic": None, "algorithmic_bytes_per_cycle": bytes_cycle},
+                "solution_norm": float(np.linalg.norm(hx))}
+        print(json.dumps(line), flush=True)
+    H.free()
 
 
 def main():
@@ -144,6 +246,9 @@ def main():
     ap.add_argument("--workload", default="poisson7")
     ap.add_argument("--size", dest="n", type=int, default=128, help="grid points per side")
     ap.add_argument("--sample-n", type=int, default=40, help="grid size of the CPU baseline's bounded sample")
+    ap.add_argument("--ref-size", type=int, default=0, help="--impl reference: grid size to time (default: --sample-n)")
+    ap.add_argument("--ref-budget", type=float, default=240.0, help="--impl reference: seconds the timed steps may take")
+    ap.add_argument("--metric", default="setup", choices=["setup", "solve"])
     ap.add_argument("--reduce", default="seq", choices=["seq", "tree"],
                     help="seq: reference-order dot products (bit-identical hierarchy); tree: fast mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -212,8 +317,17 @@ def main():
     def step_e2e():
         H = api.amg_setup(hAi.numpy(), hAj.numpy(), hAv.numpy(), L=L)
         meta = [(H.level_info(l), H.level_params(l)) for l in range(H.nlevels)]
+        hs = H.hash()
         H.free()
-        return meta
+        return meta, hs
+
+    if args.metric == "solve":
+        run_solve(args, L, api, torch, dist, rank, world, local, (dAi, dAj, dAv, nnz, rows), barrier)
+        if world > 1:
+            if partitioned:
+                api.comm_finalize(L)
+            dist.destroy_process_group()
+        return
 
     for _ in range(args.warmup):
         step_device()
@@ -243,9 +357,32 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_step = float(te[0]) / args.steps
-    nlev = len(metas[-1])
+    nlev = len(metas[-1][0])
+    hier_hash = metas[-1][1]
+    # every rank must hold the same hierarchy
+    hh = torch.tensor([hier_hash & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device="cuda")
+    hmin, hmax = hh.clone(), hh.clone()
+    if world > 1:
+        dist.all_reduce(hmin, op=dist.ReduceOp.MIN); dist.all_reduce(hmax, op=dist.ReduceOp.MAX)
+    ranks_agree = bool(int(hmin[0]) == int(hmax[0]))
     h2d = nnz * 16
-    d2h = nlev * (10 * 8 + 4 * 8)
+    d2h = nlev * (10 * 8 + 4 * 8) + 8
+    peak_dev = int(L.amgb_peak_device_bytes())
+
+    # the same bounded sample the CPU baseline is timed on, through this GPU path (same config, both
+    # measured in this run, nothing scaled)
+    sample = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        smat = workload_matrix(args.workload, args.sample_n)
+        s_t = []
+        for k in range(3):
+            t0 = time.perf_counter()
+            Hs = api.amg_setup(*smat, L=L)
+            Hs.level_info(0)
+            s_t.append(time.perf_counter() - t0)
+            s_hash = Hs.hash()
+            Hs.free()
+        sample = {"gpu_s": min(s_t[1:]), "hash": "%016x" % s_hash, "rows": int(smat[0].max()) + 1}
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -254,52 +391,55 @@ def main():
         sp_n = sum(t["spgemm_calls"] for t in tims)
         achieved = (sp_b / sp_s / 1e9) if sp_s > 0 else 0.0
         last = tims[-1]
+        traffic = load_traffic("%s_%d" % (args.workload, args.n))
+        golden = golden_hash(args.workload, args.n)
         line = {
             "metric": "amg_setup_time", "value": per_step, "unit": "s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": False,
-            "scaling": "strong" if partitioned else "weak",
+            # one hierarchy whatever N: total work is fixed (also at N = 1, so that the driver's
+            # efficiency formula is the strong-scaling one on every line)
+            "scaling": "strong" if (partitioned or world == 1) else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s_%d^3_full_hierarchy_setup" % (args.workload, args.n), "rows": rows, "nnz": nnz,
                        "levels": nlev, "reduce_mode": args.reduce, "l2": "inputs_exceed_l2" if nnz * 16 > 126e6 else "small_input",
                        "parallelism": ("row_partitioned_spgemm_and_local_solves_x%d" % world) if partitioned
                        else ("replicas_x%d" % world if world > 1 else "single_gpu")},
+            "hierarchy_hash": "%016x" % hier_hash,
+            "hierarchy_hash_all_ranks_equal": ranks_agree,
+            "hierarchy_hash_oracle": golden,
+            "hierarchy_matches_oracle": (golden == "%016x" % hier_hash) if golden else None,
             "rows_per_s": (1 if partitioned else world) * rows / per_step,
+            "peak_device_bytes": peak_dev,
             "comm": {"exchanges_per_step": int(last["comm_calls"]), "bytes_received_per_rank_per_step": int(last["comm_bytes"]),
                      "device_s_per_step": last["comm_device_s"], "transport": "nccl grouped broadcast (all-gather of row blocks)"},
             "wall_s_per_step": wall / args.steps,
             "stage_s": {k: last[k] for k in ("build_csr", "coarsen", "smoother", "lanczos", "interp", "galerkin")},
             "gpu_launches": int(sum(t["launches"] for t in tims)),
             "host_syncs": int(sum(t["syncs"] for t in tims)),
+            "host_syncs_per_step": int(last["syncs"]),
             "clocks": clocks,
             "e2e": {"value": e2e_step, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "roofline": {"bound": "hbm", "kernel": "spgemm (fused hash/dense SpGEMM family, all launches of the timed steps)",
+            "roofline": {"bound": "hbm", "kernel": "spgemm (hash SpGEMM family, all launches of the timed steps)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                          "peak_source": peak_src,
-                         # DRAM bytes (read + write) of the longest launch of the family, ncu, per launch
-                         "traffic": 3449320704,
-                         "traffic_note": "k_spgemm_bitmap, grid 274882 (the level-1 Galerkin product W'(Af W + Afc): "
-                                         "10.8M x 35.9M -> 53.5M entries): 66.7 ms, 2849 MB read + 600 MB written of DRAM "
-                                         "against 1.20 GB algorithmic, L2 hit 56%, 12% active warps -- "
-                                         "profiles/r1_ncu_spgemm_family_dram_traffic_poisson7_128.txt",
+                         # DRAM bytes (read + write) of the longest launch of the family from an ncu capture of
+                         # THIS workload and size (profiles/roofline_traffic.json), else null
+                         "traffic": traffic.get("traffic") if traffic else None,
+                         "traffic_note": traffic.get("note") if traffic else "no ncu capture of this workload/size committed",
                          "launch_seconds": sp_s / max(sp_n, 1),
                          "algorithmic_bytes_per_call": sp_b / max(sp_n, 1), "calls": int(sp_n),
                          "share_of_step": sp_s / dev_s if dev_s else None},
         }
-        if world == 1 and not args.no_cpu_baseline:
-            from oracle import oracle as orc
-            orc.build(ref=False)
-            O = orc.Oracle()
-            ns = args.sample_n
-            smat = workload_matrix(args.workload, ns)
-            srows = int(smat[0].max()) + 1
-            t0 = time.perf_counter()
-            h = O.setup_raw(*smat, orc.SEQ)
-            ts = time.perf_counter() - t0
-            O.free(h)
+        if sample is not None:
+            ts, srows = time_cpu_port(args.workload, args.sample_n, 1)
             line["cpu_baseline"] = {
-                "value": ts * rows / srows, "unit": "s", "cores": 1, "kind": "port",
-                "sample": "%s %d^3 (%d rows): %.3f s measured, scaled linearly in rows to %d rows (flatters the CPU)"
-                          % (args.workload, ns, srows, ts, rows)}
+                "value": ts, "unit": "s", "cores": 1, "kind": "port",
+                "sample": "%s %d^3 (%d rows): one setup of the CPU port measured, nothing scaled; the GPU time on the "
+                          "same sample is same_config_sample.gpu_s" % (args.workload, args.sample_n, srows)}
+            line["same_config_sample"] = {"workload": "%s_%d^3_full_hierarchy_setup" % (args.workload, args.sample_n),
+                                          "rows": srows, "cpu_port_s": ts, "gpu_s": sample["gpu_s"],
+                                          "cpu_over_gpu": ts / sample["gpu_s"], "hierarchy_hash": sample["hash"],
+                                          "note": "both arms measured in this run on the same input through host buffers"}
         print(json.dumps(line), flush=True)
     if world > 1:
         if partitioned:

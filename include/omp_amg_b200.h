@@ -127,16 +127,47 @@ void amgb_trace_enable(int on);
 int amgb_trace_count(void);
 int amgb_trace_get(int i, char *tag, int taglen, uint64_t *hash, int64_t *bytes);
 
+/* ---- hierarchy fingerprint ----
+ * One number over the whole hierarchy (level count, nullspace, and per level the row offsets,
+ * columns and value bits of A, Af, W, AfP, the bits of C and D, idc, idf, m, rho), computed on the
+ * device.  bench.py prints it so that runs on 1, 2, 4 and 8 GPUs can be compared; the tests compare
+ * it with the same function of the oracle's hierarchy (oracle/oracle.py: hierarchy_hash). */
+int amgb_hierarchy_hash(const amgb_hier *h, uint64_t *out);
+
+/* kernels launched / host synchronisations by this library since it was loaded */
+int64_t amgb_launch_count(void);
+int64_t amgb_sync_count(void);
+
+/* ---- V-cycle with workspaces kept across calls, repeated on device vectors (bench --metric solve) */
+int amgb_solve_device_repeat(const amgb_hier *h, double *dx, const double *db, int repeat);
+
 /* ---- gslib coarse-solver slot: crs.h:12-22 ----
  * Same names, argument meaning and order as the reference (with the crs_amg_ prefix gslib
- * gives its AMG variant).  uint -> uint32_t, ulong -> uint64_t.  One process: comm must be
- * NULL or describe np == 1.  id[i] == 0 marks a dof that is not solved for; repeated ids are
- * the same dof (entries are summed, as gs_setup/assign_dofs do in amg.c:399). */
-struct comm;                       /* gslib's struct comm (comm.h); only np == 1 is accepted */
+ * gives its AMG variant).  gslib fixes its integer widths at build time (types.h:52-64): "uint"
+ * is unsigned int, unsigned long (-DUSE_LONG) or unsigned long long (-DUSE_LONG_LONG) and
+ * "ulong" likewise with -DGLOBAL_LONG / -DGLOBAL_LONG_LONG; the reference Makefile builds with
+ * -DUSE_LONG -DGLOBAL_LONG.  The library exports one entry point per local width and this header
+ * picks the one matching the includer's gslib flags, so that a caller compiled with the
+ * reference's own CFLAGS binds to the right ABI without a conversion shim:
+ *      crs_amg_setup  ->  crs_amg_setup_u32 | crs_amg_setup_u64
+ * ("ulong" ids are always passed as 64-bit; with neither GLOBAL_LONG flag gslib's ulong is a
+ * 32-bit unsigned int and the caller must widen the id array.)
+ * One process: comm must be NULL or describe np == 1 (struct comm, comm.h:85: { uint id, np;
+ * comm_ext c; } with the same build-time uint).  id[i] == 0 marks a dof that is not solved for;
+ * repeated ids are the same dof (entries are summed, as gs_setup/assign_dofs do in amg.c:399). */
+struct comm;                       /* gslib's struct comm (comm.h:85); only np == 1 is accepted */
 struct crs_data;
-struct crs_data *crs_amg_setup(uint32_t n, const uint64_t *id, uint32_t nz, const uint32_t *Ai,
-                               const uint32_t *Aj, const double *A, uint32_t null_space,
-                               const struct comm *comm);
+struct crs_data *crs_amg_setup_u32(uint32_t n, const uint64_t *id, uint32_t nz, const uint32_t *Ai,
+                                   const uint32_t *Aj, const double *A, uint32_t null_space,
+                                   const struct comm *comm);
+struct crs_data *crs_amg_setup_u64(uint64_t n, const uint64_t *id, uint64_t nz, const uint64_t *Ai,
+                                   const uint64_t *Aj, const double *A, uint64_t null_space,
+                                   const struct comm *comm);
+#if defined(USE_LONG) || defined(USE_LONG_LONG)
+#define crs_amg_setup crs_amg_setup_u64
+#else
+#define crs_amg_setup crs_amg_setup_u32
+#endif
 void crs_amg_solve(double *x, struct crs_data *data, double *b);
 void crs_amg_stats(struct crs_data *data);
 void crs_amg_free(struct crs_data *data);

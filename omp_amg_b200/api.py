@@ -67,8 +67,14 @@ def _declare(L):
     L.amgb_trace_get.argtypes = [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]
     u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
     u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
-    L.crs_amg_setup.argtypes = [C.c_uint32, u64p, C.c_uint32, u32p, u32p, f64p, C.c_uint32, vp]
-    L.crs_amg_setup.restype = vp
+    L.crs_amg_setup_u32.argtypes = [C.c_uint32, u64p, C.c_uint32, u32p, u32p, f64p, C.c_uint32, vp]
+    L.crs_amg_setup_u32.restype = vp
+    L.crs_amg_setup_u64.argtypes = [C.c_uint64, u64p, C.c_uint64, u64p, u64p, f64p, C.c_uint64, vp]
+    L.crs_amg_setup_u64.restype = vp
+    L.amgb_launch_count.restype = C.c_int64
+    L.amgb_sync_count.restype = C.c_int64
+    L.amgb_hierarchy_hash.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.amgb_solve_device_repeat.argtypes = [vp, vp, vp, C.c_int]
     L.crs_amg_solve.argtypes = [f64p, vp, f64p]
     L.crs_amg_solve.restype = None
     L.crs_amg_stats.argtypes = [vp]
@@ -265,6 +271,16 @@ class Hierarchy:
     def solve_device(self, x_ptr, b_ptr):
         _check(self._L, self._L.amgb_solve_device(self._h, x_ptr, b_ptr))
 
+    def solve_device_repeat(self, x_ptr, b_ptr, repeat):
+        """``repeat`` V-cycles on device vectors, one host synchronisation at the end."""
+        _check(self._L, self._L.amgb_solve_device_repeat(self._h, x_ptr, b_ptr, int(repeat)))
+
+    def hash(self):
+        """Fingerprint of the whole hierarchy, computed on the device (amgb_hierarchy_hash)."""
+        out = C.c_uint64()
+        _check(self._L, self._L.amgb_hierarchy_hash(self._h, C.byref(out)))
+        return out.value
+
     def timing(self):
         t = (C.c_double * 16)()
         _check(self._L, self._L.amgb_timing(self._h, t))
@@ -313,14 +329,19 @@ class _Crs:
         self.L, self.ptr, self.n = L, ptr, n
 
 
-def crs_setup(n, id, nz, Ai, Aj, A, null_space, comm=None, L=None):
-    """``crs_setup`` (crs.h:14): same argument order and meaning as the reference."""
+def crs_setup(n, id, nz, Ai, Aj, A, null_space, comm=None, L=None, uint_bits=64):
+    """``crs_setup`` (crs.h:14): same argument order and meaning as the reference.  ``uint_bits``
+    is the width of gslib's build-time ``uint``: 64 for the reference's own build (-DUSE_LONG,
+    types.h:52-64), 32 for a gslib built without it.  ``comm`` is the address of a ``struct comm``
+    (comm.h:85) or None."""
     L = L or lib()
     id = np.ascontiguousarray(id, np.uint64)
-    Ai = np.ascontiguousarray(Ai, np.uint32)
-    Aj = np.ascontiguousarray(Aj, np.uint32)
+    ut = np.uint64 if uint_bits == 64 else np.uint32
+    Ai = np.ascontiguousarray(Ai, ut)
+    Aj = np.ascontiguousarray(Aj, ut)
     A = np.ascontiguousarray(A, np.float64)
-    p = L.crs_amg_setup(n, id, nz, Ai, Aj, A, null_space, comm)
+    fn = L.crs_amg_setup_u64 if uint_bits == 64 else L.crs_amg_setup_u32
+    p = fn(n, id, nz, Ai, Aj, A, null_space, comm)
     if not p:
         raise AmgError("crs_setup failed: %s" % L.amgb_last_error().decode())
     return _Crs(L, p, n)

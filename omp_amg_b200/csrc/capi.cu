@@ -172,6 +172,72 @@ int amgb_get_vec(const amgb_hier *h, int l, int which, double *out) {
   API_END
 }
 
+}  // extern "C"
+
+// ---- hierarchy fingerprint (bench.py prints it; oracle.hierarchy_hash is the same number) ----
+namespace {
+HD inline unsigned long long mix64(unsigned long long z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+// sum_i mix64(w[i] ^ ((i+1) * golden)) mod 2^64 over 8-byte words; 4-byte arrays are zero-extended
+template <class T>
+unsigned long long array_hash(const T *p, i64 n) {
+  if (n <= 0) return 0;
+  Buf<unsigned long long> acc(1);
+  acc.zero();
+  unsigned long long *a = acc.p;
+  const i64 chunks = (n + 255) / 256;
+  parallel_for(chunks, [=] DEV(i64 c) {
+    unsigned long long s = 0;
+    const i64 e = (c + 1) * 256 < n ? (c + 1) * 256 : n;
+    for (i64 i = c * 256; i < e; i++) {
+      unsigned long long w;
+      if (sizeof(T) == 8) w = ((const unsigned long long *)p)[i];
+      else w = (unsigned long long)((const unsigned *)p)[i];
+      s += mix64(w ^ ((unsigned long long)(i + 1) * 0x9E3779B97F4A7C15ULL));
+    }
+    atomic_add(a, s);
+  });
+  return acc.get(0);
+}
+void fnv_word(unsigned long long &h, unsigned long long x) {
+  for (int b = 0; b < 8; b++) { h ^= (x >> (8 * b)) & 0xFF; h *= 0x100000001B3ULL; }
+}
+unsigned long long dbits(double v) { unsigned long long b; memcpy(&b, &v, 8); return b; }
+}  // namespace
+
+extern "C" int amgb_hierarchy_hash(const amgb_hier *h, uint64_t *out) {
+  API_BEGIN
+  if (!h || !out) return fail(-2, "null argument");
+  const Hierarchy &H = h->H;
+  const int nl = (int)H.lv.size();
+  unsigned long long x = 0xCBF29CE484222325ULL;
+  fnv_word(x, (unsigned long long)nl); fnv_word(x, (unsigned long long)H.nullspace);
+  for (int l = 0; l < nl; l++) {
+    const Level &L = H.lv[(size_t)l];
+    const bool last = (l == nl - 1);
+    const Csr *ms[4] = {&L.A, &L.Af, &L.W, &L.AfP};
+    for (int w = 0; w < 4; w++) {
+      if (last && w) continue;
+      const Csr &M = *ms[w];
+      fnv_word(x, (unsigned long long)l); fnv_word(x, (unsigned long long)w);
+      fnv_word(x, (unsigned long long)M.rn); fnv_word(x, (unsigned long long)M.cn); fnv_word(x, (unsigned long long)M.nnz);
+      fnv_word(x, array_hash(M.ro.p, (i64)M.rn + 1)); fnv_word(x, array_hash(M.col.p, M.nnz)); fnv_word(x, array_hash(M.a.p, M.nnz));
+    }
+    if (!last) {
+      fnv_word(x, array_hash(L.C.p, L.n)); fnv_word(x, array_hash(L.D.p, L.nf));
+      fnv_word(x, array_hash(L.idc.p, L.nc)); fnv_word(x, array_hash(L.idf.p, L.nf));
+      fnv_word(x, dbits(L.m)); fnv_word(x, dbits(L.rho));
+    }
+  }
+  *out = x;
+  return 0;
+  API_END
+}
+
+extern "C" {
 // ---- amg_export (amg_setup.c:405), savemats (:483), savevec (:550) ----
 namespace {
 struct HostCsr { int rn = 0, cn = 0; std::vector<int> ro, col; std::vector<double> a; };
@@ -214,6 +280,7 @@ int amgb_export(const amgb_hier *h, const char *dir) {
   const Hierarchy &H = h->H;
   const int nl = (int)H.lv.size(), n = H.lv[0].n;
   if (nl < 2) return fail(-2, "single-level hierarchy has nothing to export");
+  if (H.lv[(size_t)nl - 1].n < 1 || H.lv[(size_t)nl - 2].nc < 1) return fail(-2, "the last level is empty: nothing to export");
   std::vector<int> lvl((size_t)n, 1);
   std::vector<double> dvec((size_t)n, 0.0);
   std::vector<std::vector<int>> idc((size_t)nl - 1), idf((size_t)nl - 1);
@@ -228,7 +295,7 @@ int amgb_export(const amgb_hier *h, const char *dir) {
     W.push_back(fetch(L.W)); P.push_back(fetch(L.AfP)); F.push_back(fetch(L.Af));
   }
   const int k = idc[(size_t)nl - 2][0] - 1;
-  dvec[(size_t)k] = H.nullspace ? 0. : 1. / H.lv[(size_t)nl - 1].A.a.get(0);
+  dvec[(size_t)k] = (H.nullspace || H.lv[(size_t)nl - 1].A.nnz == 0) ? 0. : 1. / H.lv[(size_t)nl - 1].A.a.get(0);
   std::vector<int> Wl((size_t)n), Pl((size_t)n), Fl((size_t)n);
   const std::string d(dir ? dir : ".");
   if (save_mats(Wl, n, nl - 1, lvl, W, idc, d + "/amg_W.dat") ||
@@ -259,6 +326,14 @@ int amgb_solve_device(const amgb_hier *h, double *dx, const double *db) {
   API_BEGIN
   if (!h) return fail(-2, "null hierarchy");
   vcycle_solve(h->H, dx, db);
+  stream_sync();
+  return 0;
+  API_END
+}
+int amgb_solve_device_repeat(const amgb_hier *h, double *dx, const double *db, int repeat) {
+  API_BEGIN
+  if (!h) return fail(-2, "null hierarchy");
+  for (int r = 0; r < repeat; r++) vcycle_solve(h->H, dx, db);
   stream_sync();
   return 0;
   API_END
@@ -316,6 +391,8 @@ int amgb_comm_finalize(void) {
 int amgb_comm_rank(void) { return comm_rank(); }
 int amgb_comm_size(void) { return comm_size(); }
 
+int64_t amgb_launch_count(void) { return (int64_t)ctx().launches; }
+int64_t amgb_sync_count(void) { return (int64_t)ctx().syncs; }
 void amgb_release_memory(void) { dev_release_cache(); }
 int64_t amgb_peak_device_bytes(void) { return (int64_t)dev_peak_bytes(); }
 
@@ -333,7 +410,7 @@ int amgb_debug_dot(const double *a, const double *b, int64_t n, int mode, double
   Buf<double> da(n), db(n);
   da.upload(a, n);
   if (b) db.upload(b, n);
-  *out = mode ? seq_dot(da.p, b ? db.p : nullptr, n) : tree_dot(da.p, b ? db.p : da.p, n);
+  *out = mode ? seq_dot(da.p, b ? db.p : nullptr, n) : (b ? tree_dot(da.p, db.p, n) : tree_sum(da.p, n));
   return 0;
   API_END
 }
@@ -377,36 +454,46 @@ int amgb_trace_get(int i, char *tag, int taglen, uint64_t *hash, int64_t *bytes)
 // ---- gslib coarse-solver slot (crs.h:12-22), one process ----
 struct crs_data {
   amgb_hier *h = nullptr;
-  uint32_t n = 0, un = 0, null_space = 0;
-  std::vector<int32_t> umap;     // local dof -> unique dof, -1 for id 0
-  std::vector<double> ub, ux;
+  uint64_t n = 0, un = 0, null_space = 0;
+  // local dof -> unique dof (-1 for id 0), and its inverse as a CSR list (unique dof -> local
+  // copies, ascending) so that repeated ids are summed in the order crs_solve's gs_add sees them
+  Buf<int> umap, inv_off, inv_idx;
+  Buf<double> db, dx, ub, ux;     // local and unique vectors in HBM, kept across solves
   int64_t solves = 0;
   double solve_seconds = 0;
 };
+}  // extern "C"
 
-struct comm_np1 { void *c; uint32_t id, np; };   // leading fields of gslib's struct comm (comm.h)
+namespace {
+// leading fields of gslib's struct comm (comm.h:85: "uint id, np; comm_ext c;") for a build whose
+// uint is UI
+template <class UI> struct comm_head { UI id, np; };
 
-struct crs_data *crs_amg_setup(uint32_t n, const uint64_t *id, uint32_t nz, const uint32_t *Ai,
-                               const uint32_t *Aj, const double *A, uint32_t null_space,
-                               const struct comm *comm) {
+template <class UI>
+crs_data *crs_setup_impl(UI n, const uint64_t *id, UI nz, const UI *Ai, const UI *Aj, const double *A,
+                         UI null_space, const struct comm *comm) {
   try {
-    if (comm && ((const comm_np1 *)comm)->np != 1) { g_err = "crs_amg_setup: only np == 1 is supported by this build"; return nullptr; }
+    if (comm && ((const comm_head<UI> *)comm)->np != 1) {
+      g_err = "crs_amg_setup: only np == 1 is supported by this build";
+      return nullptr;
+    }
+    if ((uint64_t)n > 0x7fffffffULL || (uint64_t)nz > 0x7fffffffULL) { g_err = "crs_amg_setup: more than 2^31 local dofs or entries"; return nullptr; }
     // assign_dofs (amg_tools.c:30): unique non-zero ids, sorted
     std::vector<uint64_t> uid;
-    for (uint32_t i = 0; i < n; i++) if (id[i]) uid.push_back(id[i]);
+    for (UI i = 0; i < n; i++) if (id[i]) uid.push_back(id[i]);
     std::sort(uid.begin(), uid.end());
     uid.erase(std::unique(uid.begin(), uid.end()), uid.end());
     crs_data *d = new crs_data();
-    d->n = n; d->un = (uint32_t)uid.size(); d->null_space = null_space;
-    d->umap.assign(n, -1);
-    for (uint32_t i = 0; i < n; i++)
-      if (id[i]) d->umap[i] = (int32_t)(std::lower_bound(uid.begin(), uid.end(), id[i]) - uid.begin());
+    d->n = n; d->un = (uint64_t)uid.size(); d->null_space = null_space;
+    std::vector<int32_t> umap((size_t)n, -1);
+    for (UI i = 0; i < n; i++)
+      if (id[i]) umap[(size_t)i] = (int32_t)(std::lower_bound(uid.begin(), uid.end(), id[i]) - uid.begin());
     // assemble: entries of the same (row,col) are summed in input order (mat_condense, amg_tools.c:57)
     struct E { int32_t i, j; double v; };
     std::vector<E> e;
-    e.reserve(nz);
-    for (uint32_t k = 0; k < nz; k++) {
-      const int32_t i = d->umap[Ai[k]], j = d->umap[Aj[k]];
+    e.reserve((size_t)nz);
+    for (UI k = 0; k < nz; k++) {
+      const int32_t i = umap[(size_t)Ai[k]], j = umap[(size_t)Aj[k]];
       if (i < 0 || j < 0 || std::fabs(A[k]) == 0) continue;     // amg.c:1065
       e.push_back(E{i, j, A[k]});
     }
@@ -418,33 +505,63 @@ struct crs_data *crs_amg_setup(uint32_t n, const uint64_t *id, uint32_t nz, cons
       else { ci.push_back(e[k].i); cj.push_back(e[k].j); cv.push_back(e[k].v); }
     }
     if (amgb_setup((int64_t)cv.size(), ci.data(), cj.data(), cv.data(), &d->h) != 0) { delete d; return nullptr; }
-    if ((uint32_t)d->h->H.n0 != d->un) {
+    if ((uint64_t)d->h->H.n0 != d->un) {
       g_err = "crs_amg_setup: some dofs have an empty matrix row";
       amgb_free(d->h); delete d; return nullptr;
     }
-    d->ub.assign(d->un, 0.0); d->ux.assign(d->un, 0.0);
+    // the solve stays on the device: maps and vectors are uploaded / allocated once
+    std::vector<int> off(d->un + 1, 0), idx;
+    for (UI i = 0; i < n; i++) if (umap[(size_t)i] >= 0) off[(size_t)umap[(size_t)i] + 1]++;
+    for (uint64_t u = 0; u < d->un; u++) off[u + 1] += off[u];
+    idx.resize((size_t)off[d->un]);
+    { std::vector<int> fillp(off.begin(), off.end() - 1);
+      for (UI i = 0; i < n; i++) if (umap[(size_t)i] >= 0) idx[(size_t)fillp[(size_t)umap[(size_t)i]]++] = (int)i; }
+    d->umap.alloc((i64)n); d->umap.upload(umap.data(), (i64)n);
+    d->inv_off.alloc((i64)d->un + 1); d->inv_off.upload(off.data(), (i64)d->un + 1);
+    d->inv_idx.alloc((i64)idx.size()); d->inv_idx.upload(idx.data(), (i64)idx.size());
+    d->db.alloc((i64)n); d->dx.alloc((i64)n); d->ub.alloc((i64)d->un); d->ux.alloc((i64)d->un);
+    stream_sync();
     return d;
   } catch (const std::exception &ex) { g_err = ex.what(); return nullptr; }
 }
+}  // namespace
 
+extern "C" {
+
+struct crs_data *crs_amg_setup_u32(uint32_t n, const uint64_t *id, uint32_t nz, const uint32_t *Ai,
+                                   const uint32_t *Aj, const double *A, uint32_t null_space,
+                                   const struct comm *comm) {
+  return crs_setup_impl<uint32_t>(n, id, nz, Ai, Aj, A, null_space, comm);
+}
+struct crs_data *crs_amg_setup_u64(uint64_t n, const uint64_t *id, uint64_t nz, const uint64_t *Ai,
+                                   const uint64_t *Aj, const double *A, uint64_t null_space,
+                                   const struct comm *comm) {
+  return crs_setup_impl<uint64_t>(n, id, nz, Ai, Aj, A, null_space, comm);
+}
+
+// crs_solve (amg.c:171): gather the local right-hand side onto the unique dofs (repeated ids are
+// added in ascending local order), one V-cycle, the optional mean projection, scatter back.
+// Only b (host -> HBM) and x (HBM -> host) cross the bus; everything else is kernels.
 void crs_amg_solve(double *x, struct crs_data *d, double *b) {
   if (!d) return;
-  std::fill(d->ub.begin(), d->ub.end(), 0.0);
-  for (uint32_t i = 0; i < d->n; i++) if (d->umap[i] >= 0) d->ub[(size_t)d->umap[i]] += b[i];
-  if (amgb_solve(d->h, d->ux.data(), d->ub.data()) != 0) {
+  try {
+    const i64 n = (i64)d->n, un = (i64)d->un;
+    d->db.upload(b, n);
+    const double *bp = d->db.p;
+    double *ubp = d->ub.p, *uxp = d->ux.p, *xp = d->dx.p;
+    const int *off = d->inv_off.p, *idx = d->inv_idx.p, *um = d->umap.p;
+    parallel_for(un, [=] DEV(i64 u) { double s = 0.0; for (int q = off[u]; q < off[u + 1]; q++) s += bp[idx[q]]; ubp[u] = s; });
+    vcycle_solve(d->h->H, uxp, ubp);
+    // the hierarchy projects the mean out when it detected a singular operator; crs_solve does
+    // so when the caller asked for it (amg.c:181)
+    if (d->null_space && !d->h->H.nullspace) project_mean(uxp, un);
+    parallel_for(n, [=] DEV(i64 i) { xp[i] = um[i] >= 0 ? uxp[um[i]] : 0.0; });
+    d2h(x, xp, sizeof(double) * (size_t)n);
+    d->solves++;
+  } catch (const std::exception &ex) {
+    g_err = ex.what();
     fprintf(stderr, "crs_amg_solve: %s\n", g_err.c_str());
-    return;
   }
-  // the hierarchy projects the mean out when it detected a singular operator; crs_solve does
-  // so when the caller asked for it (amg.c:181)
-  if (d->null_space && !d->h->H.nullspace) {
-    double s = 0;
-    for (double v : d->ux) s += v;
-    const double avg = s / (double)d->un;
-    for (double &v : d->ux) v -= avg;
-  }
-  for (uint32_t i = 0; i < d->n; i++) x[i] = d->umap[i] >= 0 ? d->ux[(size_t)d->umap[i]] : 0.0;
-  d->solves++;
 }
 
 void crs_amg_stats(struct crs_data *d) {
@@ -453,7 +570,7 @@ void crs_amg_stats(struct crs_data *d) {
   amgb_timing(d->h, t);
   printf("AMG stats:\n  levels=%d rows=%u setup=%0.3e s (coarsen %0.3e, lanczos %0.3e, interp %0.3e, galerkin %0.3e)\n"
          "  kernel launches=%.0f  V-cycles=%lld\n",
-         amgb_nlevels(d->h), d->un, t[0], t[2], t[4], t[5], t[6], t[10], (long long)d->solves);
+         amgb_nlevels(d->h), (unsigned)d->un, t[0], t[2], t[4], t[5], t[6], t[10], (long long)d->solves);
 }
 
 void crs_amg_free(struct crs_data *d) {

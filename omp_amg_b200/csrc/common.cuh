@@ -225,6 +225,12 @@ double seq_dot(const double *a, const double *b, i64 n);
 inline double vdot(const double *a, const double *b, i64 n) { return ctx().reduce_seq ? seq_dot(a, b, n) : tree_dot(a, b, n); }
 inline double vsum(const double *a, i64 n) { return ctx().reduce_seq ? seq_sum(a, n) : tree_sum(a, n); }
 inline double vnorm2(const double *a, i64 n) { return sqrt(vdot(a, a, n)); }
+// the same reductions with the result left in a device scalar (no host synchronisation);
+// b == nullptr gives the plain sum
+void seq_dot_dev(double *out, const double *a, const double *b, i64 n);
+void tree_dot_dev(double *out, const double *a, const double *b, i64 n);
+inline void vdot_dev(double *out, const double *a, const double *b, i64 n) { if (ctx().reduce_seq) seq_dot_dev(out, a, b, n); else tree_dot_dev(out, a, b, n); }
+inline void vsum_dev(double *out, const double *a, i64 n) { vdot_dev(out, a, nullptr, n); }
 // largest value and the first index holding it (extr_op(max), amg_setup.c:3281)
 void max_first(const double *v, i64 n, double *val, i64 *idx);
 // both maxima of one coarsening round in one pass and one read-back
@@ -247,6 +253,13 @@ void stage_count(const char *name, long n);   // event counters shown by stage_r
 // block SpGEMM with its overflow path) take over at tiny sizes, so that the parity tests against
 // the oracle, which only finishes small problems, run through them.  Never set in production.
 bool test_small_bins();
+// Test hook (env AMGB_TEST_FORCE, a string of letters, read at every call): routes that the size
+// heuristics only choose on the large levels are forced on inputs small enough for the oracle.
+//   't'  every SpGEMM goes through the transposed product (spgemm.cu)
+//   'o'  the SpGEMM arena is far too small, so the overflow second pass runs
+//   'b'  vector reductions use the many-block exact reduction whatever the length (runtime.cu)
+//   'p'  the A-orthogonalisation treats every support as a large one (localsolve.cu panel kernels)
+bool test_force(char what);
 
 // trace: FNV-1a of a device array; the tests compare the tag/hash sequence with their checker
 void trace_dev(const char *tag, const void *dptr, size_t bytes);

@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(256) k_tree_dot(const double *a, const double 
   double r = chunk_tree(x);
   if (threadIdx.x == 0) out[blockIdx.x] = r;
 }
-static double tree_finish(Buf<double> &part, i64 nc) {
+static void tree_finish(Buf<double> &part, i64 nc, double *out) {
   while (nc > 1) {
     i64 nc2 = (nc + 1023) / 1024;
     Buf<double> nxt(nc2);
@@ -222,23 +222,29 @@ static double tree_finish(Buf<double> &part, i64 nc) {
     part = std::move(nxt);
     nc = nc2;
   }
-  return part.get(0);
+  d2d(out, part.p, sizeof(double));
+}
+// result in the device scalar *out; b == nullptr: plain sum
+void tree_dot_dev(double *out, const double *a, const double *b, i64 n) {
+  if (n <= 0) { dev_memset(out, 0, sizeof(double)); return; }
+  i64 nc = (n + 1023) / 1024;
+  Buf<double> part(nc);
+  if (b) k_tree_dot<<<(unsigned)nc, 256, 0, g_ctx.stream>>>(a, b, n, part.p);
+  else k_tree_sum<<<(unsigned)nc, 256, 0, g_ctx.stream>>>(a, n, part.p);
+  g_ctx.launches++; post_launch(__func__);
+  tree_finish(part, nc, out);
 }
 double tree_sum(const double *v, i64 n) {
   if (n <= 0) return 0.0;
-  i64 nc = (n + 1023) / 1024;
-  Buf<double> part(nc);
-  k_tree_sum<<<(unsigned)nc, 256, 0, g_ctx.stream>>>(v, n, part.p);
-  g_ctx.launches++; post_launch(__func__);
-  return tree_finish(part, nc);
+  Buf<double> out(1);
+  tree_dot_dev(out.p, v, nullptr, n);
+  return out.get(0);
 }
 double tree_dot(const double *a, const double *b, i64 n) {
   if (n <= 0) return 0.0;
-  i64 nc = (n + 1023) / 1024;
-  Buf<double> part(nc);
-  k_tree_dot<<<(unsigned)nc, 256, 0, g_ctx.stream>>>(a, b, n, part.p);
-  g_ctx.launches++; post_launch(__func__);
-  return tree_finish(part, nc);
+  Buf<double> out(1);
+  tree_dot_dev(out.p, a, b, n);
+  return out.get(0);
 }
 
 // ---- left-to-right sum: thread 0 carries the running sum (one rounding per element, in index
@@ -728,23 +734,27 @@ __global__ void __launch_bounds__(EPS_T) k_eps_combine(const double *a, const do
 }
 static int g_eps = -1;
 
-double seq_dot(const double *a, const double *b, i64 n) {
-  if (n <= 0) return 0.0;
-  StageTimer st_("prim.seq_dot");
-  Buf<double> out(1);
+void seq_dot_dev(double *outp, const double *a, const double *b, i64 n) {
+  if (n <= 0) { dev_memset(outp, 0, sizeof(double)); return; }
   if (g_eps < 0) { const char *e = getenv("AMGB_SEQDOT"); g_eps = (e && !strcmp(e, "chain")) ? 0 : (e && !strcmp(e, "block")) ? 1 : 2; }
-  if (g_eps == 2 && n >= 4 * (i64)EPS_C) {
+  if (g_eps == 2 && (n >= 4 * (i64)EPS_C || (test_force('b') && n > EPS_C))) {
     const int nch = (int)((n + EPS_C - 1) / EPS_C);
     Buf<double> sums(nch);
     Buf<EpsChunk> rec(nch);
     k_eps_chunk_sums<<<nch, 256, 0, g_ctx.stream>>>(a, b, n, sums.p);
     k_eps_guess<<<1, 1, 0, g_ctx.stream>>>(sums.p, nch, rec.p);
     k_eps_chunk_stats<<<nch, EPS_T, 0, g_ctx.stream>>>(a, b, n, rec.p);
-    k_eps_combine<<<1, EPS_T, 0, g_ctx.stream>>>(a, b, n, rec.p, nch, out.p, nullptr);
+    k_eps_combine<<<1, EPS_T, 0, g_ctx.stream>>>(a, b, n, rec.p, nch, outp, nullptr);
     g_ctx.launches += 3;
-  } else if (g_eps) k_eps_dot<<<1, EPS_T, 0, g_ctx.stream>>>(a, b, n, out.p);
-  else k_seq_dot<<<1, 1024, 0, g_ctx.stream>>>(a, b, n, out.p);
+  } else if (g_eps) k_eps_dot<<<1, EPS_T, 0, g_ctx.stream>>>(a, b, n, outp);
+  else k_seq_dot<<<1, 1024, 0, g_ctx.stream>>>(a, b, n, outp);
   g_ctx.launches++; post_launch(__func__);
+}
+double seq_dot(const double *a, const double *b, i64 n) {
+  if (n <= 0) return 0.0;
+  StageTimer st_("prim.seq_dot");
+  Buf<double> out(1);
+  seq_dot_dev(out.p, a, b, n);
   return out.get(0);
 }
 double seq_sum(const double *v, i64 n) { return seq_dot(v, nullptr, n); }
@@ -934,7 +944,9 @@ static double tree_host(const double *v, const double *b, i64 n) {
 double tree_sum(const double *v, i64 n) { return tree_host(v, nullptr, n); }
 double tree_dot(const double *a, const double *b, i64 n) { return tree_host(a, b, n); }
 double seq_sum(const double *v, i64 n) { double r = 0; for (i64 i = 0; i < n; i++) r += v[i]; return r; }
-double seq_dot(const double *a, const double *b, i64 n) { double r = 0; for (i64 i = 0; i < n; i++) r += a[i] * b[i]; return r; }
+double seq_dot(const double *a, const double *b, i64 n) { double r = 0; for (i64 i = 0; i < n; i++) r += b ? a[i] * b[i] : a[i]; return r; }
+void seq_dot_dev(double *out, const double *a, const double *b, i64 n) { *out = seq_dot(a, b, n); }
+void tree_dot_dev(double *out, const double *a, const double *b, i64 n) { *out = tree_host(a, b, n); }
 void max_first(const double *v, i64 n, double *val, i64 *idx) {
   if (n <= 0) throw Error(-3, "max_first on an empty vector");
   double m = v[0]; i64 k = 0;
@@ -949,6 +961,7 @@ void max_first2(const double *a, const double *b, i64 n, double *amax, i64 *aidx
 #endif
 
 bool test_small_bins() { const char *e = getenv("AMGB_TEST_SMALL_BINS"); return e && *e == '1'; }
+bool test_force(char what) { const char *e = getenv("AMGB_TEST_FORCE"); return e && strchr(e, what) != nullptr; }
 
 // ---- sub-stage profile ----
 static std::map<std::string, std::pair<double, long>> g_stage;

@@ -928,7 +928,9 @@ void setup(i64 nnz, const int *dAi, const int *dAj, const double *dAv, Hierarchy
     if (c.trace_on) c.trace_prefix = "L" + std::to_string(level) + ".";
     trace_csr("A", A);
     if (rn <= 1) {
-      H.nullspace = (rn == 1 && A.nnz > 0 && A.a.get(0) < 1e-9) ? 1 : 0;
+      // a 1x1 last level whose only entry cancelled exactly (mpm drops exact zeros of a singular
+      // operator) is a null space as much as a tiny entry is: project the mean, dvec = 0
+      H.nullspace = (rn == 1 && (A.nnz == 0 || A.a.get(0) < 1e-9)) ? 1 : 0;
       L.A = std::move(A);
       break;
     }

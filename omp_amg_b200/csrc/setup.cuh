@@ -17,6 +17,9 @@ struct Level {
   int n = 0, nf = 0, nc = 0;
   double m = 0, rho = 0, lmin = 0, lmax = 0;
   int coarsen_rounds = 0, lanczos_k = 0, interp_rounds = 0;
+  // V-cycle workspaces (bf, bc, xc, xf, t, c1, c2, r), allocated on the first solve and kept:
+  // amg.c keeps b, x, c, c_old, r, buf in struct crs_data for the same reason
+  mutable Buf<double> ws[8];
 };
 
 struct StageTimes {    // host wall-clock with a stream sync at stage ends, seconds
@@ -47,5 +50,7 @@ void setup(i64 nnz, const int *dAi, const int *dAj, const double *dAv, Hierarchy
 
 // V-cycle (amg.c:114 amg_exec + amg.c:171 crs_solve), device vectors of length n0
 void vcycle_solve(const Hierarchy &H, double *x, const double *b);
+// x -= mean(x) with the mean formed on the device (no host round trip)
+void project_mean(double *x, i64 n);
 
 }  // namespace amgb

@@ -15,7 +15,11 @@ void vcycle_level(const Hierarchy &H, int l, double *x, const double *b) {
     return;
   }
   const int n = L.n, nf = L.nf, nc = L.nc;
-  Buf<double> bf(nf), bc(nc), xc(nc), xf(nf), t(nc), c1(nf), c2(nf), r(nf);
+  if (!L.ws[0].p) {
+    const int sz[8] = {nf, nc, nc, nf, nc, nf, nf, nf};
+    for (int k = 0; k < 8; k++) L.ws[k].alloc(sz[k]);
+  }
+  Buf<double> &bf = L.ws[0], &bc = L.ws[1], &xc = L.ws[2], &xf = L.ws[3], &t = L.ws[4], &c1 = L.ws[5], &c2 = L.ws[6], &r = L.ws[7];
   const double *Cf = L.C.p;
   const int *fpos = L.fpos.p, *cpos = L.cpos.p;
   double *bfp = bf.p, *bcp = bc.p, *xcp = xc.p, *xfp = xf.p, *tp = t.p;
@@ -57,11 +61,17 @@ void vcycle_level(const Hierarchy &H, int l, double *x, const double *b) {
 void vcycle_solve(const Hierarchy &H, double *x, const double *b) {
   const int n = H.n0;
   vcycle_level(H, 0, x, b);
-  if (H.nullspace) {
-    const double s = vsum(x, n);
-    const double avg = (1 / (double)n) * s;
-    parallel_for(n, [=] DEV(i64 i) { x[i] = x[i] - avg; });
-  }
+  if (H.nullspace) project_mean(x, n);
+}
+
+// x -= (1/n) * sum(x), the sum in the order the context asks for (amg.c:181-184), its result kept
+// on the device: a solve never waits for the host
+void project_mean(double *x, i64 n) {
+  Buf<double> s(1);
+  vsum_dev(s.p, x, n);
+  const double *sp = s.p;
+  const double inv = 1 / (double)n;
+  parallel_for(n, [=] DEV(i64 i) { const double avg = inv * sp[0]; x[i] = x[i] - avg; });
 }
 
 }  // namespace amgb

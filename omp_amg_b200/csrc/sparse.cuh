@@ -13,13 +13,17 @@ struct Csr {
   i64 nnz = 0;
   Buf<int> ro, col;
   Buf<double> a;
+  // identity of the stored matrix for caches (never a recyclable device pointer): fresh for every
+  // constructed or cloned matrix, carried along by moves
+  unsigned long long uid = 0;
+  static unsigned long long next_uid() { static unsigned long long g = 0; return ++g; }
   Csr() {}
-  Csr(int rn_, int cn_, i64 nnz_) : rn(rn_), cn(cn_), nnz(nnz_), ro(rn_ + 1), col(nnz_), a(nnz_) {}
+  Csr(int rn_, int cn_, i64 nnz_) : rn(rn_), cn(cn_), nnz(nnz_), ro(rn_ + 1), col(nnz_), a(nnz_), uid(next_uid()) {}
   Csr(Csr &&) = default;
   Csr &operator=(Csr &&) = default;
   Csr clone() const {                                   // copy_csr :3463
     Csr B;
-    B.rn = rn; B.cn = cn; B.nnz = nnz;
+    B.rn = rn; B.cn = cn; B.nnz = nnz; B.uid = next_uid();
     B.ro = ro.clone(); B.col = col.clone(); B.a = a.clone();
     return B;
   }

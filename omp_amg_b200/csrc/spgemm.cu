@@ -639,10 +639,8 @@ static Csr spgemm_core(const Csr &A, const Csr &B) {
 // rows of B (Af*W on the coarse levels: 500 against 50) are hundreds of nearly empty steps, while
 // the transposed product takes few steps that each fill the whole thread block.
 static Csr g_At_cache;
-static const void *g_At_key = nullptr;
-static i64 g_At_nnz = -1;
-static int g_At_rn = -1;
-void spgemm_cache_reset() { g_At_cache = Csr(); g_At_key = nullptr; g_At_nnz = -1; g_At_rn = -1; }
+static unsigned long long g_At_key = 0;     // Csr::uid of the cached operand (0 = empty)
+void spgemm_cache_reset() { g_At_cache = Csr(); g_At_key = 0; }
 
 Csr spgemm(const Csr &A, const Csr &B) {
   if (g_spgemm_impl < 0) { const char *e = getenv("AMGB_SPGEMM"); g_spgemm_impl = (e && !strcmp(e, "rowhash")) ? 0 : 1; }
@@ -650,13 +648,14 @@ Csr spgemm(const Csr &A, const Csr &B) {
   if (A.cn != B.rn) throw Error(-4, "spgemm: dimension mismatch");
   static int tr_on = -1;
   if (tr_on < 0) { const char *e = getenv("AMGB_SPGEMM_TRANSPOSED"); tr_on = (e && *e == '0') ? 0 : 1; }
-  if (tr_on && A.rn > 0 && B.rn > 0 && A.nnz > (1 << 20) && B.nnz > 0) {
+  const bool force_t = test_force('t');
+  if ((tr_on || force_t) && A.rn > 0 && B.rn > 0 && (A.nnz > (1 << 20) || (force_t && A.nnz > 0)) && B.nnz > 0) {
     const double la = (double)A.nnz / A.rn, lb = (double)B.nnz / B.rn;
-    if (la > 64.0 && la > 4.0 * lb) {
+    if (force_t || (la > 64.0 && la > 4.0 * lb)) {
       StageTimer st_("prim.spgemm(transposed)");
-      if (g_At_key != (const void *)A.a.p || g_At_nnz != A.nnz || g_At_rn != A.rn) {   // A = Af recurs within a level
+      if (A.uid == 0 || g_At_key != A.uid) {   // A = Af recurs within a level
         g_At_cache = transpose(A);
-        g_At_key = (const void *)A.a.p; g_At_nnz = A.nnz; g_At_rn = A.rn;
+        g_At_key = A.uid;
       }
       Csr Bt = transpose(B);
       Csr Xt = spgemm_core(Bt, g_At_cache);
@@ -778,6 +777,7 @@ static Csr spgemm_core_local(const Csr &A, const Csr &B) {
     if (cap < (1 << 20)) cap = 1 << 20;
     const i64 cap_hi = (i64)400 << 20;             // 400 Mi entries = 4.8 GB
     if (need_total > cap) cap = need_total < cap_hi ? need_total : (cap > cap_hi ? cap : cap_hi);
+    if (test_force('o')) cap = 48;                 // test hook: (nearly) every row overflows the arena
     acols.alloc(cap); avals.alloc(cap); atop.alloc(1); aflag.alloc(1); aroff.alloc(rn);
     atop.zero(); aflag.zero();
     ar = Arena{acols.p, avals.p, atop.p, cap, aroff.p, aflag.p};

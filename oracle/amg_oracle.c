@@ -1178,7 +1178,10 @@ int amgo_setup(int64_t nnz, const int32_t *Ai, const int32_t *Aj, const double *
     h->nlevels = level + 1;
     if (g_trace_on) snprintf(g_trace_prefix, sizeof g_trace_prefix, "L%d.", level);
     trace_csr("A", A);
-    if (rn <= 1) { h->nullspace = (A->a[0] < 1e-9) ? 1 : 0; break; }
+    /* amg_setup.c:166 tests A->a[0] < 1e-9; with an EMPTY 1x1 last level (the only entry
+       cancelled exactly and mpm dropped it) the reference reads an unset value there.  Checker and
+       product both treat that case as a null space. */
+    if (rn <= 1) { h->nullspace = (rn == 1 && (A->ro[1] == 0 || A->a[0] < 1e-9)) ? 1 : 0; break; }
 
     /* coarsen (:174-186) */
     double *vc = NEW(double, rn), *vf = NEW(double, rn);

@@ -409,3 +409,57 @@ def compare(H1, H2, rtol=0.0, what=("A", "Af", "W", "AfP"), params_rtol=None, na
                 if abs(a["rho"] - b["rho"]) > pr * max(abs(b["rho"]), 1e-300):
                     bad.append("L%d rho differs: %r vs %r" % (l, a["rho"], b["rho"]))
     return bad
+
+
+# ------------------------------------------------------------------------------------------
+# hierarchy fingerprint: the same number the product computes on the device
+# (amgb_hierarchy_hash, omp_amg_b200/csrc/capi.cu) -- bench.py prints the product's, the tests
+# compare it with this one computed from the oracle's hierarchy.
+# ------------------------------------------------------------------------------------------
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _array_hash(words):
+    """sum_i splitmix64(w[i] ^ ((i+1) * 0x9E3779B97F4A7C15)) mod 2^64 over 8-byte words."""
+    w = np.ascontiguousarray(words).astype(np.uint64, copy=False)
+    with np.errstate(over="ignore"):
+        i = (np.arange(1, len(w) + 1, dtype=np.uint64)) * np.uint64(0x9E3779B97F4A7C15)
+        z = w ^ i
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+        return int(np.add.reduce(z, dtype=np.uint64)) if len(z) else 0
+
+
+def _fnv_words(h, *words):
+    for x in words:
+        x = int(x) & 0xFFFFFFFFFFFFFFFF
+        for b in range(8):
+            h ^= (x >> (8 * b)) & 0xFF
+            h = (h * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def _bits(v):
+    return np.ascontiguousarray(v, np.float64).view(np.uint64)
+
+
+def hierarchy_hash(H):
+    """Fingerprint of a whole hierarchy: nlevels, nullspace and per level the matrices A (and Af,
+    W, AfP above the last level: row offsets, columns, value bits), C, D (bits), idc, idf, m and
+    rho (bits)."""
+    h = _fnv_words(0xCBF29CE484222325, H.nlevels, H.nullspace)
+    for l, lev in enumerate(H.levels):
+        last = l == H.nlevels - 1
+        for which, name in enumerate(("A", "Af", "W", "AfP")):
+            if last and which:
+                continue
+            ro, col, a, shape = lev[name]
+            h = _fnv_words(h, l, which, shape[0], shape[1], len(col), _array_hash(ro), _array_hash(col),
+                           _array_hash(_bits(a)))
+        if not last:
+            h = _fnv_words(h, _array_hash(_bits(lev["C"])), _array_hash(_bits(lev["D"])),
+                           _array_hash(np.asarray(lev["idc"]).astype(np.uint64)),
+                           _array_hash(np.asarray(lev["idf"]).astype(np.uint64)),
+                           int(_bits([lev["m"]])[0]), int(_bits([lev["rho"]])[0]))
+    return h

@@ -76,6 +76,90 @@ def test_large_level_kernels_bit_identical_to_oracle(L, O, name, n, monkeypatch)
     assert orc.compare(fetch(H), want) == []
 
 
+def _trace_fixtures():
+    import glob
+    return sorted(os.path.basename(f) for f in glob.glob(os.path.join(GOLDEN, "trace_*.json.gz")))
+
+
+@pytest.mark.parametrize("fname", _trace_fixtures())
+def test_trace_fixture_parity(L, fname):
+    """Direct oracle comparison far above the sizes the oracle finishes in seconds: the committed
+    oracle traces (tests/golden/make_trace_fixtures.py; 64^3..128^3 7-point, 32^3/48^3 27-point,
+    Q1 vertex meshes, anisotropic diffusion) hold the FNV-1a hash of every traced intermediate array
+    of the setup -- every coarsening round, skeleton, lambda, R, W, AfP, every level's A -- plus the
+    per-level sizes, m, rho and the hierarchy fingerprint.  The CUDA path must reproduce all of them
+    with the production kernel selection (no test hooks): the large-level kernels, the transposed
+    SpGEMM route and the many-block exact reduction are what runs at these sizes."""
+    from util import load_trace_fixture
+    fx = load_trace_fixture(os.path.join(GOLDEN, fname))
+    mat = M.by_name(fx["workload"], fx["n"])
+    L.amgb_trace_enable(1)
+    try:
+        H = amg.amg_setup(*mat, L=L)
+        tgot = product_trace(L)
+    finally:
+        L.amgb_trace_enable(0)
+    assert first_trace_mismatch(tgot, fx["trace"]) is None
+    assert H.nlevels == fx["nlevels"] and H.nullspace == fx["nullspace"]
+    for l, lev in enumerate(fx["levels"]):
+        info = H.level_info(l)
+        got = [info[k] for k in ("n", "nnz", "nf", "nc", "nnzf", "nnzw", "nnzfp", "coarsen_rounds", "lanczos_iters",
+                                 "interp_rounds")]
+        assert got == lev["info"], (l, got, lev["info"])
+        if l < fx["nlevels"] - 1:
+            par = H.level_params(l)
+            assert par["m"] == lev["m"] and par["rho"] == float.fromhex(lev["rho"])
+    assert "%016x" % H.hash() == fx["hierarchy_hash"]
+    # and without tracing (lazy R0, no eager downloads): the same fingerprint
+    H2 = amg.amg_setup(*mat, L=L)
+    assert "%016x" % H2.hash() == fx["hierarchy_hash"]
+
+
+@pytest.mark.parametrize("force", ["t", "o", "to", "b", "p"])
+@pytest.mark.parametrize("name,n", [("poisson7", 13), ("poisson27", 10), ("aniso7", 14), ("sem_hex", 12)])
+def test_forced_routes_bit_identical_to_oracle(L, O, name, n, force, monkeypatch):
+    """Routes the size heuristics only take on the large levels, forced on oracle-sized inputs
+    (AMGB_TEST_FORCE): 't' every SpGEMM through the transposed product, 'o' an arena that
+    overflows so that the second pass runs (with AMGB_TEST_SMALL_BINS also the branch that rebuilds
+    the overflow list), 'b' the many-block exact reduction inside a setup, 'p' the panel
+    A-orthogonalisation for large supports.  Trace and hierarchy must equal the oracle's."""
+    monkeypatch.setenv("AMGB_TEST_FORCE", force)
+    if "o" in force:
+        monkeypatch.setenv("AMGB_TEST_SMALL_BINS", "1")
+    mat = M.by_name(name, n)
+    h = O.setup_raw(*mat, orc.SEQ, trace=True)
+    want = O.fetch(h); twant = O.trace(); O.free(h)
+    L.amgb_trace_enable(1)
+    try:
+        H = amg.amg_setup(*mat, L=L)
+        tgot = product_trace(L)
+    finally:
+        L.amgb_trace_enable(0)
+    assert first_trace_mismatch(tgot, twant) is None
+    assert orc.compare(fetch(H), want) == []
+    assert H.hash() == orc.hierarchy_hash(want)
+
+
+def test_unmodified_reference_driver_on_gpu(L, tmp_path):
+    """The reference's serial_amg.c + fail.c, compiled unmodified with the reference's flags and
+    linked against libamg_setup_b200.so (amg_setup / amg_export / free_data with the reference's
+    signatures and its build-time uint): run on the bundled dump, its four files must equal the
+    reference's byte for byte.  The binary is built where /root/reference exists (oracle/Makefile
+    `drivers`) and travels in oracle/_ref/."""
+    import shutil
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "serial_amg_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/serial_amg_b200 was not built (needs /root/reference at build time)")
+    for k in "ijp":
+        shutil.copy(os.path.join(GOLDEN, "amgdmp_%s.dat" % k), str(tmp_path))
+    r = subprocess.run([exe], cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:]
+    z = np.load(os.path.join(GOLDEN, "ref_dump.npz"))
+    for f in ("amg.dat", "amg_W.dat", "amg_AfP.dat", "amg_Aff.dat"):
+        assert np.array_equal(np.fromfile(os.path.join(str(tmp_path), f)), z["file_" + f.replace(".", "_")]), f
+
+
 @pytest.mark.parametrize("fixture", ["ref_dump", "ref_sem_hex4", "ref_sem_hex6", "ref_sem_hex_3x4x5"])
 def test_identical_to_reference_fixtures(L, fixture):
     """Against struct amg_setup_data produced by the unmodified reference (tests/golden/
@@ -130,7 +214,7 @@ def test_crs_interface(L):
     Ai, Aj, Av = M.sem_hex(5)
     n = int(Ai.max()) + 1
     ids = np.arange(1, n + 1, dtype=np.uint64)
-    d = amg.crs_setup(n, ids, len(Av), Ai.astype(np.uint32), Aj.astype(np.uint32), Av, 1, None, L=L)
+    d = amg.crs_setup(n, ids, len(Av), Ai, Aj, Av, 1, None, L=L)       # uint = unsigned long, the reference's build
     import scipy.sparse as sp
     A = sp.coo_matrix((Av, (Ai, Aj))).tocsr()
     b = np.random.default_rng(2).standard_normal(n); b -= b.mean()

@@ -157,7 +157,7 @@ def test_crs_interface_mirrors_reference_test(emu):
     ids = np.array([1, 2, 4, 5, 2, 3, 5, 6], np.uint64)
     Ai2 = np.concatenate([Ai, Ai + 4]).astype(np.uint32); Aj2 = np.concatenate([Aj, Aj + 4]).astype(np.uint32)
     A2 = np.concatenate([A, A])
-    d = amg.crs_setup(8, ids, 32, Ai2, Aj2, A2, 1, None, L=emu)
+    d = amg.crs_setup(8, ids, 32, Ai2, Aj2, A2, 1, None, L=emu, uint_bits=32)
     b = np.array([1.0, -1, 0.5, -0.5, 0, 0, 0, 0])
     x = np.zeros(8)
     amg.crs_solve(x, d, b)
@@ -168,7 +168,114 @@ def test_crs_interface_mirrors_reference_test(emu):
     amg.crs_free(d)
     with pytest.raises(amg.AmgError):
         amg.crs_setup(2, np.array([0, 0], np.uint64), 0, np.zeros(0, np.uint32), np.zeros(0, np.uint32),
-                      np.zeros(0), 0, None, L=emu)
+                      np.zeros(0), 0, None, L=emu, uint_bits=32)
+
+
+@pytest.mark.parametrize("bits", [32, 64])
+def test_crs_setup_reads_gslib_struct_comm(emu, bits):
+    """A real gslib caller always passes a struct comm (comm.h:85: ``uint id, np; comm_ext c;`` with
+    the build-time uint): np == 1 must be accepted and np == 2 rejected, for both integer widths
+    (the reference Makefile's -DUSE_LONG build binds crs_amg_setup_u64)."""
+    UI = ctypes.c_uint64 if bits == 64 else ctypes.c_uint32
+
+    class Comm(ctypes.Structure):
+        _fields_ = [("id", UI), ("np", UI), ("c", ctypes.c_int)]     # comm_ext is an int without MPI
+
+    Ai, Aj, Av = M.poisson7(3)
+    n = 27
+    ids = np.arange(1, n + 1, dtype=np.uint64)
+    one = Comm(0, 1, 0)
+    d = amg.crs_setup(n, ids, len(Av), Ai, Aj, Av, 0, ctypes.addressof(one), L=emu, uint_bits=bits)
+    x = np.zeros(n)
+    amg.crs_solve(x, d, np.ones(n))
+    assert np.isfinite(x).all() and np.abs(x).max() > 0
+    amg.crs_free(d)
+    two = Comm(1, 2, 0)
+    with pytest.raises(amg.AmgError, match="np == 1"):
+        amg.crs_setup(n, ids, len(Av), Ai, Aj, Av, 0, ctypes.addressof(two), L=emu, uint_bits=bits)
+
+
+def test_unmodified_reference_driver_links_against_the_shim(emu, tmp_path):
+    """serial_amg.c (and fail.c) of the reference, compiled UNMODIFIED with the reference's own
+    flags (-DUSE_LONG: uint = unsigned long) and linked against the reference-shaped entry points
+    amg_setup / amg_export / free_data of include/amg_setup_b200.h (host-emulation build here; the
+    GPU test runs the same driver against the CUDA library): its four output files must equal the
+    ones the reference's own serial_amg wrote (tests/golden/ref_dump.npz)."""
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "drivers"], check=True, stdout=subprocess.DEVNULL)
+    exe = os.path.join(ROOT, "oracle", "_ref", "serial_amg_emu")
+    if not os.path.exists(exe):
+        pytest.skip("needs /root/reference to compile the unmodified driver")
+    import shutil
+    for k in "ijp":
+        shutil.copy(os.path.join(GOLDEN, "amgdmp_%s.dat" % k), str(tmp_path))
+    r = subprocess.run([exe], cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "Level 1, dim(A) = 49" in r.stdout and "Nullspace = 1" in r.stdout
+    z = np.load(os.path.join(GOLDEN, "ref_dump.npz"))
+    for f in ("amg.dat", "amg_W.dat", "amg_AfP.dat", "amg_Aff.dat"):
+        assert np.array_equal(np.fromfile(os.path.join(str(tmp_path), f)), z["file_" + f.replace(".", "_")]), f
+
+
+def test_shim_fills_struct_amg_setup_data(emu):
+    """amg_setup of the shim fills every field of struct amg_setup_data (amg_tools.h:29-52) with the
+    reference's build-time uint (unsigned long); compared with the fixture the reference produced."""
+    from test_oracle import load_golden
+    want, mat, _ = load_golden(os.path.join(GOLDEN, "ref_dump.npz"))
+    S = ctypes.CDLL(os.path.join(ROOT, "tests", "_emu", "libamg_setup_emu.so"))
+    data = orc._RData()
+    Ai = np.ascontiguousarray(mat[0], np.uint64); Aj = np.ascontiguousarray(mat[1], np.uint64)
+    Av = np.ascontiguousarray(mat[2], np.float64)
+    S.amg_setup.argtypes = [ctypes.c_ulong, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(orc._RData)]
+    with orc._Quiet():
+        S.amg_setup(len(Av), Ai.ctypes.data, Aj.ctypes.data, Av.ctypes.data, ctypes.byref(data))
+    assert int(data.nlevels) == want.nlevels and int(data.nullspace) == want.nullspace
+    assert data.tolc == 0.7 and abs(data.gamma ** 2 - (1 - np.sqrt(0.5))) < 1e-15
+    for l, lev in enumerate(want.levels):
+        A = orc.Ref.from_csr(data.A[l])
+        assert A[3] == lev["A"][3] and np.array_equal(A[0], lev["A"][0]) and np.array_equal(A[1], lev["A"][1])
+        assert np.array_equal(A[2], lev["A"][2])
+        assert data.n[l] == lev["A"][3][0] and data.nnz[l] == len(lev["A"][1])
+        if l == want.nlevels - 1:
+            break
+        for name, arr in (("Af", data.Af), ("W", data.W), ("AfP", data.AfP)):
+            X = orc.Ref.from_csr(arr[l])
+            assert np.array_equal(X[0], lev[name][0]) and np.array_equal(X[1], lev[name][1]) and np.array_equal(X[2], lev[name][2]), name
+        n = lev["A"][3][0]; nf, nc = lev["W"][3]
+        assert np.array_equal(np.ctypeslib.as_array(data.C[l], (n,)), lev["C"])
+        assert np.array_equal(np.ctypeslib.as_array(data.F[l], (n,)), 1.0 - lev["C"])
+        assert np.array_equal(np.ctypeslib.as_array(data.D[l], (nf,)), lev["D"])
+        assert np.array_equal(np.ctypeslib.as_array(data.idc[l], (nc,)).astype(np.float64), lev["idc"])
+        assert np.array_equal(np.ctypeslib.as_array(data.idf[l], (nf,)).astype(np.float64), lev["idf"])
+        assert data.m[l] == lev["m"] and data.rho[l] == lev["rho"]
+        assert data.nnzf[l] == len(lev["Af"][1]) and data.nnzfp[l] == len(lev["AfP"][1])
+    assert np.array_equal(np.ctypeslib.as_array(data.id, (49,)), np.arange(1, 50))
+    S.free_data.argtypes = [ctypes.c_void_p]
+
+
+def test_hierarchy_hash_matches_python_definition(emu, O):
+    """amgb_hierarchy_hash (what bench.py prints on every GPU count) equals oracle.hierarchy_hash of
+    the oracle's hierarchy for the same input, and differs when one value bit differs."""
+    for mat in (M.read_amgdmp(GOLDEN), M.poisson7(7), M.sem_hex(5)):
+        H = amg.amg_setup(*mat, L=emu)
+        want = O.setup(*mat, orc.SEQ)
+        assert H.hash() == orc.hierarchy_hash(want) == orc.hierarchy_hash(fetch(H))
+        want.levels[0]["W"][2][0] = np.nextafter(want.levels[0]["W"][2][0], 1e300)
+        assert H.hash() != orc.hierarchy_hash(want)
+
+
+def test_trace_fixtures_are_well_formed():
+    """The committed oracle traces at sizes the oracle needs minutes for (make_trace_fixtures.py)."""
+    import glob
+    from util import load_trace_fixture
+    files = sorted(glob.glob(os.path.join(GOLDEN, "trace_*.json.gz")))
+    assert len(files) >= 4
+    rows = 0
+    for f in files:
+        fx = load_trace_fixture(f)
+        assert fx["nlevels"] == len(fx["levels"]) and len(fx["trace"]) > 100
+        assert fx["levels"][-1]["info"][0] <= 1 and len(fx["hierarchy_hash"]) == 16
+        rows = max(rows, fx["levels"][0]["info"][0])
+    assert rows >= 64 ** 3
 
 
 def test_matrix_generators():

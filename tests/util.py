@@ -52,6 +52,16 @@ def product_trace(L):
     return out
 
 
+def load_trace_fixture(path):
+    """tests/golden/trace_*.json.gz (make_trace_fixtures.py): trace as (tag, hash, bytes) tuples."""
+    import gzip
+    import json
+    with gzip.open(path, "rb") as f:
+        fx = json.loads(f.read().decode())
+    fx["trace"] = [(t, int(h, 16), nb) for t, h, nb in fx["trace"]]
+    return fx
+
+
 def first_trace_mismatch(ta, tb):
     for i, (x, y) in enumerate(zip(ta, tb)):
         if x != y:
