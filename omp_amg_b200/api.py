@@ -141,6 +141,14 @@ def debug_spgemm(A, B, L=None):
     return xro, xcol[:nnz.value], xa[:nnz.value], (arn, bcn)
 
 
+def debug_spgemm_tiers(L=None):
+    """Rows per SpGEMM tier of the last :func:`debug_spgemm` call: (as binned, after hand-downs)."""
+    L = L or lib()
+    out = (C.c_int32 * 20)()
+    L.amgb_debug_spgemm_tiers(out)
+    return list(out[:10]), list(out[10:])
+
+
 def build_info(L=None):
     return (L or lib()).amgb_build_info().decode()
 

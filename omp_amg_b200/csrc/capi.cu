@@ -428,7 +428,9 @@ int amgb_debug_spgemm(int32_t arn, int32_t acn, const int32_t *aro, const int32_
   if (annz) { A.col.upload(acol, annz); A.a.upload(aa, annz); }
   if (bnnz) { B.col.upload(bcol, bnnz); B.a.upload(ba, bnnz); }
   spgemm_cache_reset();
+  spgemm_debug_collect(true);
   Csr X = spgemm(A, B);
+  spgemm_debug_collect(false);
   spgemm_cache_reset();
   *xnnz = X.nnz;
   d2h(xro, X.ro.p, sizeof(int) * (size_t)(arn + 1));
@@ -440,6 +442,8 @@ int amgb_debug_spgemm(int32_t arn, int32_t acn, const int32_t *aro, const int32_
   return 0;
   API_END
 }
+
+int amgb_debug_spgemm_tiers(int32_t out[20]) { spgemm_debug_tiers(out); return 0; }
 
 void amgb_trace_enable(int on) { ctx().trace_on = on != 0; ctx().trace.clear(); }
 int amgb_trace_count(void) { return (int)ctx().trace.size(); }

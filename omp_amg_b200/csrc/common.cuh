@@ -83,6 +83,7 @@ size_t dev_peak_bytes();       // high-water mark of live device memory
 void dev_memset(void *p, int v, size_t bytes);
 void h2d(void *dst, const void *src, size_t bytes);
 void d2h(void *dst, const void *src, size_t bytes);   // synchronises the stream
+void d2h_async(void *dst, const void *src, size_t bytes);   // no synchronisation: call stream_sync() before reading
 void d2d(void *dst, const void *src, size_t bytes);
 void stream_sync();
 
@@ -211,6 +212,7 @@ HD inline double key_dbl(unsigned long long k) {
 // out[i] = sum_{j<i} in[j] for i in [0,n]; out has n+1 entries; returns out[n] on the host.
 i64 exclusive_scan(const int *in, int *out, i64 n);
 i64 exclusive_scan64(const i64 *in, i64 *out, i64 n);
+void exclusive_scan_dev(const int *in, int *out, i64 n);   // the total stays in out[n] on the device
 
 // Deterministic tree sum of n doubles with the fixed shape documented in DESIGN.md
 // (1024-value chunks, 256 "threads" x 4 strided values, strides 16..1 inside a warp,

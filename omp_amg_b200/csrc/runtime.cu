@@ -112,6 +112,9 @@ void d2h(void *dst, const void *src, size_t bytes) {
   if (bytes) CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_ctx.stream));
   stream_sync();
 }
+void d2h_async(void *dst, const void *src, size_t bytes) {       // the caller synchronises
+  if (bytes) CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_ctx.stream));
+}
 void d2d(void *dst, const void *src, size_t bytes) {
   if (bytes) CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g_ctx.stream));
 }
@@ -177,6 +180,12 @@ static T scan_total(const T *in, T *out, i64 n) {
   return tot;
 }
 i64 exclusive_scan(const int *in, int *out, i64 n) { return (i64)scan_total<int>(in, out, n); }
+void exclusive_scan_dev(const int *in, int *out, i64 n) {      // total left in out[n], no read-back
+  if (n <= 0) { dev_memset(out, 0, sizeof(int)); return; }
+  scan_rec<int>(in, out, n);
+  k_scan_last<int><<<1, 1, 0, g_ctx.stream>>>(in, out, n);
+  g_ctx.launches++; post_launch(__func__);
+}
 i64 exclusive_scan64(const i64 *in, i64 *out, i64 n) { return scan_total<i64>(in, out, n); }
 
 // ---- deterministic tree sum ----
@@ -895,6 +904,7 @@ size_t dev_peak_bytes() { return 0; }
 void dev_memset(void *p, int v, size_t bytes) { memset(p, v, bytes); }
 void h2d(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); }
 void d2h(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); g_ctx.syncs++; }
+void d2h_async(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); }
 void d2d(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); }
 void stream_sync() { g_ctx.syncs++; }
 
@@ -904,6 +914,7 @@ i64 exclusive_scan(const int *in, int *out, i64 n) {
   out[n] = s;
   return s;
 }
+void exclusive_scan_dev(const int *in, int *out, i64 n) { exclusive_scan(in, out, n); }
 i64 exclusive_scan64(const i64 *in, i64 *out, i64 n) {
   i64 s = 0;
   for (i64 i = 0; i < n; i++) { i64 v = in[i]; out[i] = s; s += v; }

@@ -570,6 +570,11 @@ Csr find_support(const Csr &R, Csr &Rt, Buf<int> &tpos, double goal) {   // Rt =
     while (mv <= (1 + theta) * goal) theta = theta / 2.;
     const double thr = (1 + theta) * goal;
 #ifdef AMGB_EMU
+    if (getenv("AMGB_FS_LOG")) {
+      int nb = 0;
+      for (int c = 0; c < nc; c++) if (wp[c] > thr) nb++;
+      fprintf(stderr, "fs nf %d nc %d nnz %lld bad %d mv %.6g thr %.6g\n", nf, nc, (long long)R.nnz, nb, mv, thr);
+    }
     parallel_for(nc, [=] DEV(i64 c) {
       double sum = 0.0;
       for (int p = tro[c]; p < tro[c + 1]; p++) sum = sum + rtv[p];

@@ -89,6 +89,59 @@ __global__ void __launch_bounds__(256) k_spmv_row32(int rn, const int *ro, const
     z[i] = r;
   }
 }
+// Long rows, second generation: G = 16 lanes per row (two rows per warp, so an add instruction of
+// the ordered chain serves two rows), products parked in a double-buffered slice of shared memory
+// and read back as broadcast LDS.128, and the loads software-pipelined three deep: while batch b
+// is added, x[col] of batch b+1 and (col, val) of batch b+2 are in flight, so the chain of
+// dependent adds never waits for a gather.
+template <int G>
+__global__ void __launch_bounds__(256) k_spmv_pipe(int rn, const int *ro, const int *col, const double *vals,
+                                                   const double *x, double *z, double alpha, const double *y,
+                                                   double beta, bool plain, const double *post) {
+  __shared__ __align__(16) double buf[256 / G][2][G];
+  const int grp = threadIdx.x / G, lane = threadIdx.x % G;
+  const int i = blockIdx.x * (256 / G) + grp;
+  if (i >= rn) return;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+  const int beg = ro[i], end = ro[i + 1];
+  // stage 2: (col, val) of the batch after next; stage 1: x of the next batch; stage 0: the product
+  int c1 = 0, c2 = 0;
+  double v0 = 0.0, x0 = 0.0, v1 = 0.0, v2 = 0.0;
+  { const int j = beg + lane; if (j < end) { c1 = col[j]; v1 = vals[j]; } }
+  { const int j = beg + G + lane; if (j < end) { c2 = col[j]; v2 = vals[j]; } }
+  if (beg + lane < end) x0 = x[c1];
+  v0 = v1;
+  double t = 0;
+  int par = 0;
+  for (int base = beg; base < end; base += G, par ^= 1) {
+    const double p = (base + lane < end) ? v0 * x0 : 0.0;
+    // advance the pipeline: gather x for the next batch (its columns are here), fetch the batch after
+    double xn = 0.0;
+    if (base + G + lane < end) xn = x[c2];
+    const double vn = v2;
+    { const int j = base + 2 * G + lane; if (j < end) { c2 = col[j]; v2 = vals[j]; } }
+    double *b = buf[grp][par];
+    b[lane] = p;
+    __syncwarp(gmask);
+    const int m = end - base;
+    if (m >= G) {
+#pragma unroll
+      for (int l = 0; l < G; l += 2) {
+        const double2 q = *reinterpret_cast<const double2 *>(b + l);
+        t = t + q.x;
+        t = t + q.y;
+      }
+    } else {
+      for (int l = 0; l < m; l++) t = t + b[l];
+    }
+    v0 = vn; x0 = xn;
+  }
+  if (lane == 0) {
+    double r = plain ? beta * t : alpha * y[i] + beta * t;
+    if (post) r = r * post[i];
+    z[i] = r;
+  }
+}
 #endif
 
 static void spmv_vals_run(double *z, double alpha, const double *y, double beta, const Csr &M, const double *vals,
@@ -124,10 +177,14 @@ static void spmv_vals_run(double *z, double alpha, const double *y, double beta,
 #ifndef AMGB_EMU
   if (M.rn > 0 && (double)M.nnz / (double)M.rn > 8.0) {
     Context &c = ctx();
+    static int spmv_kind = -1;      // AMGB_SPMV=row32: the first-generation long-row kernel (A/B measurements)
+    if (spmv_kind < 0) { const char *e = getenv("AMGB_SPMV"); spmv_kind = (e && !strcmp(e, "row32")) ? 0 : 1; }
     if ((double)M.nnz / (double)M.rn <= 64.0 && !test_small_bins())
       k_spmv_tile<8><<<(M.rn + 31) / 32, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post);
-    else
+    else if (spmv_kind == 0)
       k_spmv_row32<<<(M.rn + 7) / 8, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post);
+    else
+      k_spmv_pipe<16><<<(M.rn + 15) / 16, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post);
     c.launches++; post_launch("spmv_tile");
     return;
   }
@@ -304,6 +361,72 @@ Csr sub_mat(const Csr &A, const double *vr, const double *vc) {
 // ---------------------------------------------------------------------------------------
 // mpm (:1684): X = alpha*A + beta*B
 // ---------------------------------------------------------------------------------------
+#ifndef AMGB_EMU
+// G lanes per row.  Every entry finds its partner in the other row by binary search; its place in
+// the merged row is (own index) + (entries of the other row with a smaller column) - (coincident
+// pairs before it, which are one entry instead of two) - (those of them whose sum is exactly 0,
+// which mpm drops altogether).  The count kernel leaves that running correction per entry of A
+// (dropsbefore) so that the fill kernel needs no ordered pass.
+__device__ __forceinline__ int lower_bound_col(const int *col, int lo, int hi, int key) {
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (col[mid] < key) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+template <int G>
+__global__ void __launch_bounds__(256) k_mpm_count(int rn, double alpha, const int *aro, const int *acol, const double *aa,
+                                                   double beta, const int *bro, const int *bcol, const double *ba,
+                                                   int *cnt, int *dropsbefore, int *ndrop) {
+  const int i = blockIdx.x * (256 / G) + threadIdx.x / G;
+  if (i >= rn) return;
+  const int lane = threadIdx.x % G;
+  const int sub = (threadIdx.x & 31) / G * G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << sub);
+  const int a0 = aro[i], a1 = aro[i + 1], b0 = bro[i], b1 = bro[i + 1];
+  int carry = 0;
+  for (int base = a0; base < a1; base += G) {
+    const int j = base + lane;
+    bool drop = false, match = false;
+    if (j < a1) {
+      const int c = acol[j];
+      const int p = lower_bound_col(bcol, b0, b1, c);
+      if (p < b1 && bcol[p] == c) { match = true; const double s = alpha * aa[j] + beta * ba[p]; drop = (s == 0.); }
+    }
+    const unsigned bd = (__ballot_sync(gmask, drop) >> sub) & ((G == 32) ? 0xffffffffu : ((1u << G) - 1u));
+    const unsigned bm = (__ballot_sync(gmask, match) >> sub) & ((G == 32) ? 0xffffffffu : ((1u << G) - 1u));
+    const unsigned lt = (1u << lane) - 1u;
+    if (j < a1) dropsbefore[j] = carry + __popc(bd & lt) + __popc(bm & lt);
+    carry += __popc(bd) + __popc(bm);
+  }
+  if (lane == 0) { cnt[i] = (a1 - a0) + (b1 - b0) - carry; ndrop[i] = carry; }
+}
+template <int G>
+__global__ void __launch_bounds__(256) k_mpm_fill(int rn, double alpha, const int *aro, const int *acol, const double *aa,
+                                                  double beta, const int *bro, const int *bcol, const double *ba,
+                                                  const int *xro, const int *dropsbefore, const int *ndrop, int *xcol,
+                                                  double *xa) {
+  const int i = blockIdx.x * (256 / G) + threadIdx.x / G;
+  if (i >= rn) return;
+  const int lane = threadIdx.x % G;
+  const int a0 = aro[i], a1 = aro[i + 1], b0 = bro[i], b1 = bro[i + 1], x0 = xro[i];
+  for (int j = a0 + lane; j < a1; j += G) {
+    const int c = acol[j];
+    const int p = lower_bound_col(bcol, b0, b1, c);
+    double v;
+    if (p < b1 && bcol[p] == c) { v = alpha * aa[j] + beta * ba[p]; if (v == 0.) continue; }
+    else v = alpha * aa[j];
+    const int pos = x0 + (j - a0) + (p - b0) - dropsbefore[j];
+    xcol[pos] = c; xa[pos] = v;
+  }
+  const int nd = ndrop[i];
+  for (int k = b0 + lane; k < b1; k += G) {
+    const int c = bcol[k];
+    const int p = lower_bound_col(acol, a0, a1, c);
+    if (p < a1 && acol[p] == c) continue;            // written from the A side
+    const int pos = x0 + (k - b0) + (p - a0) - (p < a1 ? dropsbefore[p] : nd);
+    xcol[pos] = c; xa[pos] = beta * ba[k];
+  }
+}
+#endif
+
 Csr mpm(double alpha, const Csr &A, double beta, const Csr &B) {
   StageTimer st_("prim.mpm");
   if (A.rn != B.rn || A.cn != B.cn) throw Error(-4, "mpm: dimension mismatch");
@@ -312,6 +435,24 @@ Csr mpm(double alpha, const Csr &A, double beta, const Csr &B) {
   const double *aa = A.a.p, *ba = B.a.p;
   Buf<int> cnt(rn + 1);
   int *cntp = cnt.p;
+#ifndef AMGB_EMU
+  if (rn > 0 && ((double)(A.nnz + B.nnz) / rn > 12.0 || test_small_bins())) {
+    Context &c = ctx();
+    const bool wide = (double)(A.nnz + B.nnz) / rn > 64.0;
+    Buf<int> dropsbefore(A.nnz), ndrop(rn);
+    if (wide) k_mpm_count<32><<<(rn + 7) / 8, 256, 0, c.stream>>>(rn, alpha, aro, acol, aa, beta, bro, bcol, ba, cntp, dropsbefore.p, ndrop.p);
+    else k_mpm_count<8><<<(rn + 31) / 32, 256, 0, c.stream>>>(rn, alpha, aro, acol, aa, beta, bro, bcol, ba, cntp, dropsbefore.p, ndrop.p);
+    c.launches++; post_launch("mpm_count");
+    Buf<int> xro(rn + 1);
+    const i64 nnz = exclusive_scan(cnt.p, xro.p, rn);
+    Csr X(rn, A.cn, nnz);
+    X.ro = std::move(xro);
+    if (wide) k_mpm_fill<32><<<(rn + 7) / 8, 256, 0, c.stream>>>(rn, alpha, aro, acol, aa, beta, bro, bcol, ba, X.ro.p, dropsbefore.p, ndrop.p, X.col.p, X.a.p);
+    else k_mpm_fill<8><<<(rn + 31) / 32, 256, 0, c.stream>>>(rn, alpha, aro, acol, aa, beta, bro, bcol, ba, X.ro.p, dropsbefore.p, ndrop.p, X.col.p, X.a.p);
+    c.launches++; post_launch("mpm_fill");
+    return X;
+  }
+#endif
   parallel_for(rn, [=] DEV(i64 i) {
     int ja = aro[i], ea = aro[i + 1], jb = bro[i], eb = bro[i + 1], c = 0;
     while (ja < ea || jb < eb) {

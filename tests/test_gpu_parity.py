@@ -320,14 +320,18 @@ def test_two_rank_partitioned_setup_identical_to_one_gpu(L):
 
 @pytest.mark.parametrize("small_bins", ["0", "1"])
 def test_spgemm_primitive_every_bin(L, small_bins, monkeypatch):
-    """mxm in isolation through the C ABI on operands whose rows fall into every SpGEMM bin (tile,
-    warp hash, warp bitmap, optimistic warp + dense fallback, block bitmap, optimistic block table +
-    HBM overflow, global hash): bit-identical to the exact-order reference, exact-zero drops
-    included.  With the test hook on, every row with more than 24 products goes through the
-    optimistic block kernel with a 40-key limit and its overflow path."""
+    """mxm in isolation through the C ABI on operands whose rows fall into every SpGEMM tier (tiles,
+    warps with 512/2048 slots and cp.async rings, blocks with 4096/8192 slots and bulk-async rings,
+    HBM tables, global hash), with rows handed down the optimistic ladder: bit-identical to the
+    exact-order reference, exact-zero drops included.  With the test hook on, every row with more
+    than 96 products starts at the smallest warp tier with limits of 20/40/60/80 keys, so that most
+    rows walk through every tier."""
     from util import spgemm_adversarial_operands, spgemm_reference, same_csr_bits
     monkeypatch.setenv("AMGB_TEST_SMALL_BINS", small_bins)
     A, B = spgemm_adversarial_operands(0)
     want = spgemm_reference(A, B)
     got = api.debug_spgemm(A, B, L=L)
     assert got[3] == want[3] and same_csr_bits(got, want)
+    binned, final = api.debug_spgemm_tiers(L=L)
+    assert all(n > 0 for n in final), ("every SpGEMM tier must have processed rows", binned, final)
+    assert sum(final) > sum(binned)            # some rows were handed down the ladder
