@@ -122,10 +122,10 @@ int amgb_debug_spgemm(int32_t arn, int32_t acn, const int32_t *aro, const int32_
                       int32_t brn, int32_t bcn, const int32_t *bro, const int32_t *bcol, const double *ba,
                       int64_t cap, int64_t *xnnz, int32_t *xro, int32_t *xcol, double *xa);
 
-/* rows per SpGEMM tier of the last amgb_debug_spgemm call: out[0..10) as binned, out[10..20) after the
+/* rows per SpGEMM tier of the last amgb_debug_spgemm call: out[0..11) as binned, out[11..22) after the
  * optimistic hand-downs (tile8, tile32, warp512, warp2048, block4096, block8192, HBM table, global,
- * dense <= 8192 columns, dense <= 22000 columns) */
-int amgb_debug_spgemm_tiers(int32_t out[20]);
+ * block-dense <= 8192 columns, block-dense <= 22000 columns, warp-dense <= 4608 columns) */
+int amgb_debug_spgemm_tiers(int32_t out[22]);
 
 /* ---- stage trace (debug): FNV-1a hashes of intermediate arrays, in stage order ---- */
 void amgb_trace_enable(int on);

@@ -144,9 +144,9 @@ def debug_spgemm(A, B, L=None):
 def debug_spgemm_tiers(L=None):
     """Rows per SpGEMM tier of the last :func:`debug_spgemm` call: (as binned, after hand-downs)."""
     L = L or lib()
-    out = (C.c_int32 * 20)()
+    out = (C.c_int32 * 22)()
     L.amgb_debug_spgemm_tiers(out)
-    return list(out[:10]), list(out[10:])
+    return list(out[:11]), list(out[11:])
 
 
 def build_info(L=None):

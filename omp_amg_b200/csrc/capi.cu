@@ -443,7 +443,7 @@ int amgb_debug_spgemm(int32_t arn, int32_t acn, const int32_t *aro, const int32_
   API_END
 }
 
-int amgb_debug_spgemm_tiers(int32_t out[20]) { spgemm_debug_tiers(out); return 0; }
+int amgb_debug_spgemm_tiers(int32_t out[22]) { spgemm_debug_tiers(out); return 0; }
 
 void amgb_trace_enable(int on) { ctx().trace_on = on != 0; ctx().trace.clear(); }
 int amgb_trace_count(void) { return (int)ctx().trace.size(); }

@@ -61,9 +61,9 @@ void trace_csr(const char *tag, const Csr &A);
 void spgemm_stats_reset();
 void spgemm_cache_reset();      // drops the cached transpose of the last large left operand
 void spgemm_stats_get(double *seconds, i64 *bytes, i64 *calls);
-// diagnostics: rows per SpGEMM tier of the last product ([0..10) as binned, [10..20) after hand-downs)
+// diagnostics: rows per SpGEMM tier of the last product ([0..11) as binned, [11..22) after hand-downs)
 void spgemm_debug_collect(bool on);
-void spgemm_debug_tiers(int out[20]);
+void spgemm_debug_tiers(int out[22]);
 
 // element-wise helpers
 void fill(double *p, i64 n, double v);

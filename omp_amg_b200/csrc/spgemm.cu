@@ -322,7 +322,7 @@ __device__ __forceinline__ bool table_add(int *keys, double *vals, unsigned mask
 // destination after the warp tiers (block 4096 / block 8192 / HBM table / global), decided by the
 // binning kernel from the row's column span.
 struct Tiers {
-  int *list[10];       // per tier: rows to process (bin members first, rows handed down appended)
+  int *list[11];       // per tier: rows to process (bin members first, rows handed down appended)
   int *count;          // count[t]: entries of list[t] (device side)
   int *cursor;         // cursor[t]: next position a warp/block takes
   signed char *done;   // tier that completed the row
@@ -367,18 +367,25 @@ template <int HS>
 struct WarpSm {
   static constexpr int U = (RING_D * RING_C * 12 > HS * 2) ? RING_D * RING_C * 12 : HS * 2;
   static constexpr int PER = HS * 12 + U;
+  static constexpr int PER_DENSE = HS * 8 + RING_D * RING_C * 12;
   static constexpr int BITS = HS == 128 ? 7 : HS == 256 ? 8 : HS == 512 ? 9 : HS == 1024 ? 10 : HS == 2048 ? 11 : 12;
 };
-template <int HS, int WPB>
+// DENSE: the table is replaced by one accumulator per column of the row's span (at most HS
+// columns: the coarse levels, where a row touches most of the few thousand columns there are); no
+// probing, no sorting -- the columns come out in order.
+template <int HS, int WPB, bool DENSE>
 __global__ void __launch_bounds__(WPB * 32) k_spgemm_warp(int phase, int mytier, Tiers tr, const int *aro, const int *acol,
                                                           const double *aa, const int *bro, const int *bcol,
                                                           const double *ba, int *cnt, const int *xro, int *xcol,
-                                                          double *xa, int optimistic, Arena ar) {
+                                                          double *xa, int optimistic, const int *cminv,
+                                                          const int *spanv, Arena ar) {
   extern __shared__ __align__(16) unsigned char wsm[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned sv = smem_u32(wsm) + (unsigned)w * WarpSm<HS>::PER;     // values
+  unsigned sv = smem_u32(wsm) + (unsigned)w * (DENSE ? WarpSm<HS>::PER_DENSE : WarpSm<HS>::PER);   // values / accumulators
+  asm volatile("mov.u32 %0, %0;\n" : "+r"(sv));      // opaque: keep the shared-window offset in a register
+                                                      // (rematerialised, it is an S2R + LEA per use)
   const unsigned sk = sv + HS * 8;                                        // keys
-  const unsigned su = sv + HS * 12;                                       // ring / sort buffer
+  const unsigned su = sv + (DENSE ? HS * 8 : HS * 12);                    // ring / sort buffer
   const unsigned rv = su, rc = su + RING_D * RING_C * 8;
   constexpr int SH = 32 - WarpSm<HS>::BITS;
   const int *list = tr.list[mytier];
@@ -392,7 +399,13 @@ __global__ void __launch_bounds__(WPB * 32) k_spgemm_warp(int phase, int mytier,
     const int i = list[idx];
     if (phase == 2 && tr.done[i] != mytier) continue;
     __syncwarp();
-    for (int h = lane; h < HS; h += 32) sts_i32(sk + 4 * h, EMPTY);
+    int cmin = 0, span = 0;
+    if (DENSE) {
+      cmin = cminv[i]; span = spanv[i];
+      for (int h = lane; h < span; h += 32) sts_f64(sv + 8 * h, 0.0);
+    } else {
+      for (int h = lane; h < HS; h += 32) sts_i32(sk + 4 * h, EMPTY);
+    }
     __syncwarp();
     int filled = 0;
     bool gaveup = false;
@@ -433,6 +446,7 @@ __global__ void __launch_bounds__(WPB * 32) k_spgemm_warp(int phase, int mytier,
           if (q < RING_C) { c = lds_i32(rc + 4 * (so + q)); v = lds_f64(rv + 8 * (so + q)); }
           else { c = bcol[b0 + q]; v = ba[b0 + q]; }
           const double p = v * av;
+          if (DENSE) { const unsigned a = sv + 8 * (unsigned)(c - cmin); sts_f64(a, lds_f64(a) + p); continue; }
           unsigned h = ((unsigned)c * 2654435761u) >> SH;
           for (;;) {
             int cur = lds_i32(sk + 4 * h);
@@ -444,7 +458,7 @@ __global__ void __launch_bounds__(WPB * 32) k_spgemm_warp(int phase, int mytier,
             h = (h + 1) & (HS - 1);
           }
         }
-        if (optimistic) filled += __reduce_add_sync(0xffffffffu, mine);
+        if (!DENSE && optimistic) filled += __reduce_add_sync(0xffffffffu, mine);
         __syncwarp();
       }
 #undef RING_ISSUE
@@ -452,6 +466,29 @@ __global__ void __launch_bounds__(WPB * 32) k_spgemm_warp(int phase, int mytier,
     cp_async_wait<0>();
     if (gaveup) {
       if (lane == 0) hand_down(tr, mytier, i);
+      continue;
+    }
+    if (DENSE) {
+      // count, claim the row's place, write the non-zeros in column order
+      int n = 0;
+      for (int h = lane; h < span; h += 32) n += (lds_f64(sv + 8 * h) != 0.0);
+      n = __reduce_add_sync(0xffffffffu, n);
+      if (lane == 0) tr.done[i] = (signed char)mytier;
+      if (phase == 1) { if (lane == 0) cnt[i] = n; continue; }
+      long long rowbase = 0;
+      if (phase == 3) {
+        if (lane == 0) rowbase = arena_claim(ar, i, n, cnt);
+        rowbase = __shfl_sync(0xffffffffu, rowbase, 0);
+        if (rowbase < 0) continue;
+      } else rowbase = xro[i];
+      int run = 0;
+      for (int h0 = 0; h0 < span; h0 += 32) {
+        const int h = h0 + lane;
+        const double v = h < span ? lds_f64(sv + 8 * h) : 0.0;
+        const unsigned b = __ballot_sync(0xffffffffu, v != 0.0);
+        if (v != 0.0) { const long long pos = rowbase + run + __popc(b & ((1u << lane) - 1u)); xcol[pos] = h + cmin; xa[pos] = v; }
+        run += __popc(b);
+      }
       continue;
     }
     // survivors (exact zeros leave the row): their slots, to be sorted by column
@@ -734,12 +771,13 @@ __global__ void __launch_bounds__(256) k_arena_copy(int rn, const int *xro, cons
 constexpr int SPAN4 = 90000, SPAN8 = 330000, SPAN_HBM = 720000;   // bitmap = span/4 bytes of shared memory
 constexpr int DSPAN8 = 8192, DSPAN = 22000;                       // dense accumulators: 8 bytes per column of the span
 constexpr int T_TILE8 = 0, T_TILE32 = 1, T_W512 = 2, T_W2048 = 3, T_B4096 = 4, T_B8192 = 5, T_HBM = 6, T_GLOBAL = 7,
-              T_DENSE8 = 8, T_DENSE = 9, NTIER = 10;
+              T_DENSE8 = 8, T_DENSE = 9, T_WDENSE = 10, NTIER = 11;
+constexpr int WDSPAN = 4608;                                      // warp-level dense accumulator: 36 KB per warp
 template <int G>
 __global__ void __launch_bounds__(256) k_spgemm_bin(int rn, const int *aro, const int *acol, const int *bro,
                                                     const int *bcol, int bcn, int small, Tiers tr, int *need,
                                                     int *cminv, int *spanv, unsigned char *route, int *stats,
-                                                    unsigned long long *needsum) {
+                                                    unsigned long long *needsum, const signed char *hint) {
   const int i = blockIdx.x * (256 / G) + threadIdx.x / G;
   if (i >= rn) return;
   const int lane = threadIdx.x % G;
@@ -773,12 +811,22 @@ __global__ void __launch_bounds__(256) k_spgemm_bin(int rn, const int *aro, cons
   // must be long enough to keep 256 threads busy)
   else if (!small && span <= DSPAN && products * 2 >= span && products >= 128LL * (aro[i + 1] - aro[i]))
     bin = span <= DSPAN8 ? T_DENSE8 : T_DENSE;
-  else if (small && span <= DSPAN && (i & 3) == 3) bin = (i & 4) ? T_DENSE8 : T_DENSE;   // test hook: a quarter of the rows
+  // the same with short steps: a warp per row
+  else if (!small && span <= WDSPAN && products * 2 >= span) bin = T_WDENSE;
+  else if (small && span <= DSPAN && (i & 3) == 3) bin = span <= WDSPAN ? T_WDENSE : (i & 4) ? T_DENSE8 : T_DENSE;   // test hook: a quarter of the rows
   else if (small || lb <= 192) bin = T_W512;     // test hook: every larger row walks down the whole ladder
   else if (lb <= 768) bin = T_W2048;
   else bin = r;
+  // the tier that finished this row in the last product with the same left operand (Af*W0, Af*W,
+  // Af*W of the next skeleton: the patterns grow slowly): start there instead of at the bottom of
+  // the ladder.  A stale hint costs time, never correctness -- the row is still handed down.
+  if (hint && !small && bin >= T_W512 && bin <= T_GLOBAL) {
+    int ht = hint[i];
+    if (ht > bin && ht <= T_GLOBAL) { if (ht >= T_B4096 && r > ht) ht = r; bin = ht; }
+  }
   tr.list[bin][atomicAdd(&tr.count[bin], 1)] = i;
-  if (bin >= T_DENSE8) atomicMax(&stats[bin == T_DENSE8 ? 2 : 3], span);     // stats[2]/[3]: largest dense span
+  if (bin == T_WDENSE) {}
+  else if (bin >= T_DENSE8) atomicMax(&stats[bin == T_DENSE8 ? 2 : 3], span);     // stats[2]/[3]: largest dense span
   else if (bin >= T_W512) {
     atomicMax(&stats[r], span);                                  // stats[4..6]: largest span per route class
     atomicMax(&stats[r >= T_HBM ? 1 : 0], (int)ub);              // stats[0]/[1]: largest bound (route < / >= HBM)
@@ -818,11 +866,16 @@ struct EventPair {
 };
 
 static int g_spgemm_impl = -1;
+// entry-tier hints: which tier completed every row of the last product with left operand uid
+// (a few entries: between Af*W0 and the next round's Af*W0 the pattern product W_skel*W_skel' runs)
+struct TierHint { unsigned long long uid = 0; int rn = 0; unsigned long long stamp = 0; Buf<signed char> done; };
+static TierHint g_hints[4];
+static unsigned long long g_hint_clock = 0;
 // diagnostics (amgb_debug_spgemm): rows per tier of the last product, entry counts and final counts
 static bool g_collect_tiers = false;
-static int g_last_tiers[20];
+static int g_last_tiers[2 * 11];
 void spgemm_debug_collect(bool on) { g_collect_tiers = on; }
-void spgemm_debug_tiers(int out[20]) { memcpy(out, g_last_tiers, sizeof g_last_tiers); }
+void spgemm_debug_tiers(int out[22]) { memcpy(out, g_last_tiers, sizeof g_last_tiers); }
 
 static Csr spgemm_core_local(const Csr &A, const Csr &B);
 // one GPU: the kernels below; several ranks: the rows of X are partitioned (sparse.cu)
@@ -841,7 +894,7 @@ static Csr spgemm_core(const Csr &A, const Csr &B) {
 // AMGB_SPGEMM_TRANSPOSED=1 and the test hook.
 static Csr g_At_cache;
 static unsigned long long g_At_key = 0;     // Csr::uid of the cached operand (0 = empty)
-void spgemm_cache_reset() { g_At_cache = Csr(); g_At_key = 0; }
+void spgemm_cache_reset() { g_At_cache = Csr(); g_At_key = 0; for (auto &h : g_hints) h = TierHint(); }
 
 Csr spgemm(const Csr &A, const Csr &B) {
   if (g_spgemm_impl < 0) { const char *e = getenv("AMGB_SPGEMM"); g_spgemm_impl = (e && !strcmp(e, "rowhash")) ? 0 : 1; }
@@ -886,13 +939,18 @@ static Csr spgemm_core_local(const Csr &A, const Csr &B) {
   Buf<unsigned char> route(rn);
   Buf<signed char> done(rn);
   Buf<unsigned long long> needsum(1);
-  meta.zero(); needsum.zero();
+  meta.zero(); needsum.zero(); done.zero();
   Tiers tr;
   for (int t = 0; t < NTIER; t++) tr.list[t] = lists.p + (i64)t * rn;
   tr.count = meta.p; tr.cursor = meta.p + NTIER; tr.done = done.p; tr.route = route.p;
   int *stats = meta.p + 2 * NTIER;
-  if ((double)A.nnz / rn > 12.0) k_spgemm_bin<8><<<(rn + 31) / 32, 256, 0, c.stream>>>(rn, aro, acol, bro, bcol, B.cn, small ? 1 : 0, tr, need.p, cminv.p, spanv.p, route.p, stats, needsum.p);
-  else k_spgemm_bin<1><<<(rn + 255) / 256, 256, 0, c.stream>>>(rn, aro, acol, bro, bcol, B.cn, small ? 1 : 0, tr, need.p, cminv.p, spanv.p, route.p, stats, needsum.p);
+  static int hints_on = -1;
+  if (hints_on < 0) { const char *e = getenv("AMGB_SPGEMM_HINTS"); hints_on = (e && *e == '0') ? 0 : 1; }
+  const signed char *hint = nullptr;
+  if (hints_on && A.uid != 0)
+    for (auto &h : g_hints) if (h.uid == A.uid && h.rn == rn) hint = h.done.p;
+  if ((double)A.nnz / rn > 12.0) k_spgemm_bin<8><<<(rn + 31) / 32, 256, 0, c.stream>>>(rn, aro, acol, bro, bcol, B.cn, small ? 1 : 0, tr, need.p, cminv.p, spanv.p, route.p, stats, needsum.p, hint);
+  else k_spgemm_bin<1><<<(rn + 255) / 256, 256, 0, c.stream>>>(rn, aro, acol, bro, bcol, B.cn, small ? 1 : 0, tr, need.p, cminv.p, spanv.p, route.p, stats, needsum.p, hint);
   c.launches++; post_launch("spgemm_bin");
   int hm[32];
   unsigned long long need_total_u = 0;
@@ -972,21 +1030,31 @@ static Csr spgemm_core_local(const Csr &A, const Csr &B) {
       k_spgemm_block<true><<<std::min(hc[t], c.sm_count * bps), 256, sm, c.stream>>>(phase, t, tr, 0, 0, cminv.p, spanv.p, nullptr, nullptr, nullptr, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, 0, rg, ar);
       c.launches++; post_launch("spgemm_block_dense");
     }
+    if (hc[T_WDENSE]) {
+      constexpr size_t sm = WarpSm<WDSPAN>::PER_DENSE;
+      static int bps = 0;
+      if (!bps) {
+        CUDA_CHECK(cudaFuncSetAttribute((const void *)k_spgemm_warp<WDSPAN, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        bps = blocks_per_sm(k_spgemm_warp<WDSPAN, 1, true>, 32, sm);
+      }
+      k_spgemm_warp<WDSPAN, 1, true><<<std::min(hc[T_WDENSE], c.sm_count * bps), 32, sm, c.stream>>>(phase, T_WDENSE, tr, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, 0, cminv.p, spanv.p, ar);
+      c.launches++; post_launch("spgemm_warp_dense");
+    }
     // the ladder: every tier also takes the rows handed down by the tiers above it (first pass)
     const bool lower = hc[T_W512] || hc[T_W2048];
     if (hc[T_W512]) {
       constexpr size_t sm = 4 * WarpSm<512>::PER;
       static int bps = 0;
-      if (!bps) bps = blocks_per_sm(k_spgemm_warp<512, 4>, 128, sm);
+      if (!bps) bps = blocks_per_sm(k_spgemm_warp<512, 4, false>, 128, sm);
       const int grid = std::min((hc[T_W512] + 3) / 4, c.sm_count * bps);
-      k_spgemm_warp<512, 4><<<grid, 128, sm, c.stream>>>(phase, T_W512, tr, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, first ? lim512 : 0, ar);
+      k_spgemm_warp<512, 4, false><<<grid, 128, sm, c.stream>>>(phase, T_W512, tr, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, first ? lim512 : 0, cminv.p, spanv.p, ar);
       c.launches++; post_launch("spgemm_warp512");
     }
     if (lower) {
       constexpr size_t sm = WarpSm<2048>::PER;
       static int bps = 0;
-      if (!bps) bps = blocks_per_sm(k_spgemm_warp<2048, 1>, 32, sm);
-      k_spgemm_warp<2048, 1><<<c.sm_count * bps, 32, sm, c.stream>>>(phase, T_W2048, tr, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, first ? lim2048 : 0, ar);
+      if (!bps) bps = blocks_per_sm(k_spgemm_warp<2048, 1, false>, 32, sm);
+      k_spgemm_warp<2048, 1, false><<<c.sm_count * bps, 32, sm, c.stream>>>(phase, T_W2048, tr, aro, acol, aa, bro, bcol, ba, cnt.p, xro.p, xcol, xa, first ? lim2048 : 0, cminv.p, spanv.p, ar);
       c.launches++; post_launch("spgemm_warp2048");
     }
     const bool to4 = hc[T_B4096] || (lower && (small || maxneed_lo > lim2048) && span4 > 0);
@@ -1072,9 +1140,14 @@ static Csr spgemm_core_local(const Csr &A, const Csr &B) {
       d2h(hcnt, tr.count, sizeof hcnt);
       fprintf(stderr, "spgemm A %dx%d nnz %lld  B %dx%d nnz %lld  X nnz %lld | tiers in %d %d %d %d %d %d %d %d d %d %d | total %d %d %d %d %d %d %d %d | %.3f ms | %.1f GB/s\n",
               A.rn, A.cn, (long long)A.nnz, B.rn, B.cn, (long long)B.nnz, (long long)X.nnz, hc[0], hc[1], hc[2], hc[3], hc[4],
-              hc[5], hc[6], hc[7], hc[8], hc[9], hcnt[0], hcnt[1], hcnt[2], hcnt[3], hcnt[4], hcnt[5], hcnt[6], hcnt[7], m1,
+              hc[5], hc[6], hc[7], hc[8], hc[9] * 1000000 + hc[10], hcnt[0], hcnt[1], hcnt[2], hcnt[3], hcnt[4], hcnt[5], hcnt[6], hcnt[7], m1,
               (12.0 * (A.nnz + B.nnz + X.nnz)) / (m1 * 1e-3) / 1e9);
     }
+  }
+  if (hints_on && A.uid != 0) {          // replace this operand's entry, else the oldest one
+    TierHint *slot = &g_hints[0];
+    for (auto &h : g_hints) { if (h.uid == A.uid) { slot = &h; break; } if (h.stamp < slot->stamp) slot = &h; }
+    slot->uid = A.uid; slot->rn = rn; slot->stamp = ++g_hint_clock; slot->done = std::move(done);
   }
   if (g_collect_tiers) {
     int hcnt[NTIER];
@@ -1089,7 +1162,7 @@ static Csr spgemm_core_local(const Csr &A, const Csr &B) {
 #else
 void spgemm_stats_reset() {}
 void spgemm_debug_collect(bool) {}
-void spgemm_debug_tiers(int out[20]) { memset(out, 0, 20 * sizeof(int)); }
+void spgemm_debug_tiers(int out[22]) { memset(out, 0, 22 * sizeof(int)); }
 void spgemm_cache_reset() {}
 void spgemm_stats_get(double *seconds, i64 *bytes, i64 *calls) { *seconds = 0; *bytes = 0; *calls = 0; }
 Csr spgemm(const Csr &A, const Csr &B) {

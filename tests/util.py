@@ -107,7 +107,7 @@ def spgemm_adversarial_operands(seed=0):
     bcn = 1_200_000
     classes = [(1000, (0, 7), 20_000), (1000, (20, 61), 24_000), (400, (20, 61), 380_000),
                (300, (20, 61), 790_000), (300, (200, 401), 790_000), (300, (200, 401), bcn),
-               (600, (130, 161), 6_000), (600, (140, 201), 21_000)]      # rows that fill most of a narrow span (dense tiers)
+               (600, (130, 161), 6_000), (600, (140, 201), 21_000), (500, (20, 61), 3_000)]      # rows that fill most of a narrow span (dense tiers)
     bro, bcol, ba, first = [0], [], [], []
     for count, (lo, hi), width in classes:
         first.append(len(bro) - 1)
@@ -118,7 +118,7 @@ def spgemm_adversarial_operands(seed=0):
             bcol.extend(c.tolist()); ba.extend(v.tolist()); bro.append(len(bcol))
     brn = len(bro) - 1
     plan = [(0, (1, 5)), (0, (10, 16)), (1, (3, 5)), (1, (20, 61)), (2, (10, 15)), (2, (40, 51)),
-            (4, (18, 23)), (4, (30, 36)), (5, (4, 9)), (3, (60, 90)), (1, (70, 91)), (1, (110, 141)), (1, (230, 281)), (6, (30, 41)), (7, (60, 81))]
+            (4, (18, 23)), (4, (30, 36)), (5, (4, 9)), (3, (60, 90)), (1, (70, 91)), (1, (110, 141)), (1, (230, 281)), (6, (30, 41)), (7, (60, 81)), (8, (50, 81))]
     aro, acol, aa = [0], [], []
     for cls, (lo, hi) in plan:
         count = classes[cls][0]
