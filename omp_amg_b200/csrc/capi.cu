@@ -333,7 +333,7 @@ int amgb_solve_device(const amgb_hier *h, double *dx, const double *db) {
 int amgb_solve_device_repeat(const amgb_hier *h, double *dx, const double *db, int repeat) {
   API_BEGIN
   if (!h) return fail(-2, "null hierarchy");
-  for (int r = 0; r < repeat; r++) vcycle_solve(h->H, dx, db);
+  for (int r = 0; r < repeat; r++) vcycle_solve_graph(h->H, dx, db);
   stream_sync();
   return 0;
   API_END
@@ -555,7 +555,7 @@ void crs_amg_solve(double *x, struct crs_data *d, double *b) {
     double *ubp = d->ub.p, *uxp = d->ux.p, *xp = d->dx.p;
     const int *off = d->inv_off.p, *idx = d->inv_idx.p, *um = d->umap.p;
     parallel_for(un, [=] DEV(i64 u) { double s = 0.0; for (int q = off[u]; q < off[u + 1]; q++) s += bp[idx[q]]; ubp[u] = s; });
-    vcycle_solve(d->h->H, uxp, ubp);
+    vcycle_solve_graph(d->h->H, uxp, ubp);       // replayed as a CUDA graph from the second solve on
     // the hierarchy projects the mean out when it detected a singular operator; crs_solve does
     // so when the caller asked for it (amg.c:181)
     if (d->null_space && !d->h->H.nullspace) project_mean(uxp, un);

@@ -417,6 +417,337 @@ k_build_q_cluster(const int *list, int nlist, int maxnz, const int *wro, double 
   }
 }
 
+// =======================================================================================
+// Huge supports: blocked, right-looking A-orthogonalisation over the whole GPU.
+//
+// The reference piles every F row without a coupling to a C row into column 0 (min_skel :2229):
+// one coarse column with a support of 1050 rows at 128^3 Poisson, of 18 568 rows at 64^3
+// anisotropic diffusion.  Step k of the reference (:2083-2098) is
+//     sqv2[j] = sum_{m<=j} Q_j[m] G[k][m]              (G = Gram rows of A on the support, sparse)
+//     q_k[r]  = sum_{j=r}^{k-1} Q_j[r] sqv2[j]          (ascending j, starting from 0)
+//     alpha   = G[k][k] - sum_{m<k} G[k][m] q_k[m];  q_k *= -1/sqrt(alpha);  q_k[k] = 1/sqrt(alpha)
+// i.e. O(k^2) work with O(k) dependent additions per step, O(nz^3/6) in all.  Two facts make it a
+// blocked algorithm without touching a single rounding:
+//   * sqv2[j] of step k depends on row j of Q and on G only, so S2[k][j] can be formed as soon as
+//     row j is final, for all k > j at once;
+//   * q_k[r] receives its addends in ascending j, so after row j is final the update
+//     Y[k][r] += Q_j[r] S2[k][j] may be applied to every later row k -- each element still sees its
+//     addends in ascending j, one rounded product and one rounded addition each.
+// Rows are processed in panels of b: inside a panel the rows are finished one after the other by
+// a cooperative kernel (one grid barrier per row: a row applies the pending updates of its own
+// panel lazily), then S2 of the panel against all later rows is formed (sparse dots) and the
+// trailing rows take the b updates of the panel in one register-tiled pass (k_q_trail: the bulk of
+// the work, a GEMM-shaped loop with the accumulation order fixed).  Exact zeros of G are skipped:
+// adding a (signed) zero product changes no partial sum.
+// =======================================================================================
+struct LocalGram { Buf<int> ro, col; Buf<double> a; };   // lower triangle incl. diagonal, local indices
+
+__global__ void __launch_bounds__(256) k_lg_count(int nz, const int *Qj, const int *aro, const int *acol, int *cnt) {
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  if (k >= nz) return;
+  const int s = Qj[k];
+  int c = 0;
+  for (int e = aro[s]; e < aro[s + 1]; e++) { const int m = pos_of(Qj, k + 1, acol[e]); c += (m >= 0); }
+  cnt[k] = c;
+}
+__global__ void __launch_bounds__(256) k_lg_fill(int nz, const int *Qj, const int *aro, const int *acol, const double *aa,
+                                                 const int *gro, int *gcol, double *ga) {
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  if (k >= nz) return;
+  const int s = Qj[k];
+  int p = gro[k];
+  for (int e = aro[s]; e < aro[s + 1]; e++) {
+    const int m = pos_of(Qj, k + 1, acol[e]);
+    if (m >= 0) { gcol[p] = m; ga[p] = aa[e]; p++; }
+  }
+}
+
+#define QP_BMAX 64
+// rows [j0, j1) of one column; cooperative launch.  Inside the panel the rows are kept UNSCALED
+// with their factor -1/sqrt(alpha) aside (every block holds the factors in shared memory): a read
+// multiplies on the fly, which is the same rounded product the reference stores.
+__global__ void __launch_bounds__(256) k_q_panel(int j0, int j1, double *Q, const int *gro, const int *gcol,
+                                                 const double *ga) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sfac[QP_BMAX], ss2[QP_BMAX];
+  const int t = threadIdx.x, tid = blockIdx.x * 256 + t, T = gridDim.x * 256;
+  for (int j = j0; j <= j1; j++) {
+    // factor of the row finished in the previous step (its elements are complete after the barrier)
+    if (j > j0) {
+      if (t == 0) {
+        const int k = j - 1;
+        const double *qk = Q + tri(k);
+        double alpha = 0.0;
+        const int e1 = gro[k + 1];
+        if (e1 > gro[k] && gcol[e1 - 1] == k) alpha = ga[e1 - 1];
+        for (int e = gro[k]; e < e1; e++) { const int m = gcol[e]; if (m >= k) break; alpha = alpha - ga[e] * __ldcg(qk + m); }
+        sfac[k - j0] = -1.0 / sqrt(alpha);
+      }
+      __syncthreads();
+    }
+    if (j == j1) break;
+    const int np = j - j0;
+    // S2[j][jp] for the finished rows jp of this panel (every block forms all of them: no exchange)
+    if (t < np) {
+      const int jp = j0 + t;
+      const double *qp = Q + tri(jp);
+      const double f = sfac[t];
+      double v = 0.0;
+      for (int e = gro[j]; e < gro[j + 1]; e++) {
+        const int m = gcol[e];
+        if (m > jp) break;
+        const double q = (m == jp) ? -f : __ldcg(qp + m) * f;
+        v = v + q * ga[e];
+      }
+      ss2[t] = v;
+    }
+    __syncthreads();
+    // pending updates of this panel onto row j (earlier panels were applied by their trailing pass)
+    double *qj = Q + tri(j);
+    for (int r = tid; r < j; r += T) {
+      double y = qj[r];
+      for (int jj = r > j0 ? r - j0 : 0; jj < np; jj++) {
+        const int jp = j0 + jj;
+        const double f = sfac[jj];
+        const double q = (r == jp) ? -f : __ldcg(Q + tri(jp) + r) * f;
+        y = y + q * ss2[jj];
+      }
+      qj[r] = y;
+    }
+    grid.sync();
+  }
+  // scale the panel rows in place: Q is final from here on
+  for (int jj = 0; jj < j1 - j0; jj++) {
+    const int k = j0 + jj;
+    double *qk = Q + tri(k);
+    const double f = sfac[jj];
+    for (int m = tid; m <= k; m += T) qk[m] = (m == k) ? -f : qk[m] * f;
+  }
+}
+
+// S2 of the panel against the later rows: s2p[(k - j1) * bb + jj] = sum_{m <= j0+jj} Q_{j0+jj}[m] G[k][m]
+__global__ void __launch_bounds__(256) k_q_s2(int nz, int j0, int j1, const double *Q, const int *gro, const int *gcol,
+                                              const double *ga, double *s2p) {
+  const int bb = j1 - j0;
+  const i64 total = (i64)(nz - j1) * bb;
+  for (i64 idx = (i64)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (i64)gridDim.x * 256) {
+    const int k = j1 + (int)(idx / bb), jj = (int)(idx % bb), jp = j0 + jj;
+    const double *qp = Q + tri(jp);
+    double v = 0.0;
+    for (int e = gro[k]; e < gro[k + 1]; e++) {
+      const int m = gcol[e];
+      if (m > jp) break;
+      v = v + qp[m] * ga[e];
+    }
+    s2p[idx] = v;
+  }
+}
+
+// trailing update: Y[k][r] += sum over the panel rows jp >= r (ascending) of Q_jp[r] * S2[k][jp],
+// k in [j1, nz), r in [0, j1).  64 x 64 tiles, 4 x 4 per thread, the panel staged in shared memory.
+__global__ void __launch_bounds__(256) k_q_trail(int nz, int j0, int j1, double *Q, const double *s2p) {
+  extern __shared__ __align__(16) double trail_sm[];
+  double (*sQ)[64 + 4] = reinterpret_cast<double (*)[64 + 4]>(trail_sm);
+  double (*sS)[QP_BMAX + 1] = reinterpret_cast<double (*)[QP_BMAX + 1]>(trail_sm + QP_BMAX * (64 + 4));
+  const int bb = j1 - j0;
+  const int r0 = blockIdx.x * 64, k0 = j1 + blockIdx.y * 64;
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  for (int idx = t; idx < bb * 64; idx += 256) {
+    const int jj = idx / 64, c = idx - jj * 64, r = r0 + c, jp = j0 + jj;
+    sQ[jj][c] = (r <= jp) ? Q[tri(jp) + r] : 0.0;
+  }
+  for (int idx = t; idx < 64 * bb; idx += 256) {
+    const int kk = idx / bb, jj = idx - kk * bb, k = k0 + kk;
+    sS[kk][jj] = (k < nz) ? s2p[(i64)(k - j1) * bb + jj] : 0.0;
+  }
+  __syncthreads();
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const int k = k0 + ty * 4 + a, r = r0 + tx * 4 + c;
+      acc[a][c] = (k < nz && r < j1) ? Q[tri(k) + r] : 0.0;
+    }
+  const bool guard = (r0 + 63 > j0);          // some columns of the tile start inside the panel
+  for (int jj = 0; jj < bb; jj++) {
+    double q[4], s[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) q[c] = sQ[jj][tx * 4 + c];
+#pragma unroll
+    for (int a = 0; a < 4; a++) s[a] = sS[ty * 4 + a][jj];
+    if (!guard) {
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[a][c] = acc[a][c] + q[c] * s[a];
+    } else {
+      const int jp = j0 + jj;
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+          if (r0 + tx * 4 + c <= jp) acc[a][c] = acc[a][c] + q[c] * s[a];
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const int k = k0 + ty * 4 + a, r = r0 + tx * 4 + c;
+      if (k < nz && r < j1) Q[tri(k) + r] = acc[a][c];
+    }
+}
+
+// Q of one huge column, in place in the store (which must be zero on entry)
+static void build_q_huge(double *Q, int nz, const int *Qj, const Csr &At, int panel) {
+  Context &c = ctx();
+  LocalGram lg;
+  Buf<int> cnt(nz + 1);
+  k_lg_count<<<(nz + 255) / 256, 256, 0, c.stream>>>(nz, Qj, At.ro.p, At.col.p, cnt.p);
+  c.launches++; post_launch("lg_count");
+  lg.ro.alloc(nz + 1);
+  const i64 gn = exclusive_scan(cnt.p, lg.ro.p, nz);
+  lg.col.alloc(gn); lg.a.alloc(gn);
+  k_lg_fill<<<(nz + 255) / 256, 256, 0, c.stream>>>(nz, Qj, At.ro.p, At.col.p, At.a.p, lg.ro.p, lg.col.p, lg.a.p);
+  c.launches++; post_launch("lg_fill");
+  dev_memset(Q, 0, sizeof(double) * (size_t)tri(nz));
+  Buf<double> s2p((i64)nz * panel);
+  static int coop_blocks = 0;
+  if (!coop_blocks) {
+    int nb = 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_q_panel, 256, 0));
+    coop_blocks = std::min(c.sm_count * std::max(nb, 1), 64);
+  }
+  const int *gro = lg.ro.p, *gcol = lg.col.p;
+  const double *ga = lg.a.p;
+  for (int j0 = 0; j0 < nz; j0 += panel) {
+    int j1 = std::min(nz, j0 + panel);
+    void *args[] = {(void *)&j0, (void *)&j1, (void *)&Q, (void *)&gro, (void *)&gcol, (void *)&ga};
+    CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)k_q_panel, dim3(coop_blocks), dim3(256), args, 0, c.stream));
+    c.launches++; post_launch("q_panel");
+    if (j1 >= nz) break;
+    const i64 total = (i64)(nz - j1) * (j1 - j0);
+    k_q_s2<<<(unsigned)std::min<i64>((total + 255) / 256, (i64)c.sm_count * 16), 256, 0, c.stream>>>(nz, j0, j1, Q, gro, gcol, ga, s2p.p);
+    c.launches++; post_launch("q_s2");
+    constexpr size_t trail_bytes = sizeof(double) * (QP_BMAX * (64 + 4) + 64 * (QP_BMAX + 1));
+    static bool trail_attr = false;
+    if (!trail_attr) { CUDA_CHECK(cudaFuncSetAttribute((const void *)k_q_trail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trail_bytes)); trail_attr = true; }
+    k_q_trail<<<dim3((j1 + 63) / 64, (nz - j1 + 63) / 64), 256, trail_bytes, c.stream>>>(nz, j0, j1, Q, s2p.p);
+    c.launches++; post_launch("q_trail");
+  }
+}
+
+// ---- apply for a huge column: y = Q^t x (rows of the triangle), w = Q y (columns) ----
+__global__ void __launch_bounds__(256) k_apply_huge_rhs(int nz, const int *Qj, int i, const int *bro, const int *bcol,
+                                                        const double *ba, const double *u, const double *lambda,
+                                                        double *x) {
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  if (k >= nz) return;
+  const int bb = bro[i], bn = bro[i + 1] - bb;
+  const double v = row_at(bcol + bb, ba + bb, bn, Qj[k]);
+  x[k] = v + u[i] * lambda[Qj[k]];
+}
+__global__ void __launch_bounds__(256) k_apply_huge_utt(int nz, const double *Q, const double *x, double *y) {
+  // one warp per row r: the lanes stage 32 products at a time, lane 0's order is the row's order
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= nz) return;
+  const double *u = Q + tri(r);
+  double v = 0;
+  for (int base = 0; base <= r; base += 32) {
+    const int j = base + lane;
+    const double p = (j <= r) ? u[j] * x[j] : 0.0;
+    const int m = min(32, r + 1 - base);
+    for (int l = 0; l < m; l++) v = v + __shfl_sync(0xffffffffu, p, l);
+  }
+  if (lane == 0) y[r] = v;
+}
+__global__ void __launch_bounds__(256) k_apply_huge_ut(int nz, const double *Q, const double *y, double *w) {
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  if (r >= nz) return;
+  double acc = 0;
+  for (int j = r; j < nz; j++) acc = acc + Q[tri(j) + r] * y[j];
+  w[r] = acc;
+}
+
+// ---- Q Q^t of a huge column: out[m][j] = sum_{k >= max(m,j)} q_k[m] q_k[j], k ascending ----
+// 64 x 64 tiles of the upper triangle (mirrored on write), 4 x 4 per thread, 32 rows of Q per stage
+__global__ void __launch_bounds__(256) k_form_qq_huge(int nz, const double *Q, double *out) {
+  __shared__ double sA[32][64 + 4], sB[32][64 + 4];
+  const int m0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  if (m0 > j0) return;                                 // lower tiles come from the mirror
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) acc[a][c] = 0.0;
+  for (int kb = j0; kb < nz; kb += 32) {              // every pair of the tile starts at k >= j >= j0
+    __syncthreads();
+    for (int idx = t; idx < 32 * 64; idx += 256) {
+      const int kk = idx / 64, c = idx - kk * 64, k = kb + kk;
+      sA[kk][c] = (k < nz && m0 + c <= k) ? Q[tri(k) + m0 + c] : 0.0;
+      sB[kk][c] = (k < nz && j0 + c <= k) ? Q[tri(k) + j0 + c] : 0.0;
+    }
+    __syncthreads();
+    const int kend = min(32, nz - kb);
+    const bool guard = (kb < j0 + 64);                // pairs (m, j) start at k = max(m, j) = j here (m <= j in upper tiles... or m > j on the diagonal tile)
+    for (int kk = 0; kk < kend; kk++) {
+      const int k = kb + kk;
+      double a4[4], b4[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) a4[a] = sA[kk][ty * 4 + a];
+#pragma unroll
+      for (int c = 0; c < 4; c++) b4[c] = sB[kk][tx * 4 + c];
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          if (guard) { const int m = m0 + ty * 4 + a, j = j0 + tx * 4 + c; if (k < (m > j ? m : j)) continue; }
+          acc[a][c] = acc[a][c] + a4[a] * b4[c];
+        }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const int m = m0 + ty * 4 + a, j = j0 + tx * 4 + c;
+      if (m < nz && j < nz && (m0 < j0 || m <= j)) { out[(i64)m * nz + j] = acc[a][c]; out[(i64)j * nz + m] = acc[a][c]; }
+    }
+}
+
+// which columns are huge, and the largest support among the others (one read-back)
+struct HugeRec { int col, nz, wb, pad; long long qoff; };
+__global__ void __launch_bounds__(256) k_find_huge(int n, int bignz, const int *wro, const i64 *qoff, HugeRec *rec, int cap, int *meta) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const int nz = wro[i + 1] - wro[i];
+  if (nz > bignz) { const int p = atomicAdd(&meta[0], 1); if (p < cap) { rec[p].col = i; rec[p].nz = nz; rec[p].wb = wro[i]; rec[p].qoff = qoff[i]; } }
+  else atomicMax(&meta[1], nz);
+}
+static void find_huge(QStore &qs, const Csr &Wt) {
+  const bool force = test_force('p');
+  qs.bignz = force ? 12 : 512;
+  qs.huge.clear();
+  qs.maxnz_small = qs.maxnz;
+  if (qs.maxnz <= qs.bignz || Wt.rn == 0) return;
+  const int cap = 8192;
+  Buf<HugeRec> rec(cap);
+  Buf<int> meta(2);
+  meta.zero();
+  Context &c = ctx();
+  k_find_huge<<<(Wt.rn + 255) / 256, 256, 0, c.stream>>>(Wt.rn, qs.bignz, Wt.ro.p, qs.qoff.p, rec.p, cap, meta.p);
+  c.launches++; post_launch("find_huge");
+  std::vector<int> hm = meta.download();
+  if (hm[0] > cap) throw Error(-12, "more than 8192 interpolation supports above " + std::to_string(qs.bignz) + " rows");
+  std::vector<HugeRec> hr((size_t)hm[0]);
+  if (hm[0]) d2h(hr.data(), rec.p, sizeof(HugeRec) * (size_t)hm[0]);
+  std::sort(hr.begin(), hr.end(), [](const HugeRec &a, const HugeRec &b) { return a.col < b.col; });
+  for (const HugeRec &r : hr) qs.huge.push_back(QStore::Huge{r.col, r.nz, r.wb, (i64)r.qoff});
+  qs.maxnz_small = hm[1];
+}
+
 static void set_smem(const void *fn, size_t bytes) {
   CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
 }
@@ -439,10 +770,12 @@ void build_q_store(QStore &qs, const Csr &Wt, const Csr &At) {
   const bool part = q_partition(qs, n, cs, off);
   const int c0 = part ? cs[(size_t)comm_rank()] : 0, c1 = part ? cs[(size_t)comm_rank() + 1] : n;
   const bool small = test_small_bins();     // test hook: the HBM and cluster builders from 9 rows on
+  find_huge(qs, Wt);
+  const int bignz = qs.bignz;
   parallel_for(c1 - c0, [=] DEV(i64 ii) {
     const i64 i = c0 + ii;
     const int nz = wro[i + 1] - wro[i];
-    if (nz == 0) return;
+    if (nz == 0 || nz > bignz) return;
     const int bin = nz <= 8 ? 0 : small ? (nz <= 12 ? 4 : 5) : nz <= 32 ? 1 : nz <= 64 ? 2 : nz <= 144 ? 3 : nz <= 256 ? 4 : 5;
     const int p = atomic_add(&cp[bin], 1);
     lp[(i64)bin * n + p] = (int)i;
@@ -466,7 +799,7 @@ void build_q_store(QStore &qs, const Csr &Wt, const Csr &At) {
   static cudaStream_t aux = nullptr;
   static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   Buf<double> scratch;
-  if (hc[5] && qs.maxnz > 12800) throw Error(-12, "interpolation support of " + std::to_string(qs.maxnz) + " rows exceeds the kernel limit (12800)");
+  if (hc[5] && qs.maxnz_small > 12800) throw Error(-12, "interpolation support of " + std::to_string(qs.maxnz_small) + " rows exceeds the kernel limit (12800)");
   if (hc[5]) {
     k_gram_fill_big<<<dim3(64, hc[5]), 256, 0, c.stream>>>(lp + 5 * (i64)n, wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
     c.launches++; post_launch("gram_fill_big");
@@ -477,20 +810,20 @@ void build_q_store(QStore &qs, const Csr &Wt, const Csr &At) {
       CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
       CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     }
-    scratch.alloc((i64)hc[5] * (2 * (i64)qs.maxnz + tri(qs.maxnz)));
-    const size_t sm = sizeof(double) * 2 * (size_t)qs.maxnz;
+    scratch.alloc((i64)hc[5] * (2 * (i64)qs.maxnz_small + tri(qs.maxnz_small)));
+    const size_t sm = sizeof(double) * 2 * (size_t)qs.maxnz_small;
     static size_t sm_set = 48 * 1024;
     if (sm > sm_set) { set_smem((const void *)k_build_q_cluster, sm); sm_set = sm; }
     CUDA_CHECK(cudaEventRecord(ev_fork, c.stream));
     CUDA_CHECK(cudaStreamWaitEvent(aux, ev_fork, 0));
-    k_build_q_cluster<<<hc[5] * 8, 256, sm, aux>>>(lp + 5 * (i64)n, hc[5], qs.maxnz, wro, qs.Q.p, qs.qoff.p, scratch.p);
+    k_build_q_cluster<<<hc[5] * 8, 256, sm, aux>>>(lp + 5 * (i64)n, hc[5], qs.maxnz_small, wro, qs.Q.p, qs.qoff.p, scratch.p);
     c.launches++; post_launch("build_q_cluster");
     CUDA_CHECK(cudaEventRecord(ev_join, aux));
   } else if (hc[5]) {
-    const size_t sm = sizeof(double) * 2 * (size_t)qs.maxnz;
+    const size_t sm = sizeof(double) * 2 * (size_t)qs.maxnz_small;
     static size_t sm_set = 48 * 1024;
     if (sm > sm_set) { set_smem((const void *)k_build_q_block<false>, sm); sm_set = sm; }
-    k_build_q_block<false><<<hc[5], 256, sm, c.stream>>>(lp + 5 * (i64)n, hc[5], qs.maxnz, wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
+    k_build_q_block<false><<<hc[5], 256, sm, c.stream>>>(lp + 5 * (i64)n, hc[5], qs.maxnz_small, wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
     c.launches++; post_launch("build_q_global_big");
   }
   for (int b = 0; b < 5; b++) {
@@ -515,6 +848,11 @@ void build_q_store(QStore &qs, const Csr &Wt, const Csr &At) {
     k_build_q_block<false><<<hc[4], 256, sm, c.stream>>>(lp + 4 * (i64)n, hc[4], 256, wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
     c.launches++; post_launch("build_q_global");
   }
+  // huge supports: one column at a time, the whole GPU on each (this rank's columns only)
+  for (const QStore::Huge &h : qs.huge) {
+    if (h.col < c0 || h.col >= c1) continue;
+    build_q_huge(qs.Q.p + h.qoff, h.nz, wcol + h.wb, At, test_force('p') ? 4 : QP_BMAX);
+  }
   if (big_cluster) CUDA_CHECK(cudaStreamWaitEvent(c.stream, ev_join, 0));   // join before anything reads Q
   if (part) comm_allgatherv(qs.Q.p, off.data(), "comm.q_blocks");
 }
@@ -524,14 +862,14 @@ template <int G>
 __global__ void __launch_bounds__(256) k_apply_q(int n, int nzcap, const int *wro, const int *wcol, double *wa,
                                                  const int *bro, const int *bcol, const double *ba,
                                                  const double *u, const double *lambda, const double *Qall,
-                                                 const i64 *qoff) {
+                                                 const i64 *qoff, int bignz) {
   extern __shared__ double sm[];
   auto tile = cg::tiled_partition<G>(cg::this_thread_block());
   const int slot = threadIdx.x / G, per = blockDim.x / G;
   const int i = blockIdx.x * per + slot;
   if (i >= n) return;
   const int b = wro[i], nz = wro[i + 1] - b;
-  if (nz == 0) return;
+  if (nz == 0 || nz > bignz) return;            // huge supports: k_apply_huge_*
   const int *Qj = wcol + b;
   const double *Q = Qall + qoff[i];
   double *sqv1 = sm + (size_t)slot * 2 * nzcap, *sqv2 = sqv1 + nzcap;
@@ -561,12 +899,19 @@ void apply_q(const QStore &qs, Csr &Wt, const Csr &Bt, const double *u, const do
   const int n = Wt.rn;
   if (n == 0) return;
   Context &c = ctx();
-  const int nzcap = qs.maxnz > 0 ? qs.maxnz : 1;
-  if (qs.maxnz <= 16) {
+  const int nzcap = qs.maxnz_small > 0 ? qs.maxnz_small : 1;
+  for (const QStore::Huge &h : qs.huge) {
+    Buf<double> xv(h.nz), yv(h.nz);
+    k_apply_huge_rhs<<<(h.nz + 255) / 256, 256, 0, c.stream>>>(h.nz, Wt.col.p + h.wb, h.col, Bt.ro.p, Bt.col.p, Bt.a.p, u, lambda, xv.p);
+    k_apply_huge_utt<<<(h.nz + 7) / 8, 256, 0, c.stream>>>(h.nz, qs.Q.p + h.qoff, xv.p, yv.p);
+    k_apply_huge_ut<<<(h.nz + 255) / 256, 256, 0, c.stream>>>(h.nz, qs.Q.p + h.qoff, yv.p, Wt.a.p + h.wb);
+    c.launches += 3; post_launch("apply_huge");
+  }
+  if (qs.maxnz_small <= 16) {
     const int per = 256 / 8;
     const size_t sm = sizeof(double) * (size_t)per * 2 * nzcap;
     k_apply_q<8><<<(n + per - 1) / per, 256, sm, c.stream>>>(n, nzcap, Wt.ro.p, Wt.col.p, Wt.a.p, Bt.ro.p, Bt.col.p,
-                                                             Bt.a.p, u, lambda, qs.Q.p, qs.qoff.p);
+                                                             Bt.a.p, u, lambda, qs.Q.p, qs.qoff.p, qs.bignz);
   } else {
     int threads = 256;
     size_t sm = sizeof(double) * (size_t)(threads / 32) * 2 * nzcap;
@@ -574,18 +919,18 @@ void apply_q(const QStore &qs, Csr &Wt, const Csr &Bt, const double *u, const do
     if (sm > 48 * 1024) set_smem((const void *)k_apply_q<32>, sm);
     const int per = threads / 32;
     k_apply_q<32><<<(n + per - 1) / per, threads, sm, c.stream>>>(n, nzcap, Wt.ro.p, Wt.col.p, Wt.a.p, Bt.ro.p,
-                                                                  Bt.col.p, Bt.a.p, u, lambda, qs.Q.p, qs.qoff.p);
+                                                                  Bt.col.p, Bt.a.p, u, lambda, qs.Q.p, qs.qoff.p, qs.bignz);
   }
   c.launches++; post_launch("apply_q");
 }
 
 // ---- QQ^t: one block per column (one warp for small ones), pairs (m<=j) over threads ----
 __global__ void __launch_bounds__(128) k_form_qq(int n, const int *wro, const double *Qall, const i64 *qoff,
-                                                 double *QQ, const i64 *qqoff) {
+                                                 double *QQ, const i64 *qqoff, int bignz) {
   const int i = blockIdx.x;
   if (i >= n) return;
   const int nz = wro[i + 1] - wro[i];
-  if (nz > 192) return;                       // done by k_form_qq_big
+  if (nz > 192 || nz > bignz) return;         // done by k_form_qq_big / k_form_qq_huge
   const double *Q = Qall + qoff[i];
   double *out = QQ + qqoff[i];
   for (int idx = threadIdx.x; idx < nz * nz; idx += blockDim.x) {
@@ -599,10 +944,11 @@ __global__ void __launch_bounds__(128) k_form_qq(int n, const int *wro, const do
 }
 // tiny columns: one thread group of 8 per column
 __global__ void __launch_bounds__(256) k_form_qq_small(int n, const int *wro, const double *Qall, const i64 *qoff,
-                                                       double *QQ, const i64 *qqoff) {
+                                                       double *QQ, const i64 *qqoff, int bignz) {
   const int i = blockIdx.x * 32 + threadIdx.x / 8;
   if (i >= n) return;
   const int nz = wro[i + 1] - wro[i];
+  if (nz > bignz) return;
   const double *Q = Qall + qoff[i];
   double *out = QQ + qqoff[i];
   for (int idx = threadIdx.x & 7; idx < nz * nz; idx += 8) {
@@ -637,24 +983,31 @@ void form_qq(QQStore &qq, const QStore &qs, const Csr &Wt) {
   const int n = Wt.rn;
   if (n == 0) return;
   Context &c = ctx();
-  if (qs.maxnz > QQ_BIG) {
+  for (const QStore::Huge &h : qs.huge) {
+    const i64 qqo = qq.qqoff.get(h.col);
+    const int nt = (h.nz + 63) / 64;
+    k_form_qq_huge<<<dim3(nt, nt), 256, 0, c.stream>>>(h.nz, qs.Q.p + h.qoff, qq.QQ.p + qqo);
+    c.launches++; post_launch("form_qq_huge");
+  }
+  const int bignz = qs.bignz;
+  if (qs.maxnz_small > QQ_BIG) {
     // the few columns with a very large support (the reference piles every F row without a
     // coupling into column 0, :2229) would otherwise be one block each and set the run time
     Buf<int> big(n), nbig(1);
     nbig.zero();
     const int *wro = Wt.ro.p;
     int *bp = big.p, *np_ = nbig.p;
-    parallel_for(n, [=] DEV(i64 i) { if (wro[i + 1] - wro[i] > QQ_BIG) bp[atomic_add(np_, 1)] = (int)i; });
+    parallel_for(n, [=] DEV(i64 i) { const int nz = wro[i + 1] - wro[i]; if (nz > QQ_BIG && nz <= bignz) bp[atomic_add(np_, 1)] = (int)i; });
     const int nb = nbig.get(0);
     if (nb) {
       k_form_qq_big<<<dim3(96, nb), 256, 0, c.stream>>>(big.p, Wt.ro.p, qs.Q.p, qs.qoff.p, qq.QQ.p, qq.qqoff.p);
       c.launches++; post_launch("form_qq_big");
     }
   }
-  if (qs.maxnz <= 12)
-    k_form_qq_small<<<(n + 31) / 32, 256, 0, c.stream>>>(n, Wt.ro.p, qs.Q.p, qs.qoff.p, qq.QQ.p, qq.qqoff.p);
+  if (qs.maxnz_small <= 12)
+    k_form_qq_small<<<(n + 31) / 32, 256, 0, c.stream>>>(n, Wt.ro.p, qs.Q.p, qs.qoff.p, qq.QQ.p, qq.qqoff.p, bignz);
   else
-    k_form_qq<<<n, 128, 0, c.stream>>>(n, Wt.ro.p, qs.Q.p, qs.qoff.p, qq.QQ.p, qq.qqoff.p);
+    k_form_qq<<<n, 128, 0, c.stream>>>(n, Wt.ro.p, qs.Q.p, qs.qoff.p, qq.QQ.p, qq.qqoff.p, bignz);
   c.launches++; post_launch("form_qq");
 }
 

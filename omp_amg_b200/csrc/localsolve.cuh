@@ -13,6 +13,12 @@ struct QStore {
   Buf<double> Q;
   i64 total = 0;
   int maxnz = 0;
+  // columns with a huge support (the column-0 pile of min_skel): handled one at a time by the
+  // blocked kernels that use the whole GPU; everything else is binned by support size
+  int bignz = 0x7fffffff;          // supports larger than this are "huge"
+  int maxnz_small = 0;             // largest support among the others
+  struct Huge { int col, nz, wb; i64 qoff; };
+  std::vector<Huge> huge;
 };
 
 // Q Q^t of every column, dense nz_i x nz_i blocks at QQ[qqoff[i]]

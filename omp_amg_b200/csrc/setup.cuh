@@ -32,12 +32,29 @@ struct StageTimes {    // host wall-clock with a stream sync at stage ends, seco
   double comm = 0;                      // device seconds inside them
 };
 
+// one V-cycle captured as a CUDA graph (solve.cu): the coarse levels are launch-bound, a replay
+// costs one launch instead of ~15 per level
+struct SolveGraph {
+  void *exec = nullptr;           // cudaGraphExec_t
+  const double *b = nullptr;
+  double *x = nullptr;
+  i64 kernels = 0;                // kernels inside the graph
+  int calls = 0;                  // plain (uncaptured) solves so far
+  SolveGraph() {}
+  SolveGraph(const SolveGraph &) = delete;
+  SolveGraph &operator=(const SolveGraph &) = delete;
+  SolveGraph(SolveGraph &&o) noexcept : exec(o.exec), b(o.b), x(o.x), kernels(o.kernels), calls(o.calls) { o.exec = nullptr; }
+  ~SolveGraph();
+};
+
 struct Hierarchy {
   std::vector<Level> lv;
   int nullspace = 0;
   int n0 = 0;
   StageTimes t;
   i64 launches = 0, syncs = 0;
+  mutable Buf<double> mean_scratch;     // device scalar of the mean projection
+  mutable SolveGraph graph;
 };
 
 // stages (each cites amg_setup.c)
@@ -50,7 +67,9 @@ void setup(i64 nnz, const int *dAi, const int *dAj, const double *dAv, Hierarchy
 
 // V-cycle (amg.c:114 amg_exec + amg.c:171 crs_solve), device vectors of length n0
 void vcycle_solve(const Hierarchy &H, double *x, const double *b);
+// the same through a CUDA graph captured on the second call with the same vectors (AMGB_SOLVE_GRAPH=0: never)
+void vcycle_solve_graph(const Hierarchy &H, double *x, const double *b);
 // x -= mean(x) with the mean formed on the device (no host round trip)
-void project_mean(double *x, i64 n);
+void project_mean(double *x, i64 n, double *scratch = nullptr);
 
 }  // namespace amgb

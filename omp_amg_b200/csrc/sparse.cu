@@ -26,9 +26,10 @@ void trace_csr(const char *tag, const Csr &A) {
 template <int G>
 __global__ void __launch_bounds__(256) k_spmv_tile(int rn, const int *ro, const int *col, const double *vals,
                                                    const double *x, double *z, double alpha, const double *y,
-                                                   double beta, bool plain, const double *post) {
+                                                   double beta, bool plain, const double *post, int longrow) {
   const int i = blockIdx.x * (256 / G) + threadIdx.x / G;
   if (i >= rn) return;
+  if (ro[i + 1] - ro[i] > longrow) return;          // k_spmv_chain
   const int lane = threadIdx.x % G;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
   const int end = ro[i + 1];
@@ -57,11 +58,12 @@ __global__ void __launch_bounds__(256) k_spmv_tile(int rn, const int *ro, const 
 // then adds the 32 values in entry order.
 __global__ void __launch_bounds__(256) k_spmv_row32(int rn, const int *ro, const int *col, const double *vals,
                                                     const double *x, double *z, double alpha, const double *y,
-                                                    double beta, bool plain, const double *post) {
+                                                    double beta, bool plain, const double *post, int longrow) {
   __shared__ __align__(16) double buf[8][2][32];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.x * 8 + w;
   if (i >= rn) return;
+  if (ro[i + 1] - ro[i] > longrow) return;          // k_spmv_chain
   const int end = ro[i + 1];
   double t = 0;
   int par = 0;
@@ -89,44 +91,55 @@ __global__ void __launch_bounds__(256) k_spmv_row32(int rn, const int *ro, const
     z[i] = r;
   }
 }
-// Long rows, second generation: G = 16 lanes per row (two rows per warp, so an add instruction of
-// the ordered chain serves two rows), products parked in a double-buffered slice of shared memory
-// and read back as broadcast LDS.128, and the loads software-pipelined three deep: while batch b
-// is added, x[col] of batch b+1 and (col, val) of batch b+2 are in flight, so the chain of
-// dependent adds never waits for a gather.
-template <int G>
+// Long rows, second generation: G lanes per row (32/G rows per warp, so an add instruction of the
+// ordered chain serves several rows), U entries per lane and stage.  The products of a stage
+// (G*U of them) are parked in a double-buffered slice of shared memory and read back as
+// broadcast LDS.128; the loads are software-pipelined three stages deep: while stage s is added,
+// x[col] of stage s+1 and (col, val) of stage s+2 are in flight, so the chain of dependent adds
+// never waits for a gather.  On the coarse levels (4000 rows of 3600 entries) the run time is the
+// chain of the longest row; everything else hides behind it.
+template <int G, int U>
 __global__ void __launch_bounds__(256) k_spmv_pipe(int rn, const int *ro, const int *col, const double *vals,
                                                    const double *x, double *z, double alpha, const double *y,
-                                                   double beta, bool plain, const double *post) {
-  __shared__ __align__(16) double buf[256 / G][2][G];
+                                                   double beta, bool plain, const double *post, int longrow) {
+  constexpr int S = G * U;
+  __shared__ __align__(16) double buf[256 / G][2][S];
   const int grp = threadIdx.x / G, lane = threadIdx.x % G;
   const int i = blockIdx.x * (256 / G) + grp;
   if (i >= rn) return;
+  if (ro[i + 1] - ro[i] > longrow) return;          // k_spmv_chain
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
   const int beg = ro[i], end = ro[i + 1];
-  // stage 2: (col, val) of the batch after next; stage 1: x of the next batch; stage 0: the product
-  int c1 = 0, c2 = 0;
-  double v0 = 0.0, x0 = 0.0, v1 = 0.0, v2 = 0.0;
-  { const int j = beg + lane; if (j < end) { c1 = col[j]; v1 = vals[j]; } }
-  { const int j = beg + G + lane; if (j < end) { c2 = col[j]; v2 = vals[j]; } }
-  if (beg + lane < end) x0 = x[c1];
-  v0 = v1;
+  int c1[U], c2[U];
+  double v0[U], x0[U], v1[U], v2[U];
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const int j1 = beg + u * G + lane, j2 = j1 + S;
+    c1[u] = 0; v1[u] = 0.0; c2[u] = 0; v2[u] = 0.0;
+    if (j1 < end) { c1[u] = col[j1]; v1[u] = vals[j1]; }
+    if (j2 < end) { c2[u] = col[j2]; v2[u] = vals[j2]; }
+  }
+#pragma unroll
+  for (int u = 0; u < U; u++) { x0[u] = (beg + u * G + lane < end) ? x[c1[u]] : 0.0; v0[u] = v1[u]; }
   double t = 0;
   int par = 0;
-  for (int base = beg; base < end; base += G, par ^= 1) {
-    const double p = (base + lane < end) ? v0 * x0 : 0.0;
-    // advance the pipeline: gather x for the next batch (its columns are here), fetch the batch after
-    double xn = 0.0;
-    if (base + G + lane < end) xn = x[c2];
-    const double vn = v2;
-    { const int j = base + 2 * G + lane; if (j < end) { c2 = col[j]; v2 = vals[j]; } }
+  for (int base = beg; base < end; base += S, par ^= 1) {
     double *b = buf[grp][par];
-    b[lane] = p;
+#pragma unroll
+    for (int u = 0; u < U; u++) b[u * G + lane] = (base + u * G + lane < end) ? v0[u] * x0[u] : 0.0;
+    // advance the pipeline: gather x for the next stage (its columns are here), fetch the stage after
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      x0[u] = (base + S + u * G + lane < end) ? x[c2[u]] : 0.0;
+      v0[u] = v2[u];
+      const int j = base + 2 * S + u * G + lane;
+      if (j < end) { c2[u] = col[j]; v2[u] = vals[j]; }
+    }
     __syncwarp(gmask);
     const int m = end - base;
-    if (m >= G) {
+    if (m >= S) {
 #pragma unroll
-      for (int l = 0; l < G; l += 2) {
+      for (int l = 0; l < S; l += 2) {
         const double2 q = *reinterpret_cast<const double2 *>(b + l);
         t = t + q.x;
         t = t + q.y;
@@ -134,13 +147,68 @@ __global__ void __launch_bounds__(256) k_spmv_pipe(int rn, const int *ro, const 
     } else {
       for (int l = 0; l < m; l++) t = t + b[l];
     }
-    v0 = vn; x0 = xn;
   }
   if (lane == 0) {
     double r = plain ? beta * t : alpha * y[i] + beta * t;
     if (post) r = r * post[i];
     z[i] = r;
   }
+}
+// Very long rows: one block per row.  Warps 1..7 form the products of the next chunk of CH entries
+// (coalesced loads, gathers in flight from 224 threads) while thread 0 adds the current chunk from
+// shared memory in entry order, eight values ahead in registers: the run time is the chain of
+// dependent additions itself (about 8 cycles per entry), not the memory latency per batch that a
+// group-per-row kernel pays when only a handful of such rows exist.
+#define SPMV_CH 2048
+__global__ void __launch_bounds__(256) k_spmv_chain(const int *rows, const int *nrows, const int *ro, const int *col,
+                                                    const double *vals, const double *x, double *z, double alpha,
+                                                    const double *y, double beta, bool plain, const double *post) {
+  __shared__ double buf[2][SPMV_CH];
+  const int t = threadIdx.x;
+  const int n = *nrows;
+  for (int q = blockIdx.x; q < n; q += gridDim.x) {
+    const int i = rows[q];
+    const int beg = ro[i], end = ro[i + 1];
+    const int nch = (end - beg + SPMV_CH - 1) / SPMV_CH;
+    __syncthreads();
+    for (int j = beg + t; j < end && j < beg + SPMV_CH; j += 256) buf[0][j - beg] = vals[j] * x[col[j]];
+    double r = 0;
+    for (int c = 0; c < nch; c++) {
+      __syncthreads();
+      const int cur = c & 1;
+      if (t >= 32) {
+        const int b0 = beg + (c + 1) * SPMV_CH;
+        for (int j = b0 + (t - 32); j < end && j < b0 + SPMV_CH; j += 224) buf[cur ^ 1][j - b0] = vals[j] * x[col[j]];
+      } else if (t == 0) {
+        const int b0 = beg + c * SPMV_CH;
+        const int len = min(SPMV_CH, end - b0);
+        const double *p = buf[cur];
+        int j = 0;
+        if (len >= 8) {
+          double a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3], a4 = p[4], a5 = p[5], a6 = p[6], a7 = p[7];
+          for (; j + 16 <= len; j += 8) {
+            const double b0v = p[j + 8], b1 = p[j + 9], b2 = p[j + 10], b3 = p[j + 11], b4 = p[j + 12], b5 = p[j + 13],
+                         b6 = p[j + 14], b7 = p[j + 15];
+            r = r + a0; r = r + a1; r = r + a2; r = r + a3; r = r + a4; r = r + a5; r = r + a6; r = r + a7;
+            a0 = b0v; a1 = b1; a2 = b2; a3 = b3; a4 = b4; a5 = b5; a6 = b6; a7 = b7;
+          }
+          r = r + a0; r = r + a1; r = r + a2; r = r + a3; r = r + a4; r = r + a5; r = r + a6; r = r + a7;
+          j += 8;
+        }
+        for (; j < len; j++) r = r + p[j];
+      }
+    }
+    if (t == 0) {
+      double v = plain ? beta * r : alpha * y[i] + beta * r;
+      if (post) v = v * post[i];
+      z[i] = v;
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_find_long_rows(int rn, const int *ro, int longrow, int cap, int *rows, int *count) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= rn) return;
+  if (ro[i + 1] - ro[i] > longrow) { const int p = atomicAdd(count, 1); if (p < cap) rows[p] = i; }
 }
 #endif
 
@@ -174,28 +242,68 @@ static void spmv_vals_run(double *z, double alpha, const double *y, double beta,
   StageTimer st_("prim.spmv");
   const int *ro = M.ro.p, *col = M.col.p;
   const bool plain = (alpha == 0. || y == nullptr);
+  int longrow = 0x7fffffff;
 #ifndef AMGB_EMU
-  if (M.rn > 0 && (double)M.nnz / (double)M.rn > 8.0) {
-    Context &c = ctx();
-    static int spmv_kind = -1;      // AMGB_SPMV=row32: the first-generation long-row kernel (A/B measurements)
-    if (spmv_kind < 0) { const char *e = getenv("AMGB_SPMV"); spmv_kind = (e && !strcmp(e, "row32")) ? 0 : 1; }
-    if ((double)M.nnz / (double)M.rn <= 64.0 && !test_small_bins())
-      k_spmv_tile<8><<<(M.rn + 31) / 32, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post);
-    else if (spmv_kind == 0)
-      k_spmv_row32<<<(M.rn + 7) / 8, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post);
-    else
-      k_spmv_pipe<16><<<(M.rn + 15) / 16, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post);
-    c.launches++; post_launch("spmv_tile");
-    return;
+  Context &c = ctx();
+  // rows of more than LR entries go to the block-per-row chain kernel; which rows those are is
+  // found once per matrix (one read-back), so matrices without any pay nothing afterwards
+  const int LR = test_small_bins() ? 40 : 1536;
+  static int chain_on = -1;
+  if (chain_on < 0) { const char *e = getenv("AMGB_SPMV_CHAIN"); chain_on = (e && *e == '0') ? 0 : 1; }
+  if (M.n_long < 0) {
+    M.n_long = 0;
+    if (chain_on && M.rn > 0 && M.nnz > LR) {
+      const int cap = M.rn < 16384 ? M.rn : 16384;
+      M.long_rows.alloc((i64)cap + 1);
+      dev_memset(M.long_rows.p + cap, 0, sizeof(int));
+      k_find_long_rows<<<(M.rn + 255) / 256, 256, 0, c.stream>>>(M.rn, ro, LR, cap, M.long_rows.p, M.long_rows.p + cap);
+      c.launches++; post_launch("find_long_rows");
+      int cnt = 0;
+      d2h(&cnt, M.long_rows.p + cap, sizeof(int));
+      // more long rows than the list holds: the matrix is long rows throughout, which the
+      // group-per-row kernels stream at full rate anyway
+      if (cnt > 0 && cnt <= cap) M.n_long = cnt;
+      else M.long_rows.release();
+    }
   }
+  if (M.n_long > 0) longrow = LR;
+  static double t1 = -1;       // rows up to this average length: one thread per row (AMGB_SPMV_T1)
+  if (t1 < 0) { const char *e = getenv("AMGB_SPMV_T1"); t1 = e ? atof(e) : 24.0; }
+  bool done = false;
+  if (M.rn > 0 && (double)M.nnz / (double)M.rn > t1) {
+    // AMGB_SPMV=row32 | pipe16 | auto (default: 16 lanes per row, 8 lanes x 4 entries for a few
+    // thousand rows of a few thousand entries; measured per matrix in profiles/r2_spmv_variants_poisson7_128.txt)
+    static int spmv_kind = -1;
+    if (spmv_kind < 0) { const char *e = getenv("AMGB_SPMV"); spmv_kind = (e && !strcmp(e, "row32")) ? 0 : (e && !strcmp(e, "pipe16")) ? 1 : 2; }
+    if ((double)M.nnz / (double)M.rn <= 64.0 && !test_small_bins())
+      k_spmv_tile<8><<<(M.rn + 31) / 32, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow);
+    else if (spmv_kind == 0)
+      k_spmv_row32<<<(M.rn + 7) / 8, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow);
+    else if (spmv_kind == 1 || (spmv_kind == 2 && !((double)M.nnz / (double)M.rn >= 2048.0 && M.rn >= 2048) && !test_small_bins()))
+      k_spmv_pipe<16, 1><<<(M.rn + 15) / 16, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow);
+    else
+      k_spmv_pipe<8, 4><<<(M.rn + 31) / 32, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow);
+    c.launches++; post_launch("spmv_tile");
+    done = true;
+  }
+  if (!done)
 #endif
   parallel_for(M.rn, [=] DEV(i64 i) {
+    if (ro[i + 1] - ro[i] > longrow) return;
     double t = 0;
     for (int j = ro[i]; j < ro[i + 1]; j++) t = t + vals[j] * x[col[j]];
     double r = plain ? beta * t : alpha * y[i] + beta * t;
     if (post) r = r * post[i];
     z[i] = r;
   });
+#ifndef AMGB_EMU
+  if (M.n_long > 0) {
+    const int cap = M.rn < 16384 ? M.rn : 16384;
+    const int grid = M.n_long < c.sm_count * 6 ? M.n_long : c.sm_count * 6;
+    k_spmv_chain<<<grid, 256, 0, c.stream>>>(M.long_rows.p, M.long_rows.p + cap, ro, col, vals, x, z, alpha, y, beta, plain, post);
+    c.launches++; post_launch("spmv_chain");
+  }
+#endif
 }
 void spmv(double *z, double alpha, const double *y, double beta, const Csr &M, const double *x) {
   spmv_vals(z, alpha, y, beta, M, M.a.p, x);
@@ -227,6 +335,7 @@ __global__ void __launch_bounds__(256) k_transpose_rank(int nrows, const int *tr
   const int r0 = threadIdx.x % G;
   const int b = tro[c], L = tro[c + 1] - b;
   if (L > TR_LONG && L <= 4096) { if (r0 == 0) longlist[atomicAdd(nlong, 1)] = c; return; }
+  if (L > 4096 && L <= 16384) { if (r0 == 0) longlist[nrows - 1 - atomicAdd(nlong + 1, 1)] = c; return; }   // from the end of the list
   for (int e = r0; e < L; e += G) {
     const int key = kin[b + e];
     int rank = 0;
@@ -236,9 +345,10 @@ __global__ void __launch_bounds__(256) k_transpose_rank(int nrows, const int *tr
   }
 }
 // long rows: one block, (key, source) pairs sorted by a bitonic network in shared memory
-__global__ void __launch_bounds__(128) k_transpose_bitonic(const int *list, int nlist, const int *tro, const int *kin,
-                                                           const int *sin, int *kout, int *sout, const double *a,
-                                                           double *ta) {
+template <int T>
+__global__ void __launch_bounds__(T) k_transpose_bitonic(const int *list, int nlist, const int *tro, const int *kin,
+                                                         const int *sin, int *kout, int *sout, const double *a,
+                                                         double *ta) {
   extern __shared__ int tsm[];
   if ((int)blockIdx.x >= nlist) return;
   const int c = list[blockIdx.x];
@@ -296,7 +406,7 @@ Csr transpose(const Csr &A, Buf<int> *tpos_out) {
   });
 #else
   if (A.cn > 0 && A.nnz > 0) {
-    Buf<int> kin = T.col.clone(), sin = src.clone(), longlist(A.cn), nlong(1);
+    Buf<int> kin = T.col.clone(), sin = src.clone(), longlist(A.cn), nlong(2);
     nlong.zero();
     Context &c = ctx();
     if ((double)A.nnz / (double)A.cn <= 12.0)
@@ -304,10 +414,17 @@ Csr transpose(const Csr &A, Buf<int> *tpos_out) {
     else
       k_transpose_rank<32><<<(A.cn + 7) / 8, 256, 0, c.stream>>>(A.cn, tro, kin.p, sin.p, tcol, srcp, a, ta, longlist.p, nlong.p);
     c.launches++; post_launch("transpose_rank");
-    const int nl = nlong.get(0);
+    const std::vector<int> hl = nlong.download();
+    const int nl = hl[0], nl2 = hl[1];          // rows of 97..4096 and of 4097..16384 entries
     if (nl) {
-      k_transpose_bitonic<<<nl, 128, 4096 * 8, c.stream>>>(longlist.p, nl, tro, kin.p, sin.p, tcol, srcp, a, ta);
+      k_transpose_bitonic<128><<<nl, 128, 4096 * 8, c.stream>>>(longlist.p, nl, tro, kin.p, sin.p, tcol, srcp, a, ta);
       c.launches++; post_launch("transpose_bitonic");
+    }
+    if (nl2) {    // the column-0 pile of min_skel transposed: one row of thousands of entries
+      static bool attr = false;
+      if (!attr) { CUDA_CHECK(cudaFuncSetAttribute((const void *)k_transpose_bitonic<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8)); attr = true; }
+      k_transpose_bitonic<512><<<nl2, 512, 16384 * 8, c.stream>>>(longlist.p + (A.cn - nl2), nl2, tro, kin.p, sin.p, tcol, srcp, a, ta);
+      c.launches++; post_launch("transpose_bitonic_big");
     }
   }
 #endif
@@ -645,6 +762,9 @@ Csr spgemm_partitioned(const Csr &A, const Csr &B, Csr (*local)(const Csr &, con
       d2d(Al.col.p, A.col.p + base, sizeof(int) * (size_t)Al.nnz);
       d2d(Al.a.p, A.a.p + base, sizeof(double) * (size_t)Al.nnz);
     }
+    // the block inherits an identity derived from A's, so that the entry-tier hints of the local
+    // product (spgemm.cu) carry over from one product with this left operand to the next
+    Al.uid = A.uid ? A.uid * 1000003ULL + (unsigned long long)me + 1ULL : 0ULL;
     Xl = local(Al, B);
   }
   // row lengths of all blocks, then the global offsets

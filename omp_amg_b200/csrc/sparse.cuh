@@ -17,6 +17,11 @@ struct Csr {
   // constructed or cloned matrix, carried along by moves
   unsigned long long uid = 0;
   static unsigned long long next_uid() { static unsigned long long g = 0; return ++g; }
+  // rows too long for the group-per-row SpMV kernels (a few thousand entries: the column-0 pile
+  // of min_skel transposed, the rows of the coarsest levels), found at the first SpMV with this
+  // matrix and handled by a block each (sparse.cu: k_spmv_chain); -1 = not looked for yet
+  mutable int n_long = -1;
+  mutable Buf<int> long_rows;
   Csr() {}
   Csr(int rn_, int cn_, i64 nnz_) : rn(rn_), cn(cn_), nnz(nnz_), ro(rn_ + 1), col(nnz_), a(nnz_), uid(next_uid()) {}
   Csr(Csr &&) = default;
