@@ -466,51 +466,77 @@ __global__ void __launch_bounds__(256) k_lg_fill(int nz, const int *Qj, const in
 // rows [j0, j1) of one column; cooperative launch.  Inside the panel the rows are kept UNSCALED
 // with their factor -1/sqrt(alpha) aside (every block holds the factors in shared memory): a read
 // multiplies on the fly, which is the same rounded product the reference stores.
+// ordered sparse dot by one warp: the lanes fetch their terms side by side (the loads of a sparse
+// dot are independent of the running sum; issued one after the other by a single thread each would
+// pay its own L2 round trip), lane 0's order of additions is the entry order
+__device__ __forceinline__ double warp_sparse_dot(double v0, bool sub, int e0, int e1, const int *gcol, const double *ga,
+                                                  const double *q, double f, int diag, int mlimit) {
+  const int lane = threadIdx.x & 31;
+  double v = v0;
+  for (int base = e0; base < e1; base += 32) {
+    const int e = base + lane;
+    double p = 0.0;
+    bool ok = false;
+    if (e < e1) {
+      const int m = gcol[e];
+      if (m <= mlimit) { ok = true; const double qq = (m == diag) ? -f : __ldcg(q + m) * f; p = qq * ga[e]; }
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, ok);
+    const int cnt = __popc(b);                 // the valid entries are a prefix (columns ascending)
+    for (int l = 0; l < cnt; l++) { const double pl = __shfl_sync(0xffffffffu, p, l); v = sub ? v - pl : v + pl; }
+    if (cnt < 32) break;
+  }
+  return v;
+}
+
 __global__ void __launch_bounds__(256) k_q_panel(int j0, int j1, double *Q, const int *gro, const int *gcol,
                                                  const double *ga) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double sfac[QP_BMAX], ss2[QP_BMAX];
-  const int t = threadIdx.x, tid = blockIdx.x * 256 + t, T = gridDim.x * 256;
+  const int t = threadIdx.x, tid = blockIdx.x * 256 + t, T = gridDim.x * 256, w = t >> 5;
   for (int j = j0; j <= j1; j++) {
-    // factor of the row finished in the previous step (its elements are complete after the barrier)
+    // factor of the row finished in the previous step (its elements are complete after the barrier):
+    // alpha = G[k][k] - sum_{m<k} G[k][m] y[m]  (the rows of the panel are kept unscaled: f = 1)
     if (j > j0) {
-      if (t == 0) {
+      if (w == 0) {
         const int k = j - 1;
-        const double *qk = Q + tri(k);
+        const int e0 = gro[k], e1 = gro[k + 1];
         double alpha = 0.0;
-        const int e1 = gro[k + 1];
-        if (e1 > gro[k] && gcol[e1 - 1] == k) alpha = ga[e1 - 1];
-        for (int e = gro[k]; e < e1; e++) { const int m = gcol[e]; if (m >= k) break; alpha = alpha - ga[e] * __ldcg(qk + m); }
-        sfac[k - j0] = -1.0 / sqrt(alpha);
+        if (e1 > e0 && gcol[e1 - 1] == k) alpha = ga[e1 - 1];
+        alpha = warp_sparse_dot(alpha, true, e0, e1, gcol, ga, Q + tri(k), 1.0, -1, k - 1);
+        if (t == 0) sfac[k - j0] = -1.0 / sqrt(alpha);
       }
       __syncthreads();
     }
     if (j == j1) break;
     const int np = j - j0;
     // S2[j][jp] for the finished rows jp of this panel (every block forms all of them: no exchange)
-    if (t < np) {
-      const int jp = j0 + t;
-      const double *qp = Q + tri(jp);
-      const double f = sfac[t];
-      double v = 0.0;
-      for (int e = gro[j]; e < gro[j + 1]; e++) {
-        const int m = gcol[e];
-        if (m > jp) break;
-        const double q = (m == jp) ? -f : __ldcg(qp + m) * f;
-        v = v + q * ga[e];
-      }
-      ss2[t] = v;
+    for (int jj = w; jj < np; jj += 8) {
+      const int jp = j0 + jj;
+      const double v = warp_sparse_dot(0.0, false, gro[j], gro[j + 1], gcol, ga, Q + tri(jp), sfac[jj], jp, jp);
+      if ((t & 31) == 0) ss2[jj] = v;
     }
     __syncthreads();
-    // pending updates of this panel onto row j (earlier panels were applied by their trailing pass)
+    // pending updates of this panel onto row j (earlier panels were applied by their trailing pass);
+    // the eight loads of a batch are issued before the first of them is used
     double *qj = Q + tri(j);
     for (int r = tid; r < j; r += T) {
       double y = qj[r];
-      for (int jj = r > j0 ? r - j0 : 0; jj < np; jj++) {
-        const int jp = j0 + jj;
-        const double f = sfac[jj];
-        const double q = (r == jp) ? -f : __ldcg(Q + tri(jp) + r) * f;
-        y = y + q * ss2[jj];
+      for (int jj = r > j0 ? r - j0 : 0; jj < np; jj += 8) {
+        double q[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int jx = jj + u < np ? jj + u : np - 1, jp = j0 + jx;
+          q[u] = (r == jp) ? 0.0 : __ldcg(Q + tri(jp) + r);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          if (jj + u < np) {
+            const double f = sfac[jj + u];
+            const double qq = (r == j0 + jj + u) ? -f : q[u] * f;
+            y = y + qq * ss2[jj + u];
+          }
+        }
       }
       qj[r] = y;
     }

@@ -260,9 +260,11 @@ static void spmv_vals_run(double *z, double alpha, const double *y, double beta,
       c.launches++; post_launch("find_long_rows");
       int cnt = 0;
       d2h(&cnt, M.long_rows.p + cap, sizeof(int));
-      // more long rows than the list holds: the matrix is long rows throughout, which the
-      // group-per-row kernels stream at full rate anyway
-      if (cnt > 0 && cnt <= cap) M.n_long = cnt;
+      // many long rows: the matrix is long rows throughout, which the group-per-row kernels
+      // stream at full rate anyway (a block per row pays off when a handful of rows set the time)
+      static int chain_max = -1;
+      if (chain_max < 0) { const char *e = getenv("AMGB_SPMV_CHAIN_MAX"); chain_max = e ? atoi(e) : 1024; }
+      if (cnt > 0 && cnt <= cap && cnt <= chain_max) M.n_long = cnt;
       else M.long_rows.release();
     }
   }
@@ -274,11 +276,13 @@ static void spmv_vals_run(double *z, double alpha, const double *y, double beta,
     // AMGB_SPMV=row32 | pipe16 | auto (default: 16 lanes per row, 8 lanes x 4 entries for a few
     // thousand rows of a few thousand entries; measured per matrix in profiles/r2_spmv_variants_poisson7_128.txt)
     static int spmv_kind = -1;
-    if (spmv_kind < 0) { const char *e = getenv("AMGB_SPMV"); spmv_kind = (e && !strcmp(e, "row32")) ? 0 : (e && !strcmp(e, "pipe16")) ? 1 : 2; }
+    if (spmv_kind < 0) { const char *e = getenv("AMGB_SPMV"); spmv_kind = (e && !strcmp(e, "row32")) ? 0 : (e && !strcmp(e, "pipe16")) ? 1 : (e && !strcmp(e, "pipe16x2")) ? 3 : 2; }
     if ((double)M.nnz / (double)M.rn <= 64.0 && !test_small_bins())
       k_spmv_tile<8><<<(M.rn + 31) / 32, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow);
     else if (spmv_kind == 0)
       k_spmv_row32<<<(M.rn + 7) / 8, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow);
+    else if (spmv_kind == 3 && !((double)M.nnz / (double)M.rn >= 2048.0 && M.rn >= 2048))
+      k_spmv_pipe<16, 2><<<(M.rn + 15) / 16, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow);
     else if (spmv_kind == 1 || (spmv_kind == 2 && !((double)M.nnz / (double)M.rn >= 2048.0 && M.rn >= 2048) && !test_small_bins()))
       k_spmv_pipe<16, 1><<<(M.rn + 15) / 16, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow);
     else
