@@ -428,6 +428,7 @@ int amgb_debug_spgemm(int32_t arn, int32_t acn, const int32_t *aro, const int32_
   if (annz) { A.col.upload(acol, annz); A.a.upload(aa, annz); }
   if (bnnz) { B.col.upload(bcol, bnnz); B.a.upload(ba, bnnz); }
   spgemm_cache_reset();
+  spgemm_stats_reset();                 // the timing events of earlier calls (only setup() reads them)
   spgemm_debug_collect(true);
   Csr X = spgemm(A, B);
   spgemm_debug_collect(false);

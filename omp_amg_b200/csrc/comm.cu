@@ -141,8 +141,13 @@ void comm_allgatherv(void *buf, const i64 *off, const char *what) {
   g_comm.bytes += (off[P] - off[0]) - (off[g_comm.rank + 1] - off[g_comm.rank]);
 #ifndef AMGB_EMU
   Context &c = ctx();
-  cudaEvent_t e0, e1;
-  CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+  // the timing events belong to the statistics once recorded; on an error path they are destroyed
+  struct Pair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~Pair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+  } ev;
+  CUDA_CHECK(cudaEventCreate(&ev.a)); CUDA_CHECK(cudaEventCreate(&ev.b));
+  cudaEvent_t e0 = ev.a, e1 = ev.b;
   CUDA_CHECK(cudaEventRecord(e0, c.stream));
   nccl_check(g_nccl.GroupStart(), "ncclGroupStart");
   for (int r = 0; r < P; r++) {
@@ -154,6 +159,7 @@ void comm_allgatherv(void *buf, const i64 *off, const char *what) {
   nccl_check(g_nccl.GroupEnd(), "ncclGroupEnd");
   CUDA_CHECK(cudaEventRecord(e1, c.stream));
   g_comm.ev.emplace_back(e0, e1);
+  ev.a = ev.b = nullptr;
 #else
   std::vector<long long> o(off, off + P + 1);
   if (g_comm.host_fn(buf, o.data(), P, g_comm.host_user) != 0) throw Error(-113, "host transport failed");

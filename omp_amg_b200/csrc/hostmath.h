@@ -1,6 +1,12 @@
 // hostmath.h -- the scalar host-side pieces of the setup: the k x k arrowhead eigen-solver
 // that Lanczos calls every iteration (k <= 299), the Chebyshev iteration count, and the
 // random stream of the Lanczos start vector.  None of this touches matrix-sized data.
+//
+// PLAINLY: add3, ratroot, secular_root and tdeig below RESTATE sum_3, rat_root, sec_root and tdeig
+// of the reference (amg_setup.c:2613-2726) operation for operation.  The hierarchy must be
+// bit-identical to the reference's, and rho/m of every level come out of this iteration, so the
+// order of every floating-point operation in it is fixed by the reference; only the identifiers
+// differ.  It is 70 lines of scalar host code, k <= 299.
 #pragma once
 #include <cfloat>
 #include <cmath>

@@ -255,7 +255,11 @@ __device__ __forceinline__ void build_q_coop(const Group &g, int nz, double *Q, 
       const double *u = Q + tri(r);
       double v = 0;
       if (PIPE) v = chain_dot<8, false>(0.0, u, sqv1, r + 1);
-      else for (int j = 0; j <= r; j++) v = v + u[j] * sqv1[j];
+      else {
+        // the Gram row is sparse (a few dozen of its k entries): a product with an exact zero adds a
+        // signed zero, which changes no partial sum, so only the non-zeros enter the dependent chain
+        for (int j = 0; j <= r; j++) { const double s = sqv1[j]; if (s != 0.0) v = v + u[j] * s; }
+      }
       sqv2[r] = v;
     }
     g.sync();
@@ -268,7 +272,7 @@ __device__ __forceinline__ void build_q_coop(const Group &g, int nz, double *Q, 
     g.sync();
     double alpha = sqv1[k];                           // every thread forms the same recurrence
     if (PIPE) alpha = chain_dot<8, true>(alpha, qk, sqv1, k);
-    else for (int m = 0; m < k; m++) alpha = alpha - sqv1[m] * qk[m];
+    else for (int m = 0; m < k; m++) { const double s = sqv1[m]; if (s != 0.0) alpha = alpha - s * qk[m]; }
     alpha = -1.0 / sqrt(alpha);
     g.sync();
     for (int m = r0; m < k; m += G) qk[m] = qk[m] * alpha;

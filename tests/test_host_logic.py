@@ -369,3 +369,22 @@ def test_spgemm_primitive_against_exact_order_reference(emu):
     assert got[3] == want[3] and same_csr_bits(got, want)
     dropped = sum(int(B[0][k + 1] - B[0][k]) for k in A[1]) - len(want[1])
     assert dropped > 0 and len(want[1]) > 100000
+
+
+def test_bench_reference_arm_reports_an_unscaled_measurement():
+    """`bench.py --impl reference` (the CPU port on the host cores) must print one JSON line whose
+    value is the measured time of the config it names -- no extrapolation to the benchmark size."""
+    import json
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2",
+                        "--warmup", "1", "--sample-n", "10", "--ref-budget", "30"], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "amg_setup_time" and d["higher_is_better"] is False
+    assert d["config"]["workload"] == "poisson7_10^3_full_hierarchy_setup" and d["config"]["rows"] == 1000
+    assert d["config"]["same_config_as_gpu_arm"] is False
+    assert d["value"] == d["cpu_baseline"]["value"] == d["e2e"]["value"] and d["cpu_baseline"]["cores"] == 1
+    assert abs(d["ms_per_step"] - 1e3 * d["value"]) < 1e-6
