@@ -39,6 +39,27 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries loaded later (NCCL's version banner, the
+    reference-style progress prints of a checker) write to fd 1 directly, so fd 1 is pointed at
+    stderr for the whole run and the line is written to a private copy of the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def load_peaks():
     try:
         d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -156,7 +177,7 @@ def run_reference(args, rank, world):
                        if n != args.n else "the benchmark's own config"},
             "cpu_baseline": {"value": t, "unit": "s", "cores": 1, "kind": "port", "sample": sample},
             "e2e": {"value": t, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def load_traffic(key):
@@ -233,7 +254,7 @@ def run_solve(args, L, api, torch, dist, rank, world, local, dev, barrier):
                              "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
                              "traffic": None, "algorithmic_bytes_per_cycle": bytes_cycle},
                 "solution_norm": float(np.linalg.norm(hx))}
-        print(json.dumps(line), flush=True)
+        emit(line)
     H.free()
 
 
@@ -256,6 +277,7 @@ def main():
                     help="N > 1: partitioned = one setup, stages row-partitioned over the ranks (NCCL); "
                          "replicas = N independent setups")
     args = ap.parse_args()
+    claim_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -440,7 +462,7 @@ def main():
                                           "rows": srows, "cpu_port_s": ts, "gpu_s": sample["gpu_s"],
                                           "cpu_over_gpu": ts / sample["gpu_s"], "hierarchy_hash": sample["hash"],
                                           "note": "both arms measured in this run on the same input through host buffers"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         if partitioned:
             api.comm_finalize(L)

@@ -770,12 +770,27 @@ static void find_huge(QStore &qs, const Csr &Wt) {
   k_find_huge<<<(Wt.rn + 255) / 256, 256, 0, c.stream>>>(Wt.rn, qs.bignz, Wt.ro.p, qs.qoff.p, rec.p, cap, meta.p);
   c.launches++; post_launch("find_huge");
   std::vector<int> hm = meta.download();
-  if (hm[0] > cap) throw Error(-12, "more than 8192 interpolation supports above " + std::to_string(qs.bignz) + " rows");
+  // The blocked kernels take one column at a time with the whole GPU: right for the pile (one or
+  // two columns), wrong for a coarse level where hundreds of columns have supports of 600 rows
+  // (Q1 vertex meshes: 30 s instead of 9 s per setup at 97^3).  With more than 8 candidates only
+  // supports above 2048 rows count as huge; the others stay with one block each.
+  if (hm[0] > cap) {
+    if (force) throw Error(-12, "more than 8192 interpolation supports above " + std::to_string(qs.bignz) + " rows");
+    qs.bignz = 0x7fffffff;
+    return;
+  }
   std::vector<HugeRec> hr((size_t)hm[0]);
   if (hm[0]) d2h(hr.data(), rec.p, sizeof(HugeRec) * (size_t)hm[0]);
+  int small_max = hm[1];
+  if (!force && hm[0] > 8) {
+    qs.bignz = 2048;
+    std::vector<HugeRec> keep;
+    for (const HugeRec &r : hr) { if (r.nz > qs.bignz) keep.push_back(r); else if (r.nz > small_max) small_max = r.nz; }
+    hr.swap(keep);
+  }
   std::sort(hr.begin(), hr.end(), [](const HugeRec &a, const HugeRec &b) { return a.col < b.col; });
   for (const HugeRec &r : hr) qs.huge.push_back(QStore::Huge{r.col, r.nz, r.wb, (i64)r.qoff});
-  qs.maxnz_small = hm[1];
+  qs.maxnz_small = small_max;
 }
 
 static void set_smem(const void *fn, size_t bytes) {
