@@ -354,15 +354,16 @@ __global__ void __launch_bounds__(256) k_gram_fill(const int *list, int nlist, c
   }
 }
 
-// Gram rows of columns with a very large support: blockIdx.y = column, the pairs (k, m <= k) are
-// spread over gridDim.x blocks
+// Gram rows of columns with a very large support: blockIdx.x = column (the x dimension of a grid
+// has no 65535 limit: a 4 M-row Q1 mesh has more such columns than that), the pairs (k, m <= k)
+// are spread over gridDim.y blocks
 __global__ void __launch_bounds__(256) k_gram_fill_big(const int *list, const int *wro, const int *wcol, const int *aro,
                                                        const int *acol, const double *aa, double *Qall, const i64 *qoff) {
-  const int i = list[blockIdx.y];
+  const int i = list[blockIdx.x];
   const int b = wro[i], nz = wro[i + 1] - b;
   const int *Qj = wcol + b;
   double *Q = Qall + qoff[i];
-  for (int k = blockIdx.x * 8 + (threadIdx.x >> 5); k < nz; k += gridDim.x * 8) {
+  for (int k = blockIdx.y * 8 + (threadIdx.x >> 5); k < nz; k += gridDim.y * 8) {
     const int s = Qj[k];
     const int ab = aro[s], an = aro[s + 1] - ab;
     double *qk = Q + tri(k);
@@ -846,7 +847,7 @@ void build_q_store(QStore &qs, const Csr &Wt, const Csr &At) {
   Buf<double> scratch;
   if (hc[5] && qs.maxnz_small > 12800) throw Error(-12, "interpolation support of " + std::to_string(qs.maxnz_small) + " rows exceeds the kernel limit (12800)");
   if (hc[5]) {
-    k_gram_fill_big<<<dim3(64, hc[5]), 256, 0, c.stream>>>(lp + 5 * (i64)n, wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
+    k_gram_fill_big<<<dim3(hc[5], 64), 256, 0, c.stream>>>(lp + 5 * (i64)n, wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
     c.launches++; post_launch("gram_fill_big");
   }
   if (big_cluster) {
@@ -969,9 +970,26 @@ void apply_q(const QStore &qs, Csr &Wt, const Csr &Bt, const double *u, const do
   c.launches++; post_launch("apply_q");
 }
 
+// sum over k in [k0, nz) of Q[tri(k) + m] * Q[tri(k) + j], k ascending, with the sixteen loads of a
+// batch issued before the first product is added (AMGB_QQ_BATCH=1; A/B switch)
+__device__ __forceinline__ double qq_pair(const double *Q, int m, int j, int k0, int nz) {
+  double acc = 0;
+  for (int k = k0; k < nz; k += 8) {
+    double a[8], b[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int kk = k + u < nz ? k + u : nz - 1;
+      const i64 o = tri(kk);
+      a[u] = Q[o + m]; b[u] = Q[o + j];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) if (k + u < nz) acc = acc + a[u] * b[u];
+  }
+  return acc;
+}
 // ---- QQ^t: one block per column (one warp for small ones), pairs (m<=j) over threads ----
 __global__ void __launch_bounds__(128) k_form_qq(int n, const int *wro, const double *Qall, const i64 *qoff,
-                                                 double *QQ, const i64 *qqoff, int bignz) {
+                                                 double *QQ, const i64 *qqoff, int bignz, int batch) {
   const int i = blockIdx.x;
   if (i >= n) return;
   const int nz = wro[i + 1] - wro[i];
@@ -982,7 +1000,8 @@ __global__ void __launch_bounds__(128) k_form_qq(int n, const int *wro, const do
     const int m = idx / nz, j = idx - m * nz;
     if (m > j) continue;
     double acc = 0;
-    for (int k = j; k < nz; k++) acc = acc + Q[tri(k) + m] * Q[tri(k) + j];
+    if (batch) acc = qq_pair(Q, m, j, j, nz);
+    else for (int k = j; k < nz; k++) acc = acc + Q[tri(k) + m] * Q[tri(k) + j];
     out[(i64)m * nz + j] = acc;
     out[(i64)j * nz + m] = acc;
   }
@@ -1008,12 +1027,12 @@ __global__ void __launch_bounds__(256) k_form_qq_small(int n, const int *wro, co
 // columns with a large support: the pairs (m <= j) of one column are spread over gridDim.x blocks
 __global__ void __launch_bounds__(256) k_form_qq_big(const int *list, const int *wro, const double *Qall,
                                                      const i64 *qoff, double *QQ, const i64 *qqoff) {
-  const int i = list[blockIdx.y];
+  const int i = list[blockIdx.x];          // x: no 65535 limit on the number of columns
   const int nz = wro[i + 1] - wro[i];
   const double *Q = Qall + qoff[i];
   double *out = QQ + qqoff[i];
   const i64 total = (i64)nz * nz;
-  for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (i64)gridDim.x * blockDim.x) {
+  for (i64 idx = (i64)blockIdx.y * blockDim.x + threadIdx.x; idx < total; idx += (i64)gridDim.y * blockDim.x) {
     const int m = (int)(idx / nz), j = (int)(idx - (i64)m * nz);
     if (m > j) continue;
     double acc = 0;
@@ -1035,6 +1054,8 @@ void form_qq(QQStore &qq, const QStore &qs, const Csr &Wt) {
     c.launches++; post_launch("form_qq_huge");
   }
   const int bignz = qs.bignz;
+  static int qq_batch = -1;
+  if (qq_batch < 0) { const char *e = getenv("AMGB_QQ_BATCH"); qq_batch = (e && *e == '1') ? 1 : 0; }
   if (qs.maxnz_small > QQ_BIG) {
     // the few columns with a very large support (the reference piles every F row without a
     // coupling into column 0, :2229) would otherwise be one block each and set the run time
@@ -1045,14 +1066,14 @@ void form_qq(QQStore &qq, const QStore &qs, const Csr &Wt) {
     parallel_for(n, [=] DEV(i64 i) { const int nz = wro[i + 1] - wro[i]; if (nz > QQ_BIG && nz <= bignz) bp[atomic_add(np_, 1)] = (int)i; });
     const int nb = nbig.get(0);
     if (nb) {
-      k_form_qq_big<<<dim3(96, nb), 256, 0, c.stream>>>(big.p, Wt.ro.p, qs.Q.p, qs.qoff.p, qq.QQ.p, qq.qqoff.p);
+      k_form_qq_big<<<dim3(nb, 96), 256, 0, c.stream>>>(big.p, Wt.ro.p, qs.Q.p, qs.qoff.p, qq.QQ.p, qq.qqoff.p);
       c.launches++; post_launch("form_qq_big");
     }
   }
   if (qs.maxnz_small <= 12)
     k_form_qq_small<<<(n + 31) / 32, 256, 0, c.stream>>>(n, Wt.ro.p, qs.Q.p, qs.qoff.p, qq.QQ.p, qq.qqoff.p, bignz);
   else
-    k_form_qq<<<n, 128, 0, c.stream>>>(n, Wt.ro.p, qs.Q.p, qs.qoff.p, qq.QQ.p, qq.qqoff.p, bignz);
+    k_form_qq<<<n, 128, 0, c.stream>>>(n, Wt.ro.p, qs.Q.p, qs.qoff.p, qq.QQ.p, qq.qqoff.p, bignz, qq_batch);
   c.launches++; post_launch("form_qq");
 }
 

@@ -404,7 +404,12 @@ __device__ void eps_run(const double *a, const double *b, i64 begin, i64 n, doub
       if (t == 0) {
         const i64 j = pos + vmin_sh;
         if (vmin_sh == EPS_T * EPS_E || j >= n) pos_sh = (j < n) ? j : n;
-        else { s_sh = __dadd_rn(0.0, b ? __dmul_rn(a[j], b[j]) : a[j]); pos_sh = j + 1; }
+        else {
+          s_sh = __dadd_rn(0.0, b ? __dmul_rn(a[j], b[j]) : a[j]); pos_sh = j + 1;
+          // a sum that starts from zero doubles every few terms at first: the next 256 terms go
+          // through the plain chain (1 us) instead of one parallel pass per binade crossed
+          need_serial_sh = 1; burst_sh = 256;
+        }
       }
       __syncthreads();
       continue;
