@@ -559,53 +559,164 @@ __global__ void __launch_bounds__(EPS_T) k_eps_dot(const double *a, const double
 }
 
 // ---- many-block version for long vectors ----
-// Every chunk of 8192 terms is reduced speculatively by its own block, assuming the running sum
-// enters the chunk with the sign and exponent of an approximate (order-free) prefix sum.  A chunk
-// record holds the integer total for an even incoming mantissa, what changes for an odd one (only
-// the first tie of the chunk sees the incoming parity: delta), and the extreme values the running
-// mantissa takes before/after that tie, so that one thread can afterwards walk the chunks in
-// order, verify the assumption for the ACTUAL incoming sum (same sign, same exponent, mantissa
-// stays inside [2^52, 2^53)) and either accept the chunk in O(1) or hand it to eps_run.
+// The vector is cut into SEGMENTS of at most 8192 terms.  Every segment is reduced speculatively
+// by its own block, assuming the running sum enters it with the sign and exponent of an
+// approximate (order-free) prefix sum and stays in that binade.  A segment record holds the
+// integer total for an even incoming mantissa, what changes for an odd one (only the first tie of
+// the segment sees the incoming parity: delta), and the extreme values the running mantissa takes
+// before/after that tie, so that one thread can afterwards walk the segments in order, verify the
+// assumption for the ACTUAL incoming sum (same sign, same exponent, mantissa stays inside
+// [2^52, 2^53)) and either accept the segment in O(1) or hand it to eps_run.
+//
+// A sum of n similar terms crosses a binade about log2(n) times, and a segment with a crossing
+// inside can never be accepted.  So the plan is made from approximate prefix sums at two
+// granularities (k_eps_plan): a chunk of 8192 terms whose approximate running sum keeps its
+// exponent is one segment; a chunk where it changes is cut at its 256-term sub-chunks into runs of
+// constant exponent (speculative segments, each with its own hypothesis) and the sub-chunks where
+// the exponent changes, which the walker adds the plain way (256 dependent additions from shared
+// memory).  Whatever the plan says, every accept is verified against the actual running sum and
+// every rejected segment is redone exactly, so a wrong guess costs time, never a bit.
 struct EpsChunk {
   long long total0, lo_pre, hi_pre, lo_post, hi_post;
+  i64 begin, end;
   int delta, bad, gsign, gsex;
+  int kind, pad_;                   // 0 speculative, 1 plain chain, 2 eps_run (no hypothesis)
 };
 #define EPS_C (EPS_T * EPS_E)
-__global__ void __launch_bounds__(256) k_eps_chunk_sums(const double *a, const double *b, i64 n, double *sums) {
-  __shared__ double w[8];
-  const i64 base = (i64)blockIdx.x * EPS_C;
-  double x = 0.0;
-  for (int k = threadIdx.x; k < EPS_C; k += 256) { const i64 j = base + k; if (j < n) x += b ? a[j] * b[j] : a[j]; }
-  for (int off = 16; off >= 1; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
-  if ((threadIdx.x & 31) == 0) w[threadIdx.x >> 5] = x;
-  __syncthreads();
-  if (threadIdx.x == 0) { double t = 0; for (int k = 0; k < 8; k++) t += w[k]; sums[blockIdx.x] = t; }
-}
-__global__ void k_eps_guess(const double *sums, int nchunks, EpsChunk *rec) {
-  double pre = 0.0;
-  for (int c = 0; c < nchunks; c++) {
-    const unsigned long long bits = (unsigned long long)__double_as_longlong(pre);
-    rec[c].gsign = (bits >> 63) ? -1 : 1;
-    rec[c].gsex = (int)((bits >> 52) & 0x7ff);
-    pre += sums[c];
+#define EPS_SUB 256                  // terms per sub-chunk
+#define EPS_NSUB (EPS_C / EPS_SUB)   // 32 sub-chunks per chunk
+// sub[c*32 + w]: order-free sum of the terms [c*8192 + w*256, +256) (one warp each)
+__global__ void __launch_bounds__(256) k_eps_chunk_sums(const double *a, const double *b, i64 n, double *sub) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const i64 cbase = (i64)blockIdx.x * EPS_C;
+  for (int w = wid; w < EPS_NSUB; w += 8) {
+    const i64 base = cbase + (i64)w * EPS_SUB;
+    double x = 0.0;
+#pragma unroll
+    for (int k = 0; k < EPS_SUB / 32; k++) { const i64 j = base + k * 32 + lane; if (j < n) x += b ? a[j] * b[j] : a[j]; }
+    for (int off = 16; off >= 1; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+    if (lane == 0) sub[(i64)blockIdx.x * EPS_NSUB + w] = x;
   }
 }
-__global__ void __launch_bounds__(EPS_T) k_eps_chunk_stats(const double *a, const double *b, i64 n, EpsChunk *rec) {
+__device__ __forceinline__ int eps_expo(double x) { return (int)(((unsigned long long)__double_as_longlong(x) >> 52) & 0x7ff); }
+__device__ __forceinline__ int eps_sgn(double x) { return ((unsigned long long)__double_as_longlong(x) >> 63) ? -1 : 1; }
+__device__ __forceinline__ bool eps_same_binade(double x, double y) {
+  const int ex = eps_expo(x);
+  return ex == eps_expo(y) && eps_sgn(x) == eps_sgn(y) && ex != 0 && ex != 0x7ff;
+}
+// The plan, by one block: warp w looks at chunk c = w, w+32, ... -- lane l sees the approximate
+// running sum before and after sub-chunk l (a warp scan of the 32 sub-sums on top of the chunk's
+// approximate prefix) -- and the chunk becomes
+//   * one speculative segment, if the exponent never changes,
+//   * runs of sub-chunks with one exponent (speculative) and single sub-chunks where it changes
+//     (plain chain), if it changes in at most EPS_MAXCUT sub-chunks,
+//   * one eps_run segment otherwise (sums around zero, leading zeros: eps_run adapts by itself).
+// The chunk prefixes and the segment offsets are two short serial scans by thread 0 over shared
+// memory; chunks are handled in tiles of EPS_PLAN_TILE.
+#define EPS_MAXCUT 8
+#define EPS_SEG_PER_CHUNK (2 * EPS_MAXCUT + 1)
+#define EPS_PLAN_TILE 1024
+__device__ __forceinline__ int eps_plan_chunk(const double *sub, int c, i64 n, double pre, EpsChunk *out) {
+  // returns the number of segments of chunk c; writes them to out[0..) unless out == nullptr
+  const int lane = threadIdx.x & 31;
+  const i64 cb = (i64)c * EPS_C, ce = (cb + EPS_C < n) ? cb + EPS_C : n;
+  double incl = sub[(i64)c * EPS_NSUB + lane];
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) { const double pv = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += pv; }
+  const double after = pre + incl;                                   // approximate running sum after my sub-chunk
+  double before = __shfl_up_sync(0xffffffffu, after, 1);
+  if (lane == 0) before = pre;
+  const i64 sb = cb + (i64)lane * EPS_SUB;
+  const bool live = sb < ce;                                         // sub-chunk holds terms
+  const bool steady = !live || eps_same_binade(before, after);       // exponent kept across my sub-chunk
+  const unsigned unsteady = __ballot_sync(0xffffffffu, !steady);
+  if (unsteady == 0u) {
+    if (out && lane == 0) { EpsChunk &R = out[0]; R.begin = cb; R.end = ce; R.kind = 0; R.bad = 0; R.gsign = eps_sgn(pre); R.gsex = eps_expo(pre); }
+    return 1;
+  }
+  if (__popc(unsteady) > EPS_MAXCUT) {
+    if (out && lane == 0) { EpsChunk &R = out[0]; R.begin = cb; R.end = ce; R.kind = 2; R.bad = 1; R.gsign = 1; R.gsex = 0; }
+    return 1;
+  }
+  // a steady sub-chunk starts a run when it is the first of the chunk or follows an unsteady one
+  // (consecutive steady sub-chunks share their exponent: after of one is before of the next)
+  const bool prev_unsteady = lane > 0 && ((unsteady >> (lane - 1)) & 1u);
+  const bool head = live && (!steady || lane == 0 || prev_unsteady);
+  const unsigned heads = __ballot_sync(0xffffffffu, head);
+  if (out && head) {
+    const int slot = __popc(heads & ((1u << lane) - 1u));
+    const unsigned later = (lane == 31) ? 0u : (heads >> (lane + 1));
+    const int nextw = later ? lane + 1 + (__ffs(later) - 1) : EPS_NSUB;
+    EpsChunk &R = out[slot];
+    i64 e = cb + (i64)nextw * EPS_SUB;
+    if (e > ce) e = ce;
+    R.begin = sb; R.end = e;
+    R.kind = steady ? 0 : 1;
+    R.bad = steady ? 0 : 1;
+    R.gsign = eps_sgn(before); R.gsex = eps_expo(before);
+  }
+  return __popc(heads);
+}
+__global__ void __launch_bounds__(1024) k_eps_plan(const double *sub, int nchunks, i64 n, EpsChunk *rec, int *nseg_out) {
+  __shared__ double pre_sh[EPS_PLAN_TILE];
+  __shared__ int off_sh[EPS_PLAN_TILE];
+  __shared__ double carry_sh;
+  __shared__ int ns_sh;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  if (t == 0) { carry_sh = 0.0; ns_sh = 0; }
+  for (int c0 = 0; c0 < nchunks; c0 += EPS_PLAN_TILE) {
+    const int nt = min(EPS_PLAN_TILE, nchunks - c0);
+    __syncthreads();
+    for (int q = wid; q < nt; q += 32) {                               // approximate chunk totals
+      double x = sub[(i64)(c0 + q) * EPS_NSUB + lane];
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+      if (lane == 0) pre_sh[q] = x;
+    }
+    __syncthreads();
+    if (t == 0) {                                                      // exclusive prefix: running sum before each chunk
+      double p = carry_sh;
+      for (int q = 0; q < nt; q++) { const double x = pre_sh[q]; pre_sh[q] = p; p += x; }
+      carry_sh = p;
+    }
+    __syncthreads();
+    for (int q = wid; q < nt; q += 32) {
+      const int k = eps_plan_chunk(sub, c0 + q, n, pre_sh[q], nullptr);
+      if (lane == 0) off_sh[q] = k;
+    }
+    __syncthreads();
+    if (t == 0) {
+      int o = ns_sh;
+      for (int q = 0; q < nt; q++) { const int k = off_sh[q]; off_sh[q] = o; o += k; }
+      ns_sh = o;
+    }
+    __syncthreads();
+    for (int q = wid; q < nt; q += 32) eps_plan_chunk(sub, c0 + q, n, pre_sh[q], rec + off_sh[q]);
+  }
+  __syncthreads();
+  if (t == 0) *nseg_out = ns_sh;
+}
+__global__ void __launch_bounds__(EPS_T) k_eps_chunk_stats(const double *a, const double *b, EpsChunk *rec, const int *nseg) {
   __shared__ ParFn pf[64 + 32];
   __shared__ long long ls[64 + 32];
   __shared__ int first_tie, bad_sh, d0_sh;
   __shared__ long long lo_pre, hi_pre, lo_post, hi_post;
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  EpsChunk &R = rec[blockIdx.x];
+  const int total = *nseg;
+  for (int seg = blockIdx.x; seg < total; seg += gridDim.x) {
+  __syncthreads();
+  EpsChunk &R = rec[seg];
+  if (R.kind != 0) continue;
+  const i64 n = R.end;
   const int sex = R.gsex, ssign = R.gsign;
   if (t == 0) {
     first_tie = EPS_C; bad_sh = (sex == 0 || sex == 0x7ff) ? 1 : 0; d0_sh = 0;
     lo_pre = lo_post = (1LL << 62); hi_pre = hi_post = -(1LL << 62);
   }
   __syncthreads();
-  if (bad_sh) { if (t == 0) R.bad = 1; return; }
+  if (bad_sh) { if (t == 0) R.bad = 1; continue; }
   const int se = sex - 1075;
-  const i64 base = (i64)blockIdx.x * EPS_C + (i64)t * EPS_E;
+  const i64 base = R.begin + (i64)t * EPS_E;
   long long fl[EPS_E];
   int up[EPS_E], tie[EPS_E];
   int anybad = 0;
@@ -695,34 +806,37 @@ __global__ void __launch_bounds__(EPS_T) k_eps_chunk_stats(const double *a, cons
   }
   if (lane == 0) { atomicMin(&lo_pre, mlo_pre); atomicMax(&hi_pre, mhi_pre); atomicMin(&lo_post, mlo_post); atomicMax(&hi_post, mhi_post); }
   __syncthreads();
-  if (t == EPS_T - 1) R.total0 = P;                                   // total of the chunk (incoming parity even)
+  if (t == EPS_T - 1) R.total0 = P;                                   // total of the segment (incoming parity even)
   if (t == 0) {
     R.lo_pre = lo_pre; R.hi_pre = hi_pre; R.lo_post = lo_post; R.hi_post = hi_post;
     R.delta = (ft < EPS_C) ? (1 - 2 * d0_sh) : 0;
     R.bad = bad_sh;
   }
+  }
 }
-__global__ void __launch_bounds__(EPS_T) k_eps_combine(const double *a, const double *b, i64 n, const EpsChunk *rec,
-                                                       int nchunks, double *out, int *nfallback) {
+#define EPS_SREC 192                 // segment records cached in shared memory by the walker
+__global__ void __launch_bounds__(EPS_T) k_eps_combine(const double *a, const double *b, const EpsChunk *rec,
+                                                       const int *nseg_p, double *out, int *nfallback) {
   __shared__ EpsShared sh;
   __shared__ int next_sh;
   __shared__ double cur_sh;
-  __shared__ EpsChunk srec[160];                  // records of the first 160 chunks (1.3 M terms)
+  __shared__ EpsChunk srec[EPS_SREC];
   const int t = threadIdx.x;
+  const int nseg = *nseg_p;
   if (t == 0) { cur_sh = 0.0; next_sh = 0; }
-  for (int q = t; q < nchunks && q < 160; q += EPS_T) srec[q] = rec[q];
+  for (int q = t; q < nseg && q < EPS_SREC; q += EPS_T) srec[q] = rec[q];
   __syncthreads();
   int fb = 0;
   while (true) {
     if (t == 0) {
-      // accept as many consecutive chunks as the assumptions allow
+      // accept as many consecutive segments as the assumptions allow
       double s = cur_sh;
       int c = next_sh;
-      for (; c < nchunks; c++) {
-        const EpsChunk &R = (c < 160) ? srec[c] : rec[c];
+      for (; c < nseg; c++) {
+        const EpsChunk &R = (c < EPS_SREC) ? srec[c] : rec[c];
         const unsigned long long bits = (unsigned long long)__double_as_longlong(s);
         const int sex = (int)((bits >> 52) & 0x7ff), sg = (bits >> 63) ? -1 : 1;
-        if (R.bad || sex != R.gsex || sg != R.gsign || sex == 0 || sex == 0x7ff) break;
+        if (R.kind != 0 || R.bad || sex != R.gsex || sg != R.gsign || sex == 0 || sex == 0x7ff) break;
         const long long S = (long long)((bits & 0xfffffffffffffULL) | (1ULL << 52));
         const int odd = (int)(S & 1);
         const long long d = odd ? R.delta : 0;
@@ -736,12 +850,27 @@ __global__ void __launch_bounds__(EPS_T) k_eps_combine(const double *a, const do
     }
     __syncthreads();
     const int c = next_sh;
-    if (c >= nchunks) break;
-    const i64 b0 = (i64)c * EPS_C, b1 = (b0 + EPS_C < n) ? b0 + EPS_C : n;
-    eps_run(a, b, b0, b1, cur_sh, sh);                                // the whole block redoes this chunk exactly
-    fb++;
+    if (c >= nseg) break;
+    const EpsChunk &R = (c < EPS_SREC) ? srec[c] : rec[c];
+    const i64 b0 = R.begin, b1 = R.end;
+    const int kind = R.kind;
     __syncthreads();
-    if (t == 0) { cur_sh = sh.s_sh; next_sh = c + 1; }
+    if (kind == 1 && b1 - b0 <= EPS_BURST_MAX) {
+      // the plan expects a binade crossing in these few terms: plain chain, products staged by all
+      const int cnt = (int)(b1 - b0);
+      for (int j = t; j < cnt; j += EPS_T) sh.prod[j] = b ? __dmul_rn(a[b0 + j], b[b0 + j]) : a[b0 + j];
+      __syncthreads();
+      if (t == 0) {
+        double r = cur_sh;
+        for (int j = 0; j < cnt; j++) r = __dadd_rn(r, sh.prod[j]);
+        cur_sh = r; next_sh = c + 1;
+      }
+    } else {
+      eps_run(a, b, b0, b1, cur_sh, sh);                              // the whole block redoes this segment exactly
+      fb++;
+      __syncthreads();
+      if (t == 0) { cur_sh = sh.s_sh; next_sh = c + 1; }
+    }
     __syncthreads();
   }
   if (t == 0) { *out = cur_sh; if (nfallback) *nfallback = fb; }
@@ -753,12 +882,15 @@ void seq_dot_dev(double *outp, const double *a, const double *b, i64 n) {
   if (g_eps < 0) { const char *e = getenv("AMGB_SEQDOT"); g_eps = (e && !strcmp(e, "chain")) ? 0 : (e && !strcmp(e, "block")) ? 1 : 2; }
   if (g_eps == 2 && (n >= 4 * (i64)EPS_C || (test_force('b') && n > EPS_C))) {
     const int nch = (int)((n + EPS_C - 1) / EPS_C);
-    Buf<double> sums(nch);
-    Buf<EpsChunk> rec(nch);
-    k_eps_chunk_sums<<<nch, 256, 0, g_ctx.stream>>>(a, b, n, sums.p);
-    k_eps_guess<<<1, 1, 0, g_ctx.stream>>>(sums.p, nch, rec.p);
-    k_eps_chunk_stats<<<nch, EPS_T, 0, g_ctx.stream>>>(a, b, n, rec.p);
-    k_eps_combine<<<1, EPS_T, 0, g_ctx.stream>>>(a, b, n, rec.p, nch, outp, nullptr);
+    const int cap = EPS_SEG_PER_CHUNK * nch;
+    const int grid = 2 * nch + 64 < cap ? 2 * nch + 64 : cap;       // a plan rarely holds more segments than this
+    Buf<double> sub((i64)nch * EPS_NSUB);
+    Buf<EpsChunk> rec(cap);
+    Buf<int> nseg(1);
+    k_eps_chunk_sums<<<nch, 256, 0, g_ctx.stream>>>(a, b, n, sub.p);
+    k_eps_plan<<<1, 1024, 0, g_ctx.stream>>>(sub.p, nch, n, rec.p, nseg.p);
+    k_eps_chunk_stats<<<grid, EPS_T, 0, g_ctx.stream>>>(a, b, rec.p, nseg.p);
+    k_eps_combine<<<1, EPS_T, 0, g_ctx.stream>>>(a, b, rec.p, nseg.p, outp, nullptr);
     g_ctx.launches += 3;
   } else if (g_eps) k_eps_dot<<<1, EPS_T, 0, g_ctx.stream>>>(a, b, n, outp);
   else k_seq_dot<<<1, 1024, 0, g_ctx.stream>>>(a, b, n, outp);

@@ -292,6 +292,16 @@ def test_sequential_reduction_kernel_is_exact(L):
         "sparse_nonzeros": np.where(rng.random(400000) < 1e-3, rng.standard_normal(400000), 0.0),
         "negative_zero_start": np.concatenate([[-0.0, -0.0], np.zeros(10000), [-1.5, 2.5]]),
         "with_inf": np.concatenate([rng.standard_normal(100), [np.inf], rng.standard_normal(100)]),
+        # long vectors through the segment planner: crossings in the middle of chunks, a sum that
+        # shrinks again, one that changes sign, zeros between values, a late non-finite term
+        "growing": np.abs(rng.standard_normal(1 << 20)) * np.linspace(1e-6, 1.0, 1 << 20) ** 3,
+        "up_then_down": np.concatenate([np.abs(rng.standard_normal(300000)), -np.abs(rng.standard_normal(299000))]),
+        "sign_change": np.concatenate([np.abs(rng.standard_normal(200000)), -2.0 * np.abs(rng.standard_normal(200000))]),
+        "blocks_of_zeros": np.where((np.arange(600000) // 5000) % 2 == 0, rng.standard_normal(600000) ** 2, 0.0),
+        "around_zero_long": rng.standard_normal(500000) * 1e-3,
+        "late_inf": np.concatenate([rng.standard_normal(400000) ** 2, [np.inf], rng.standard_normal(1000)]),
+        "ties_long": np.concatenate([[2.0 ** 30], rng.integers(-3, 4, 400000) * 2.0 ** -23]),
+        "exact_powers": np.full(1 << 19, 2.0 ** -10),
     }
     for name, p in cases.items():
         got = api.debug_dot(p, None, api.REDUCE_SEQUENTIAL, L=L)
