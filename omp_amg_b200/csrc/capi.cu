@@ -559,7 +559,7 @@ void crs_amg_solve(double *x, struct crs_data *d, double *b) {
     vcycle_solve_graph(d->h->H, uxp, ubp);       // replayed as a CUDA graph from the second solve on
     // the hierarchy projects the mean out when it detected a singular operator; crs_solve does
     // so when the caller asked for it (amg.c:181)
-    if (d->null_space && !d->h->H.nullspace) project_mean(uxp, un);
+    if (d->null_space && !d->h->H.nullspace) project_mean(d->h->H, uxp);
     parallel_for(n, [=] DEV(i64 i) { xp[i] = um[i] >= 0 ? uxp[um[i]] : 0.0; });
     d2h(x, xp, sizeof(double) * (size_t)n);
     d->solves++;

@@ -54,6 +54,11 @@ struct Hierarchy {
   StageTimes t;
   i64 launches = 0, syncs = 0;
   mutable Buf<double> mean_scratch;     // device scalar of the mean projection
+  // crs_solve's storage order (amg.c:438-446: unknowns sorted by the level at which they become
+  // F, ascending inside a level): position of every top-level unknown, and the vector in that
+  // order -- the mean of amg.c:182 is summed in it.  Built at the first projection.
+  mutable Buf<int> lsort_pos;
+  mutable Buf<double> lsort_x;
   mutable SolveGraph graph;
 };
 
@@ -69,7 +74,8 @@ void setup(i64 nnz, const int *dAi, const int *dAj, const double *dAv, Hierarchy
 void vcycle_solve(const Hierarchy &H, double *x, const double *b);
 // the same through a CUDA graph captured on the second call with the same vectors (AMGB_SOLVE_GRAPH=0: never)
 void vcycle_solve_graph(const Hierarchy &H, double *x, const double *b);
-// x -= mean(x) with the mean formed on the device (no host round trip)
-void project_mean(double *x, i64 n, double *scratch = nullptr);
+// x -= mean(x) (amg.c:181-184): the sum runs over crs_solve's level-sorted storage order and
+// stays on the device (no host round trip)
+void project_mean(const Hierarchy &H, double *x);
 
 }  // namespace amgb

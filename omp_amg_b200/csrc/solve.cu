@@ -61,10 +61,8 @@ void vcycle_level(const Hierarchy &H, int l, double *x, const double *b) {
 void vcycle_solve(const Hierarchy &H, double *x, const double *b) {
   const int n = H.n0;
   vcycle_level(H, 0, x, b);
-  if (H.nullspace) {
-    if (!H.mean_scratch.p) H.mean_scratch.alloc(1);
-    project_mean(x, n, H.mean_scratch.p);
-  }
+  (void)n;
+  if (H.nullspace) project_mean(H, x);
 }
 
 SolveGraph::~SolveGraph() {
@@ -116,13 +114,39 @@ void vcycle_solve_graph(const Hierarchy &H, double *x, const double *b) {
 #endif
 }
 
-// x -= (1/n) * sum(x), the sum in the order the context asks for (amg.c:181-184), its result kept
-// on the device: a solve never waits for the host
-void project_mean(double *x, i64 n, double *scratch) {
-  Buf<double> own;
-  if (!scratch) { own.alloc(1); scratch = own.p; }
-  vsum_dev(scratch, x, n);
-  const double *sp = scratch;
+// x -= (1/n) * sum(x) (amg.c:181-184).  The reference sums ux in ITS storage order -- the
+// unknowns sorted by the level at which they become F, ascending inside a level, the last level's
+// unknown at the end (amg.c:438-446) -- so x is first gathered into that order; the sum (in the
+// reduction order the context asks for) stays on the device: a solve never waits for the host.
+static void build_level_sorted_positions(const Hierarchy &H) {
+  const int nl = (int)H.lv.size();
+  std::vector<int> off((size_t)nl + 1, 0);
+  for (int l = 0; l < nl; l++) off[(size_t)l + 1] = off[(size_t)l] + (l < nl - 1 ? H.lv[(size_t)l].nf : H.lv[(size_t)l].n);
+  Buf<int> g((i64)H.lv[(size_t)nl - 1].n + 1);
+  { int *gp = g.p; const int o = off[(size_t)nl - 1]; parallel_for(H.lv[(size_t)nl - 1].n, [=] DEV(i64 i) { gp[i] = o + (int)i; }); }
+  for (int l = nl - 2; l >= 0; l--) {
+    const Level &L = H.lv[(size_t)l];
+    Buf<int> gl((i64)L.n + 1);
+    int *glp = gl.p;
+    const int *gn = g.p, *cpos = L.cpos.p, *fpos = L.fpos.p;
+    const double *Cf = L.C.p;
+    const int o = off[(size_t)l];
+    parallel_for(L.n, [=] DEV(i64 i) { glp[i] = (Cf[i] != 0.) ? gn[cpos[i]] : o + fpos[i]; });
+    g = std::move(gl);
+  }
+  H.lsort_pos = std::move(g);
+  H.lsort_x.alloc(H.n0);
+}
+void project_mean(const Hierarchy &H, double *x) {
+  const i64 n = H.n0;
+  if (n <= 0) return;
+  if (!H.mean_scratch.p) H.mean_scratch.alloc(1);
+  if (!H.lsort_pos.p) build_level_sorted_positions(H);
+  const int *pos = H.lsort_pos.p;
+  double *ux = H.lsort_x.p;
+  parallel_for(n, [=] DEV(i64 i) { ux[pos[i]] = x[i]; });
+  vsum_dev(H.mean_scratch.p, ux, n);
+  const double *sp = H.mean_scratch.p;
   const double inv = 1 / (double)n;
   parallel_for(n, [=] DEV(i64 i) { const double avg = inv * sp[0]; x[i] = x[i] - avg; });
 }

@@ -1387,8 +1387,10 @@ int amgo_export(const amgo_hier *h, const char *dir) {
 /* V-cycle: amg_exec (amg.c:114) + crs_solve (amg.c:171), one process.        */
 /* amg.c stores every level's F rows back to back; here each level keeps its   */
 /* own numbering, which is the same arithmetic up to the order of the columns */
-/* inside a row of W / AfP.  No runnable reference exists for this part       */
-/* (amg.c does not compile against amg_setup.h), so it is restated, unpinned. */
+/* inside a row of W / AfP.  amg.c does not compile as a file, but its solve   */
+/* path (amg.c:85-189) does in isolation: oracle/vcycle_ref_harness.c runs    */
+/* those lines unchanged, and tests/test_oracle.py pins this restatement to   */
+/* them bit for bit.                                                          */
 /* ------------------------------------------------------------------------- */
 static void vcycle(const amgo_hier *h, int l, double *x, double *b) {
   const olevel *L = &h->lv[l];
@@ -1439,10 +1441,30 @@ int amgo_solve(const amgo_hier *h, double *x, const double *b) {
   memcpy(bb, b, sizeof(double) * (size_t)n);
   vcycle(h, 0, x, bb);
   if (h->nullspace) {
+    /* crs_solve (amg.c:181-184) sums ux in ITS storage order: the unknowns sorted by the level at
+       which they become F, ascending inside a level (amg.c:438-446), the last level's unknown at
+       the end.  g[i] = position of top-level unknown i in that order. */
+    int nl = h->nlevels;
+    int *off = NEW(int, nl + 1);
+    off[0] = 0;
+    for (int l = 0; l < nl; l++) off[l + 1] = off[l] + (l < nl - 1 ? h->lv[l].nf : h->lv[l].n);
+    int *g = NEW(int, h->lv[nl - 1].n + 1);
+    for (int i = 0; i < h->lv[nl - 1].n; i++) g[i] = off[nl - 1] + i;
+    for (int l = nl - 2; l >= 0; l--) {
+      const olevel *L = &h->lv[l];
+      int *gl = NEW(int, L->n + 1);
+      int cf = 0, cc = 0;
+      for (int i = 0; i < L->n; i++) gl[i] = (L->C[i] != 0.) ? g[cc++] : off[l] + cf++;
+      free(g);
+      g = gl;
+    }
+    double *ux = NEW(double, n + 1);
+    for (int i = 0; i < n; i++) ux[g[i]] = x[i];
     double s = 0;
-    for (int i = 0; i < n; i++) s += x[i];
+    for (int i = 0; i < n; i++) s += ux[i];
     double avg = (1 / (double)n) * s;
     for (int i = 0; i < n; i++) x[i] -= avg;
+    free(ux); free(g); free(off);
   }
   free(bb);
   return 0;

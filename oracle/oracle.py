@@ -3,6 +3,9 @@
 * ``Oracle``   -- oracle/libamg_oracle.so, the restatement (amg_oracle.c)
 * ``Ref``      -- oracle/_ref/libamg_ref.so, the unmodified reference compiled by
                   oracle/Makefile from /root/reference (amg_setup.c, amg_tools.c, ...)
+* ``RefVcycle`` -- oracle/_ref/libvcycle_ref.so: the reference's own amg_exec / crs_solve
+                  (amg.c:85-189, cut out at build time and compiled unchanged inside
+                  oracle/vcycle_ref_harness.c) on a hierarchy in this module's container
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
 import this module.  The product package never does.
@@ -20,6 +23,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "libamg_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libamg_ref.so")
 REF_BIN = os.path.join(HERE, "_ref", "serial_amg")
+VREF_SO = os.path.join(HERE, "_ref", "libvcycle_ref.so")
 
 SEQ, TREE = 0, 1
 CSR_A, CSR_AF, CSR_W, CSR_AFP = 0, 1, 2, 3
@@ -195,6 +199,85 @@ class Oracle:
 
     def free(self, h):
         self.L.amgo_free(h)
+
+
+# ------------------------------------------------------------------------------------------
+# the reference's V-cycle (amg.c:114-189) on a Hierarchy
+# ------------------------------------------------------------------------------------------
+def level_sorted_layout(H):
+    """The storage amg_exec works on (amg.c:117, :438-446): the unknowns sorted by the level at
+    which they become F (the last level's single unknown at the end), ascending inside a level.
+    Returns (off, g): off[l] = first position of level l (len nlevels+1), g[l][i] = position of
+    unknown i of level l."""
+    nl = H.nlevels
+    nf = [int(H.levels[l]["W"][3][0]) for l in range(nl - 1)]
+    nlast = int(H.levels[nl - 1]["A"][3][0])
+    off = np.concatenate([[0], np.cumsum(nf + [nlast])]).astype(np.int64)
+    g = [None] * nl
+    g[nl - 1] = off[nl - 1] + np.arange(nlast, dtype=np.int64)
+    for l in range(nl - 2, -1, -1):
+        C_ = np.asarray(H.levels[l]["C"]) != 0.0
+        gl = np.empty(len(C_), np.int64)
+        gl[~C_] = off[l] + np.arange(int((~C_).sum()), dtype=np.int64)
+        gl[C_] = g[l + 1]
+        g[l] = gl
+    return off, g
+
+
+class RefVcycle:
+    """crs_solve of the reference (one process, every id unique) on a Hierarchy.  The matrices keep
+    the storage order of their rows (level-local ascending columns); only the column numbers are
+    mapped into the level-sorted layout, as amg_setup_mats does (amg.c:295-377)."""
+
+    def __init__(self, path=VREF_SO):
+        if not os.path.exists(path):
+            raise FileNotFoundError(path + " (run `make -C oracle ref` where /root/reference exists)")
+        self.L = C.CDLL(path)
+        self.L.vref_solve.restype = C.c_int
+
+    @staticmethod
+    def available():
+        return os.path.exists(VREF_SO)
+
+    def solve(self, H, b, null_space=None):
+        nl = H.nlevels
+        off, g = level_sorted_layout(H)
+        tot = int(off[nl])
+        n0 = int(H.levels[0]["A"][3][0])
+        assert tot == n0, (tot, n0)
+        Dff = np.zeros(tot + 1, np.float64)
+        m = np.ones(max(nl, 1), np.uint32)
+        rho = np.zeros(max(nl, 1), np.float64)
+        keep, ros, cols, vals = [], [], [], []
+        for l in range(nl - 1):
+            lev = H.levels[l]
+            Dff[off[l]:off[l + 1]] = lev["D"]
+            m[l] = int(lev["m"]); rho[l] = lev["rho"]
+            tail = g[l + 1] - off[l + 1]            # level l+1 numbering -> position behind off[l+1]
+            for name in ("W", "AfP", "Af"):
+                ro, col, a, _ = lev[name]
+                c2 = col if name == "Af" else tail[col]
+                arrs = (np.ascontiguousarray(ro, np.uint64), np.ascontiguousarray(np.append(c2, 0), np.uint64),
+                        np.ascontiguousarray(np.append(a, 0.0), np.float64))
+                keep.append(arrs)
+                ros.append(arrs[0].ctypes.data); cols.append(arrs[1].ctypes.data); vals.append(arrs[2].ctypes.data)
+        last = H.levels[nl - 1]["A"]
+        if off[nl] - off[nl - 1] == 1:              # dvec of the last level as amg_export writes it (amg_setup.c:166, :452)
+            Dff[off[nl - 1]] = 0.0 if (H.nullspace or len(last[2]) == 0) else 1.0 / last[2][0]
+        umap = np.empty(tot, np.uint64)
+        umap[g[0]] = np.arange(n0, dtype=np.uint64)
+        P = C.c_void_p * max(len(ros), 1)
+        offu = np.ascontiguousarray(off, np.uint64)
+        bb = np.ascontiguousarray(b, np.float64).copy()
+        x = np.zeros(n0, np.float64)
+        ns = H.nullspace if null_space is None else null_space
+        rc = self.L.vref_solve(C.c_uint(nl), offu.ctypes.data_as(C.c_void_p), Dff.ctypes.data_as(C.c_void_p),
+                               m.ctypes.data_as(C.c_void_p), rho.ctypes.data_as(C.c_void_p), P(*ros), P(*cols), P(*vals),
+                               C.c_ulong(n0), umap.ctypes.data_as(C.c_void_p), C.c_int(int(ns)),
+                               x.ctypes.data_as(C.c_void_p), bb.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        del keep
+        return x
 
 
 # ------------------------------------------------------------------------------------------

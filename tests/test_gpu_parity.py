@@ -210,6 +210,25 @@ def test_vcycle_matches_oracle(L, O):
         assert np.abs(x - xo).max() <= 1e-12 * np.abs(xo).max()
 
 
+def test_vcycle_identical_to_reference_fixture(L):
+    """tests/golden/vcycle_ref.npz: x = crs_solve(b) computed by the REFERENCE's own amg_exec /
+    crs_solve lines (amg.c:85-189, oracle/vcycle_ref_harness.c).  The CUDA V-cycle -- plain and
+    replayed as a CUDA graph -- must give the same vector: bit for bit (every row sum, the
+    restriction through W' and the mean in the reference's order), and in any case within the
+    1e-12 relative of BASELINE.json's north_star."""
+    fx = np.load(os.path.join(GOLDEN, "vcycle_ref.npz"))
+    names = sorted(k[:-3] for k in fx.files if k.endswith("_Ai"))
+    assert len(names) >= 7
+    for name in names:
+        H = amg.amg_setup(fx[name + "_Ai"], fx[name + "_Aj"], fx[name + "_Av"], L=L)
+        want = fx[name + "_x"]
+        for rep in range(3):            # first call plain, then captured, then replayed
+            x = H.solve(fx[name + "_b"])
+            assert np.abs(x - want).max() <= 1e-12 * np.abs(want).max(), (name, rep)
+            assert np.array_equal(x, want), (name, rep, np.abs(x - want).max())
+        H.free()
+
+
 def test_crs_interface(L):
     Ai, Aj, Av = M.sem_hex(5)
     n = int(Ai.max()) + 1

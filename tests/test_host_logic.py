@@ -138,6 +138,9 @@ def test_vcycle_matches_oracle_and_reduces_residual(emu, O):
     x = H.solve(b); xo = O.solve(h, b)
     O.free(h)
     assert np.abs(x - xo).max() <= 1e-12 * np.abs(xo).max()
+    # the host-emulation build runs the same operations in the same order: identical bits (the
+    # oracle's V-cycle is itself pinned to the reference's amg_exec, tests/test_oracle.py)
+    assert np.array_equal(x, xo)
     import scipy.sparse as sp
     A = sp.coo_matrix((mat[2], (mat[0], mat[1]))).tocsr()
     # one V-cycle as a preconditioner must contract the error of a few Richardson steps

@@ -152,3 +152,38 @@ def test_single_stages_vs_live_reference(O):
     vc_o = np.zeros(n)
     O.L.amgo_coarsen(vc_o, O.to_csr(*A), 0.7)
     assert np.array_equal(vc_o, R.coarsen(A, 0.7))
+
+
+def _vcycle_cases():
+    fx = np.load(os.path.join(GOLDEN, "vcycle_ref.npz"))
+    names = sorted(k[:-3] for k in fx.files if k.endswith("_Ai"))
+    return fx, names
+
+
+def test_oracle_vcycle_bit_identical_to_reference_fixture(O):
+    """tests/golden/vcycle_ref.npz holds x = crs_solve(b) of the REFERENCE's own amg_exec/crs_solve
+    (amg.c:85-189, compiled unchanged in oracle/vcycle_ref_harness.c; make_vcycle_golden.py).  The
+    oracle's restatement of the V-cycle must reproduce every vector bit for bit."""
+    fx, names = _vcycle_cases()
+    assert len(names) >= 7
+    for name in names:
+        mat = (fx[name + "_Ai"], fx[name + "_Aj"], fx[name + "_Av"])
+        h = O.setup_raw(*mat, orc.SEQ)
+        x = O.solve(h, fx[name + "_b"])
+        O.free(h)
+        assert np.array_equal(x, fx[name + "_x"]), (name, np.abs(x - fx[name + "_x"]).max())
+
+
+@pytest.mark.skipif(not orc.RefVcycle.available(), reason="oracle/_ref/libvcycle_ref.so not built (needs /root/reference)")
+@pytest.mark.parametrize("name,n", [("dump", 0), ("sem_hex", 7), ("poisson7", 9), ("poisson27", 7), ("aniso7", 9)])
+def test_oracle_vcycle_vs_live_reference_code(O, name, n):
+    """The same comparison against the harness run live, on more inputs and right-hand sides."""
+    V = orc.RefVcycle()
+    mat = M.read_amgdmp(GOLDEN) if name == "dump" else M.by_name(name, n)
+    h = O.setup_raw(*mat, orc.SEQ)
+    H = O.fetch(h)
+    nrow = H.levels[0]["A"][3][0]
+    for seed in range(3):
+        b = np.random.default_rng(seed).standard_normal(nrow) * 10.0 ** seed
+        assert np.array_equal(O.solve(h, b), V.solve(H, b)), (name, seed)
+    O.free(h)
