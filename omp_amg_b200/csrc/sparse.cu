@@ -381,12 +381,36 @@ __global__ void __launch_bounds__(T) k_transpose_bitonic(const int *list, int nl
 // ---------------------------------------------------------------------------------------
 // transpose (:2000): A^t rows list the source rows in ascending order
 // ---------------------------------------------------------------------------------------
+#ifndef AMGB_EMU
+// order-free work on every entry (i, j) of a matrix with long rows: one warp per row
+template <class F>
+__global__ void __launch_bounds__(256) k_row_entries(int rn, const int *ro, F f) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= rn) return;
+  for (int j = ro[i] + lane; j < ro[i + 1]; j += 32) f(i, j);
+}
+#endif
+// f(i, j) for every entry j of every row i; f must not depend on the order inside a row
+template <class F>
+static void for_row_entries(const Csr &A, F f) {
+  const int *ro = A.ro.p;
+#ifndef AMGB_EMU
+  if (A.rn > 0 && A.nnz > 12 * (i64)A.rn) {
+    Context &c = ctx();
+    k_row_entries<<<(A.rn + 7) / 8, 256, 0, c.stream>>>(A.rn, ro, f);
+    c.launches++; post_launch("row_entries");
+    return;
+  }
+#endif
+  parallel_for(A.rn, [=] DEV(i64 i) { for (int j = ro[i]; j < ro[i + 1]; j++) f((int)i, j); });
+}
+
 Csr transpose(const Csr &A, Buf<int> *tpos_out) {
   StageTimer st_("prim.transpose");
   Csr T(A.cn, A.rn, A.nnz);
   Buf<int> cnt(A.cn + 1);
   cnt.zero();
-  const int *ro = A.ro.p, *col = A.col.p;
+  const int *col = A.col.p;
   const double *a = A.a.p;
   int *cntp = cnt.p;
   parallel_for(A.nnz, [=] DEV(i64 e) { atomic_add(&cntp[col[e]], 1); });
@@ -394,12 +418,8 @@ Csr transpose(const Csr &A, Buf<int> *tpos_out) {
   Buf<int> cursor(A.cn), src(A.nnz);
   d2d(cursor.p, T.ro.p, sizeof(int) * (size_t)A.cn);
   int *cur = cursor.p, *tcol = T.col.p, *srcp = src.p;
-  parallel_for(A.rn, [=] DEV(i64 i) {
-    for (int e = ro[i]; e < ro[i + 1]; e++) {
-      int p = atomic_add(&cur[col[e]], 1);
-      tcol[p] = (int)i; srcp[p] = e;
-    }
-  });
+  // any order: the rows of T are sorted by source row below
+  for_row_entries(A, [=] DEV(int i, int e) { const int p = atomic_add(&cur[col[e]], 1); tcol[p] = i; srcp[p] = e; });
   const int *tro = T.ro.p;
   double *ta = T.a.p;
 #ifdef AMGB_EMU
@@ -443,6 +463,37 @@ Csr transpose(const Csr &A, Buf<int> *tpos_out) {
 // ---------------------------------------------------------------------------------------
 // sub_mat (:3058)
 // ---------------------------------------------------------------------------------------
+#ifndef AMGB_EMU
+// sub_mat for rows of more than a dozen entries: one warp per kept row, the kept entries keep
+// their order (ballot + popcount prefix), loads and stores coalesced
+__global__ void __launch_bounds__(256) k_sub_mat_count(int rn, const int *ro, const int *col, const int *rf, const int *rm,
+                                                       const int *cf, int *cnt) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= rn || !rf[i]) return;
+  int c = 0;
+  for (int j = ro[i] + lane; j < ro[i + 1]; j += 32) c += cf[col[j]];
+  c = __reduce_add_sync(0xffffffffu, c);
+  if (lane == 0) cnt[rm[i]] = c;
+}
+__global__ void __launch_bounds__(256) k_sub_mat_fill(int rn, const int *ro, const int *col, const double *a, const int *rf,
+                                                      const int *rm, const int *cf, const int *cm, const int *sr,
+                                                      int *scol, double *sa) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= rn || !rf[i]) return;
+  int p = sr[rm[i]];
+  const int end = ro[i + 1];
+  for (int base = ro[i]; base < end; base += 32) {
+    const int j = base + lane;
+    int c = 0;
+    bool keep = false;
+    if (j < end) { c = col[j]; keep = cf[c] != 0; }
+    const unsigned b = __ballot_sync(0xffffffffu, keep);
+    if (keep) { const int q = p + __popc(b & ((1u << lane) - 1u)); scol[q] = cm[c]; sa[q] = a[j]; }
+    p += __popc(b);
+  }
+}
+#endif
+
 Csr sub_mat(const Csr &A, const double *vr, const double *vc) {
   StageTimer st_("prim.sub_mat");
   const int rn = A.rn, cn = A.cn;
@@ -457,6 +508,14 @@ Csr sub_mat(const Csr &A, const double *vr, const double *vc) {
   Buf<int> cnt(subrn + 1);
   int *cntp = cnt.p;
   const int *rm = rmap.p, *cm = cmap.p;
+#ifndef AMGB_EMU
+  const bool warp_rows = rn > 0 && A.nnz > 12 * (i64)rn;
+  if (warp_rows) {
+    Context &c = ctx();
+    k_sub_mat_count<<<(rn + 7) / 8, 256, 0, c.stream>>>(rn, ro, col, rf, rm, cf, cntp);
+    c.launches++; post_launch("sub_mat_count");
+  } else
+#endif
   parallel_for(rn, [=] DEV(i64 i) {
     if (!rf[i]) return;
     int c = 0;
@@ -470,6 +529,14 @@ Csr sub_mat(const Csr &A, const double *vr, const double *vc) {
   const int *sr = S.ro.p;
   int *scol = S.col.p;
   double *sa = S.a.p;
+#ifndef AMGB_EMU
+  if (warp_rows) {
+    Context &c = ctx();
+    k_sub_mat_fill<<<(rn + 7) / 8, 256, 0, c.stream>>>(rn, ro, col, a, rf, rm, cf, cm, sr, scol, sa);
+    c.launches++; post_launch("sub_mat_fill");
+    return S;
+  }
+#endif
   parallel_for(rn, [=] DEV(i64 i) {
     if (!rf[i]) return;
     int p = sr[rm[i]];
@@ -691,18 +758,14 @@ Csr coo_to_csr(i64 n, const int *Ai, const int *Aj, const double *Av, int rn, in
 // diagonal helpers
 // ---------------------------------------------------------------------------------------
 void diag_of(double *D, const Csr &A) {
-  const int *ro = A.ro.p, *col = A.col.p;
+  const int *col = A.col.p;
   const double *a = A.a.p;
-  parallel_for(A.rn, [=] DEV(i64 i) {
-    double d = 0.;
-    for (int j = ro[i]; j < ro[i + 1]; j++) if (col[j] == i) { d = a[j]; break; }
-    D[i] = d;
-  });
+  fill(D, A.rn, 0.);                              // rows without a diagonal entry (columns are unique inside a row)
+  for_row_entries(A, [=] DEV(int i, int j) { if (col[j] == i) D[i] = a[j]; });
 }
 void scale_rows(Csr &A, const double *D) {
-  const int *ro = A.ro.p;
   double *a = A.a.p;
-  parallel_for(A.rn, [=] DEV(i64 i) { for (int j = ro[i]; j < ro[i + 1]; j++) a[j] = a[j] * D[i]; });
+  for_row_entries(A, [=] DEV(int i, int j) { a[j] = a[j] * D[i]; });
 }
 void scale_cols(Csr &A, const double *D) {
   const int *col = A.col.p;
@@ -710,11 +773,9 @@ void scale_cols(Csr &A, const double *D) {
   parallel_for(A.nnz, [=] DEV(i64 e) { a[e] = a[e] * D[col[e]]; });
 }
 void sub_diag(Csr &A, const double *D) {
-  const int *ro = A.ro.p, *col = A.col.p;
+  const int *col = A.col.p;
   double *a = A.a.p;
-  parallel_for(A.rn, [=] DEV(i64 i) {
-    for (int j = ro[i]; j < ro[i + 1]; j++) if (col[j] == i) { a[j] = a[j] - D[i]; break; }
-  });
+  for_row_entries(A, [=] DEV(int i, int j) { if (col[j] == i) a[j] = a[j] - D[i]; });
 }
 void col_sums(double *s, const Csr &A) {
   Csr T = transpose(A);
