@@ -802,10 +802,15 @@ void build_q_store(QStore &qs, const Csr &Wt, const Csr &At) {
   q_offsets(qs, Wt);
   const int n = Wt.rn;
   if (n == 0) return;
-  // bin the columns by support size: <=8 | <=32 | <=64 | <=144 | larger.  The block size and the
-  // shared-memory footprint follow the bin, so that small supports do not pay the occupancy of
-  // the largest one.
-  constexpr int NBIN = 6;
+  // bin the columns by support size.  The block size and the shared-memory footprint follow the
+  // bin, so that small supports do not pay the occupancy of the largest one: the builders are
+  // chains of dependent additions with five barriers per step, i.e. bound by latency, and what
+  // hides latency is the number of columns resident per SM (a triangle of 144 rows is 86 KB: two
+  // blocks per SM; of 96 rows 39 KB: five).
+  //   0: <=8 (8-thread tiles) | 1..NSM: Q in shared memory, caps below | B_HBM: <=256, Q in HBM/L2 |
+  //   B_BIG: larger
+  constexpr int NSM = 7, B_HBM = NSM + 1, B_BIG = NSM + 2, NBIN = NSM + 3;
+  const int caps[NSM] = {32, 48, 64, 80, 96, 112, 144}, threads[NSM] = {32, 64, 64, 128, 128, 128, 128};
   Buf<int> lists((i64)NBIN * n), cnt(NBIN);
   cnt.zero();
   const int *wro = Wt.ro.p;
@@ -822,7 +827,8 @@ void build_q_store(QStore &qs, const Csr &Wt, const Csr &At) {
     const i64 i = c0 + ii;
     const int nz = wro[i + 1] - wro[i];
     if (nz == 0 || nz > bignz) return;
-    const int bin = nz <= 8 ? 0 : small ? (nz <= 12 ? 4 : 5) : nz <= 32 ? 1 : nz <= 64 ? 2 : nz <= 144 ? 3 : nz <= 256 ? 4 : 5;
+    const int bin = nz <= 8 ? 0 : small ? (nz <= 12 ? B_HBM : B_BIG) : nz <= 32 ? 1 : nz <= 48 ? 2 : nz <= 64 ? 3 : nz <= 80 ? 4 :
+                    nz <= 96 ? 5 : nz <= 112 ? 6 : nz <= 144 ? 7 : nz <= 256 ? B_HBM : B_BIG;
     const int p = atomic_add(&cp[bin], 1);
     lp[(i64)bin * n + p] = (int)i;
   });
@@ -835,19 +841,19 @@ void build_q_store(QStore &qs, const Csr &Wt, const Csr &At) {
   {
     static int logit = -1;
     if (logit < 0) { const char *e = getenv("AMGB_Q_LOG"); logit = (e && *e && *e != '0') ? 1 : 0; }
-    if (logit) fprintf(stderr, "build_q: columns %d  maxnz %d  Q entries %lld | bins(<=8,32,64,144,256,more) %d %d %d %d %d %d\n",
-                       n, qs.maxnz, (long long)qs.total, hc[0], hc[1], hc[2], hc[3], hc[4], hc[5]);
+    if (logit) fprintf(stderr, "build_q: columns %d  maxnz %d  Q entries %lld | bins(<=8,32,48,64,80,96,112,144,256,more) %d %d %d %d %d %d %d %d %d %d\n",
+                       n, qs.maxnz, (long long)qs.total, hc[0], hc[1], hc[2], hc[3], hc[4], hc[5], hc[6], hc[7], hc[8], hc[9]);
   }
   // columns with more than 256 rows: a handful (the column-0 pile of the reference) goes to the
   // cluster kernel on a second stream, next to the other bins; many of them are better off as one
   // block each, like the bin below
-  const bool big_cluster = hc[5] > 0 && hc[5] <= 32;
+  const bool big_cluster = hc[B_BIG] > 0 && hc[B_BIG] <= 32;
   static cudaStream_t aux = nullptr;
   static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   Buf<double> scratch;
-  if (hc[5] && qs.maxnz_small > 12800) throw Error(-12, "interpolation support of " + std::to_string(qs.maxnz_small) + " rows exceeds the kernel limit (12800)");
-  if (hc[5]) {
-    k_gram_fill_big<<<dim3(hc[5], 64), 256, 0, c.stream>>>(lp + 5 * (i64)n, wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
+  if (hc[B_BIG] && qs.maxnz_small > 12800) throw Error(-12, "interpolation support of " + std::to_string(qs.maxnz_small) + " rows exceeds the kernel limit (12800)");
+  if (hc[B_BIG]) {
+    k_gram_fill_big<<<dim3(hc[B_BIG], 64), 256, 0, c.stream>>>(lp + B_BIG * (i64)n, wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
     c.launches++; post_launch("gram_fill_big");
   }
   if (big_cluster) {
@@ -856,23 +862,23 @@ void build_q_store(QStore &qs, const Csr &Wt, const Csr &At) {
       CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
       CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     }
-    scratch.alloc((i64)hc[5] * (2 * (i64)qs.maxnz_small + tri(qs.maxnz_small)));
+    scratch.alloc((i64)hc[B_BIG] * (2 * (i64)qs.maxnz_small + tri(qs.maxnz_small)));
     const size_t sm = sizeof(double) * 2 * (size_t)qs.maxnz_small;
     static size_t sm_set = 48 * 1024;
     if (sm > sm_set) { set_smem((const void *)k_build_q_cluster, sm); sm_set = sm; }
     CUDA_CHECK(cudaEventRecord(ev_fork, c.stream));
     CUDA_CHECK(cudaStreamWaitEvent(aux, ev_fork, 0));
-    k_build_q_cluster<<<hc[5] * 8, 256, sm, aux>>>(lp + 5 * (i64)n, hc[5], qs.maxnz_small, wro, qs.Q.p, qs.qoff.p, scratch.p);
+    k_build_q_cluster<<<hc[B_BIG] * 8, 256, sm, aux>>>(lp + B_BIG * (i64)n, hc[B_BIG], qs.maxnz_small, wro, qs.Q.p, qs.qoff.p, scratch.p);
     c.launches++; post_launch("build_q_cluster");
     CUDA_CHECK(cudaEventRecord(ev_join, aux));
-  } else if (hc[5]) {
+  } else if (hc[B_BIG]) {
     const size_t sm = sizeof(double) * 2 * (size_t)qs.maxnz_small;
     static size_t sm_set = 48 * 1024;
     if (sm > sm_set) { set_smem((const void *)k_build_q_block<false>, sm); sm_set = sm; }
-    k_build_q_block<false><<<hc[5], 256, sm, c.stream>>>(lp + 5 * (i64)n, hc[5], qs.maxnz_small, wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
+    k_build_q_block<false><<<hc[B_BIG], 256, sm, c.stream>>>(lp + B_BIG * (i64)n, hc[B_BIG], qs.maxnz_small, wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
     c.launches++; post_launch("build_q_global_big");
   }
-  for (int b = 0; b < 5; b++) {
+  for (int b = 0; b < B_BIG; b++) {
     if (!hc[b]) continue;
     k_gram_fill<<<(hc[b] + 7) / 8, 256, 0, c.stream>>>(lp + (i64)b * n, hc[b], wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
     c.launches++; post_launch("gram_fill");
@@ -881,17 +887,16 @@ void build_q_store(QStore &qs, const Csr &Wt, const Csr &At) {
     k_build_q_tile8<8><<<(hc[0] + 31) / 32, 256, 0, c.stream>>>(lp, hc[0], wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
     c.launches++; post_launch("build_q_tile8");
   }
-  const int caps[3] = {32, 64, 144}, threads[3] = {32, 64, 128};
-  for (int b = 0; b < 3; b++) {
+  for (int b = 0; b < NSM; b++) {
     if (!hc[b + 1]) continue;
     const size_t sm = sizeof(double) * (2 * caps[b] + tri(caps[b]));
     k_build_q_block<true><<<hc[b + 1], threads[b], sm, c.stream>>>(lp + (i64)(b + 1) * n, hc[b + 1], caps[b], wro, wcol, aro,
                                                                    acol, aa, qs.Q.p, qs.qoff.p);
     c.launches++; post_launch("build_q_block");
   }
-  if (hc[4]) {
+  if (hc[B_HBM]) {
     const size_t sm = sizeof(double) * (2 * (size_t)256);
-    k_build_q_block<false><<<hc[4], 256, sm, c.stream>>>(lp + 4 * (i64)n, hc[4], 256, wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
+    k_build_q_block<false><<<hc[B_HBM], 256, sm, c.stream>>>(lp + B_HBM * (i64)n, hc[B_HBM], 256, wro, wcol, aro, acol, aa, qs.Q.p, qs.qoff.p);
     c.launches++; post_launch("build_q_global");
   }
   // huge supports: one column at a time, the whole GPU on each (this rank's columns only)
@@ -987,6 +992,13 @@ __device__ __forceinline__ double qq_pair(const double *Q, int m, int j, int k0,
   }
   return acc;
 }
+// p = tri(j) + m with 0 <= m <= j
+__device__ __forceinline__ void tri_index(i64 p, int &j, int &m) {
+  i64 jj = (i64)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+  while (tri(jj + 1) <= p) jj++;
+  while (tri(jj) > p) jj--;
+  j = (int)jj; m = (int)(p - tri(jj));
+}
 // ---- QQ^t: one block per column (one warp for small ones), pairs (m<=j) over threads ----
 __global__ void __launch_bounds__(128) k_form_qq(int n, const int *wro, const double *Qall, const i64 *qoff,
                                                  double *QQ, const i64 *qqoff, int bignz, int batch) {
@@ -996,9 +1008,13 @@ __global__ void __launch_bounds__(128) k_form_qq(int n, const int *wro, const do
   if (nz > 192 || nz > bignz) return;         // done by k_form_qq_big / k_form_qq_huge
   const double *Q = Qall + qoff[i];
   double *out = QQ + qqoff[i];
-  for (int idx = threadIdx.x; idx < nz * nz; idx += blockDim.x) {
-    const int m = idx / nz, j = idx - m * nz;
-    if (m > j) continue;
+  // the pairs (m <= j) enumerated along the packed triangle, p = tri(j) + m: neighbouring threads
+  // share j (same chain length, Q[tri(k)+j] is a broadcast) and read neighbouring Q[tri(k)+m];
+  // no thread idles on the m > j half of the square
+  const int T = (int)tri(nz);
+  for (int p = threadIdx.x; p < T; p += blockDim.x) {
+    int j, m;
+    tri_index(p, j, m);
     double acc = 0;
     if (batch) acc = qq_pair(Q, m, j, j, nz);
     else for (int k = j; k < nz; k++) acc = acc + Q[tri(k) + m] * Q[tri(k) + j];
@@ -1031,10 +1047,10 @@ __global__ void __launch_bounds__(256) k_form_qq_big(const int *list, const int 
   const int nz = wro[i + 1] - wro[i];
   const double *Q = Qall + qoff[i];
   double *out = QQ + qqoff[i];
-  const i64 total = (i64)nz * nz;
+  const i64 total = tri(nz);
   for (i64 idx = (i64)blockIdx.y * blockDim.x + threadIdx.x; idx < total; idx += (i64)gridDim.y * blockDim.x) {
-    const int m = (int)(idx / nz), j = (int)(idx - (i64)m * nz);
-    if (m > j) continue;
+    int j, m;
+    tri_index(idx, j, m);
     double acc = 0;
     for (int k = j; k < nz; k++) acc = acc + Q[tri(k) + m] * Q[tri(k) + j];
     out[(i64)m * nz + j] = acc;

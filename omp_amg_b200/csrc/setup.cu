@@ -415,7 +415,7 @@ void solve_weights(Csr &W, Csr &W0, double *lam, const Csr &Wsk, const Csr &Af, 
 // is order-free -- and removes that entry from R and R'.
 __global__ void __launch_bounds__(256) k_find_support_cols(int nc, const int *tro, const int *tcol, double *rtv,
                                                            const double *rs, const double *w, double thr, int *alive,
-                                                           double *rv, const int *src, int *skel) {
+                                                           double *rv, const int *src, int *skel, int *gen, int next) {
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (c >= nc) return;
   const int lane = threadIdx.x & 31;
@@ -441,6 +441,7 @@ __global__ void __launch_bounds__(256) k_find_support_cols(int nc, const int *tr
   if (lane == 0 && arg != 0x7fffffff) {
     alive[arg] = 0; rtv[arg] = 0.0;
     rv[src[arg]] = 0.0; skel[src[arg]] = 1;
+    gen[tcol[arg]] = next;                        // row tcol[arg] of R lost an entry: its sum is redone next round
   }
 }
 
@@ -449,7 +450,8 @@ __global__ void __launch_bounds__(256) k_find_support_cols(int nc, const int *tr
 // ~100 dependent gather rounds.
 __global__ void __launch_bounds__(256) k_find_support_cols_block(int nc, const int *tro, const int *tcol, double *rtv,
                                                                  const double *rs, const double *w, double thr,
-                                                                 int *alive, double *rv, const int *src, int *skel) {
+                                                                 int *alive, double *rv, const int *src, int *skel,
+                                                                 int *gen, int next) {
   __shared__ double sbest[8];
   __shared__ int sarg[8], sany[8];
   const int c = blockIdx.x;
@@ -487,6 +489,7 @@ __global__ void __launch_bounds__(256) k_find_support_cols_block(int nc, const i
     if (a_any && arg != 0x7fffffff) {
       alive[arg] = 0; rtv[arg] = 0.0;
       rv[src[arg]] = 0.0; skel[src[arg]] = 1;
+      gen[tcol[arg]] = next;
     }
   }
 }
@@ -550,15 +553,21 @@ Csr find_support(const Csr &R, Csr &Rt, Buf<int> &tpos, double goal) {   // Rt =
   skel.zero();
   fill_int(alive_t.p, R.nnz, 1);
   { int *s = src.p; const int *tp = tpos.p; parallel_for(R.nnz, [=] DEV(i64 e) { s[tp[e]] = (int)e; }); }
-  Buf<double> rs(nf), tmp(nf), onec(nc), w(nc), w2(nc), v(nc);
-  fill(onec.p, nc, 1.);
+  Buf<double> rs(nf), tmp(nf), w(nc), w2(nc), v(nc);
+  // rs = R*1 changes only in the rows that lost an entry in the round before: gen[i] is the round
+  // in which row i has to be summed again (round 0: every row); the other rows keep their sum,
+  // which a full recomputation would reproduce bit for bit
+  Buf<int> gen(nf);
+  gen.zero();
+  int *genp = gen.p;
+  int round = 0;
   double theta = 0.5;
   double *rvp = rv.p, *rtv = Rt.a.p, *rsp = rs.p, *wp = w.p, *w2p = w2.p, *vp = v.p;
   const int *tro = Rt.ro.p, *tcol = Rt.col.p, *srcp = src.p;
   int *skp = skel.p, *alp = alive_t.p;
   int guard = 0;
   for (;;) {
-    spmv_vals(rsp, 0., nullptr, 1., R, rvp, onec.p);
+    spmv_vals(rsp, 0., nullptr, 1., R, rvp, nullptr, nullptr, genp, round);      // x = ones, rows of this round
     spmv_vals(wp, 0., nullptr, 1., Rt, rtv, rsp);
     spmv_vals(tmp.p, 0., nullptr, 1., R, rvp, wp);
     spmv_vals(w2p, 0., nullptr, 1., Rt, rtv, tmp.p);
@@ -589,18 +598,20 @@ Csr find_support(const Csr &R, Csr &Rt, Buf<int> &tpos, double goal) {   // Rt =
       if (arg < 0) return;
       alp[arg] = 0; rtv[arg] = 0.0;
       rvp[srcp[arg]] = 0.0; skp[srcp[arg]] = 1;
+      genp[tcol[arg]] = round + 1;
     });
 #else
     {
       Context &cx = ctx();
       if (R.nnz > 512 * (i64)nc || test_small_bins())
-        k_find_support_cols_block<<<nc, 256, 0, cx.stream>>>(nc, tro, tcol, rtv, rsp, wp, thr, alp, rvp, srcp, skp);
+        k_find_support_cols_block<<<nc, 256, 0, cx.stream>>>(nc, tro, tcol, rtv, rsp, wp, thr, alp, rvp, srcp, skp, genp, round + 1);
       else
-        k_find_support_cols<<<(nc + 7) / 8, 256, 0, cx.stream>>>(nc, tro, tcol, rtv, rsp, wp, thr, alp, rvp, srcp, skp);
+        k_find_support_cols<<<(nc + 7) / 8, 256, 0, cx.stream>>>(nc, tro, tcol, rtv, rsp, wp, thr, alp, rvp, srcp, skp, genp, round + 1);
       cx.launches++; post_launch("find_support_cols");
     }
 #endif
     stage_count("find_support.rounds", 1);
+    round++;
     if (++guard > 100000) throw Error(-8, "find_support: no convergence");
   }
   // Skel = sparse(skel_i, skel_j, 1): the flagged entries, in place
@@ -781,11 +792,10 @@ Csr interpolation(const Csr &Af, const Csr &Ac, const Csr &Ar, double gamma2, do
     scale_cols(ArD, dci);
     Wsk = min_skel(ArD);
   }
-  Buf<double> lam(nf), alpha(nc), Dcsqrti(nc), w1(nc), w2(nc), ones(nc), r(nc);
+  Buf<double> lam(nf), alpha(nc), Dcsqrti(nc), w1(nc), w2(nc), r(nc);
   lam.zero();
   d2d(alpha.p, Dc.p, sizeof(double) * (size_t)nc);
   parallel_for(nf, [=] DEV(i64 i) { dfi[i] = sqrt(dfi[i]); });
-  fill(ones.p, nc, 1.0);
   Csr Armt = transpose(Ar);
   { double *a = Armt.a.p; parallel_for(Armt.nnz, [=] DEV(i64 e) { a[e] = a[e] * -1.0; }); }
   double *dsq = Dcsqrti.p, *w1p = w1.p, *w2p = w2.p, *rp = r.p, *alp = alpha.p;
@@ -831,7 +841,7 @@ Csr interpolation(const Csr &Af, const Csr &Ac, const Csr &Ar, double gamma2, do
     {
       StageTimer t_("ip.Rt_w1w2");
       Rt = transpose(R, &rtpos);
-      spmv(tmp.p, 0., nullptr, 1., R, ones.p);
+      spmv_vals(tmp.p, 0., nullptr, 1., R, R.a.p, nullptr);      // R * ones: row sums, nothing to gather
       spmv(w1p, 0., nullptr, 1., Rt, tmp.p);
       spmv(tmp.p, 0., nullptr, 1., R, w1p);
       spmv(w2p, 0., nullptr, 1., Rt, tmp.p);

@@ -26,17 +26,19 @@ void trace_csr(const char *tag, const Csr &A) {
 template <int G>
 __global__ void __launch_bounds__(256) k_spmv_tile(int rn, const int *ro, const int *col, const double *vals,
                                                    const double *x, double *z, double alpha, const double *y,
-                                                   double beta, bool plain, const double *post, int longrow) {
+                                                   double beta, bool plain, const double *post, int longrow,
+                                                   const int *gen, int want) {
   const int i = blockIdx.x * (256 / G) + threadIdx.x / G;
   if (i >= rn) return;
   if (ro[i + 1] - ro[i] > longrow) return;          // k_spmv_chain
+  if (gen && gen[i] != want) return;                // row unchanged since its last sum (find_support)
   const int lane = threadIdx.x % G;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
   const int end = ro[i + 1];
   double t = 0;
   for (int base = ro[i]; base < end; base += G) {
     const int j = base + lane;
-    const double p = (j < end) ? vals[j] * x[col[j]] : 0.0;
+    const double p = (j < end) ? (x ? vals[j] * x[col[j]] : vals[j] * 1.0) : 0.0;
     const int m = end - base;
     if (m >= G) {                          // full batch: straight line of G shuffles and adds
 #pragma unroll
@@ -58,18 +60,20 @@ __global__ void __launch_bounds__(256) k_spmv_tile(int rn, const int *ro, const 
 // then adds the 32 values in entry order.
 __global__ void __launch_bounds__(256) k_spmv_row32(int rn, const int *ro, const int *col, const double *vals,
                                                     const double *x, double *z, double alpha, const double *y,
-                                                    double beta, bool plain, const double *post, int longrow) {
+                                                    double beta, bool plain, const double *post, int longrow,
+                                                    const int *gen, int want) {
   __shared__ __align__(16) double buf[8][2][32];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.x * 8 + w;
   if (i >= rn) return;
   if (ro[i + 1] - ro[i] > longrow) return;          // k_spmv_chain
+  if (gen && gen[i] != want) return;
   const int end = ro[i + 1];
   double t = 0;
   int par = 0;
   for (int base = ro[i]; base < end; base += 32, par ^= 1) {
     const int j = base + lane;
-    const double p = (j < end) ? vals[j] * x[col[j]] : 0.0;
+    const double p = (j < end) ? (x ? vals[j] * x[col[j]] : vals[j] * 1.0) : 0.0;
     double *b = buf[w][par];
     b[lane] = p;
     __syncwarp();
@@ -101,13 +105,15 @@ __global__ void __launch_bounds__(256) k_spmv_row32(int rn, const int *ro, const
 template <int G, int U>
 __global__ void __launch_bounds__(256) k_spmv_pipe(int rn, const int *ro, const int *col, const double *vals,
                                                    const double *x, double *z, double alpha, const double *y,
-                                                   double beta, bool plain, const double *post, int longrow) {
+                                                   double beta, bool plain, const double *post, int longrow,
+                                                   const int *gen, int want) {
   constexpr int S = G * U;
   __shared__ __align__(16) double buf[256 / G][2][S];
   const int grp = threadIdx.x / G, lane = threadIdx.x % G;
   const int i = blockIdx.x * (256 / G) + grp;
   if (i >= rn) return;
   if (ro[i + 1] - ro[i] > longrow) return;          // k_spmv_chain
+  if (gen && gen[i] != want) return;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
   const int beg = ro[i], end = ro[i + 1];
   int c1[U], c2[U];
@@ -116,11 +122,11 @@ __global__ void __launch_bounds__(256) k_spmv_pipe(int rn, const int *ro, const 
   for (int u = 0; u < U; u++) {
     const int j1 = beg + u * G + lane, j2 = j1 + S;
     c1[u] = 0; v1[u] = 0.0; c2[u] = 0; v2[u] = 0.0;
-    if (j1 < end) { c1[u] = col[j1]; v1[u] = vals[j1]; }
-    if (j2 < end) { c2[u] = col[j2]; v2[u] = vals[j2]; }
+    if (j1 < end) { if (x) c1[u] = col[j1]; v1[u] = vals[j1]; }
+    if (j2 < end) { if (x) c2[u] = col[j2]; v2[u] = vals[j2]; }
   }
 #pragma unroll
-  for (int u = 0; u < U; u++) { x0[u] = (beg + u * G + lane < end) ? x[c1[u]] : 0.0; v0[u] = v1[u]; }
+  for (int u = 0; u < U; u++) { x0[u] = (beg + u * G + lane < end) ? (x ? x[c1[u]] : 1.0) : 0.0; v0[u] = v1[u]; }
   double t = 0;
   int par = 0;
   for (int base = beg; base < end; base += S, par ^= 1) {
@@ -130,10 +136,10 @@ __global__ void __launch_bounds__(256) k_spmv_pipe(int rn, const int *ro, const 
     // advance the pipeline: gather x for the next stage (its columns are here), fetch the stage after
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      x0[u] = (base + S + u * G + lane < end) ? x[c2[u]] : 0.0;
+      x0[u] = (base + S + u * G + lane < end) ? (x ? x[c2[u]] : 1.0) : 0.0;
       v0[u] = v2[u];
       const int j = base + 2 * S + u * G + lane;
-      if (j < end) { c2[u] = col[j]; v2[u] = vals[j]; }
+      if (j < end) { if (x) c2[u] = col[j]; v2[u] = vals[j]; }
     }
     __syncwarp(gmask);
     const int m = end - base;
@@ -171,14 +177,14 @@ __global__ void __launch_bounds__(256) k_spmv_chain(const int *rows, const int *
     const int beg = ro[i], end = ro[i + 1];
     const int nch = (end - beg + SPMV_CH - 1) / SPMV_CH;
     __syncthreads();
-    for (int j = beg + t; j < end && j < beg + SPMV_CH; j += 256) buf[0][j - beg] = vals[j] * x[col[j]];
+    for (int j = beg + t; j < end && j < beg + SPMV_CH; j += 256) buf[0][j - beg] = x ? vals[j] * x[col[j]] : vals[j] * 1.0;
     double r = 0;
     for (int c = 0; c < nch; c++) {
       __syncthreads();
       const int cur = c & 1;
       if (t >= 32) {
         const int b0 = beg + (c + 1) * SPMV_CH;
-        for (int j = b0 + (t - 32); j < end && j < b0 + SPMV_CH; j += 224) buf[cur ^ 1][j - b0] = vals[j] * x[col[j]];
+        for (int j = b0 + (t - 32); j < end && j < b0 + SPMV_CH; j += 224) buf[cur ^ 1][j - b0] = x ? vals[j] * x[col[j]] : vals[j] * 1.0;
       } else if (t == 0) {
         const int b0 = beg + c * SPMV_CH;
         const int len = min(SPMV_CH, end - b0);
@@ -213,9 +219,9 @@ __global__ void __launch_bounds__(256) k_find_long_rows(int rn, const int *ro, i
 #endif
 
 static void spmv_vals_run(double *z, double alpha, const double *y, double beta, const Csr &M, const double *vals,
-                          const double *x, const double *post);
+                          const double *x, const double *post, const int *gen, int want);
 void spmv_vals(double *z, double alpha, const double *y, double beta, const Csr &M, const double *vals,
-               const double *x, const double *post) {
+               const double *x, const double *post, const int *gen, int want) {
 #ifndef AMGB_EMU
   static int logit = -1;
   if (logit < 0) { const char *e = getenv("AMGB_SPMV_LOG"); logit = (e && *e && *e != '0') ? 1 : 0; }
@@ -224,7 +230,7 @@ void spmv_vals(double *z, double alpha, const double *y, double beta, const Csr 
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, c.stream);
-    spmv_vals_run(z, alpha, y, beta, M, vals, x, post);
+    spmv_vals_run(z, alpha, y, beta, M, vals, x, post, gen, want);
     cudaEventRecord(e1, c.stream);
     cudaEventSynchronize(e1);
     float ms = 0;
@@ -235,10 +241,10 @@ void spmv_vals(double *z, double alpha, const double *y, double beta, const Csr 
     return;
   }
 #endif
-  spmv_vals_run(z, alpha, y, beta, M, vals, x, post);
+  spmv_vals_run(z, alpha, y, beta, M, vals, x, post, gen, want);
 }
 static void spmv_vals_run(double *z, double alpha, const double *y, double beta, const Csr &M, const double *vals,
-                          const double *x, const double *post) {
+                          const double *x, const double *post, const int *gen, int want) {
   StageTimer st_("prim.spmv");
   const int *ro = M.ro.p, *col = M.col.p;
   const bool plain = (alpha == 0. || y == nullptr);
@@ -278,15 +284,15 @@ static void spmv_vals_run(double *z, double alpha, const double *y, double beta,
     static int spmv_kind = -1;
     if (spmv_kind < 0) { const char *e = getenv("AMGB_SPMV"); spmv_kind = (e && !strcmp(e, "row32")) ? 0 : (e && !strcmp(e, "pipe16")) ? 1 : (e && !strcmp(e, "pipe16x2")) ? 3 : 2; }
     if ((double)M.nnz / (double)M.rn <= 64.0 && !test_small_bins())
-      k_spmv_tile<8><<<(M.rn + 31) / 32, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow);
+      k_spmv_tile<8><<<(M.rn + 31) / 32, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow, gen, want);
     else if (spmv_kind == 0)
-      k_spmv_row32<<<(M.rn + 7) / 8, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow);
+      k_spmv_row32<<<(M.rn + 7) / 8, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow, gen, want);
     else if (spmv_kind == 3 && !((double)M.nnz / (double)M.rn >= 2048.0 && M.rn >= 2048))
-      k_spmv_pipe<16, 2><<<(M.rn + 15) / 16, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow);
+      k_spmv_pipe<16, 2><<<(M.rn + 15) / 16, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow, gen, want);
     else if (spmv_kind == 1 || (spmv_kind == 2 && !((double)M.nnz / (double)M.rn >= 2048.0 && M.rn >= 2048) && !test_small_bins()))
-      k_spmv_pipe<16, 1><<<(M.rn + 15) / 16, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow);
+      k_spmv_pipe<16, 1><<<(M.rn + 15) / 16, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow, gen, want);
     else
-      k_spmv_pipe<8, 4><<<(M.rn + 31) / 32, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow);
+      k_spmv_pipe<8, 4><<<(M.rn + 31) / 32, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow, gen, want);
     c.launches++; post_launch("spmv_tile");
     done = true;
   }
@@ -294,8 +300,10 @@ static void spmv_vals_run(double *z, double alpha, const double *y, double beta,
 #endif
   parallel_for(M.rn, [=] DEV(i64 i) {
     if (ro[i + 1] - ro[i] > longrow) return;
+    if (gen && gen[i] != want) return;
     double t = 0;
-    for (int j = ro[i]; j < ro[i + 1]; j++) t = t + vals[j] * x[col[j]];
+    if (x) for (int j = ro[i]; j < ro[i + 1]; j++) t = t + vals[j] * x[col[j]];
+    else for (int j = ro[i]; j < ro[i + 1]; j++) t = t + vals[j] * 1.0;
     double r = plain ? beta * t : alpha * y[i] + beta * t;
     if (post) r = r * post[i];
     z[i] = r;

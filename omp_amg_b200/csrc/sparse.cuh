@@ -38,7 +38,9 @@ struct Csr {
 void spmv(double *z, double alpha, const double *y, double beta, const Csr &M, const double *x);
 // values-only variant: same pattern as M, other value array
 void spmv_vals(double *z, double alpha, const double *y, double beta, const Csr &M, const double *vals,
-               const double *x, const double *post = nullptr);   // post != null: z[i] = (...) * post[i]
+               const double *x, const double *post = nullptr,    // post != null: z[i] = (...) * post[i]
+               const int *gen = nullptr, int want = 0);          // gen != null: only rows with gen[i] == want
+// x == null stands for a vector of ones (row sums: no column is read, nothing is gathered)
 
 // transpose :2000.  If tpos != null it receives, for every entry e of A, its position in A^t.
 Csr transpose(const Csr &A, Buf<int> *tpos = nullptr);
