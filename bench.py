@@ -198,10 +198,13 @@ def golden_hash(workload, n):
         return None
 
 
-def run_solve(args, L, api, torch, dist, rank, world, local, dev, barrier):
-    """--metric solve: V-cycles per second on the resident hierarchy (amg_exec, amg.c:114).  Every
-    rank holds the hierarchy and applies the cycle to its own right-hand sides, so
-    N ranks are N independent solve streams (weak scaling); value = cycles/s over all ranks."""
+def run_solve(args, L, api, torch, dist, rank, world, local, dev, barrier, partitioned=False):
+    """--metric solve: V-cycles per second on the resident hierarchy (amg_exec, amg.c:114).
+    N > 1, --parallel partitioned (default): the ranks apply ONE cycle together -- the matrix-vector
+    products of the large levels are row-partitioned, the result vectors exchanged over NCCL
+    (solve.cu: spmv_dist) -- so total work is fixed (strong scaling) and value = cycles/s of that one
+    stream; the solution is bit-identical to one GPU's (solution_norm).  --parallel replicas: every
+    rank applies the cycle to its own right-hand sides, N independent streams (weak scaling)."""
     dAi, dAj, dAv, nnz, rows = dev
     H = api.amg_setup(dAi.data_ptr(), dAj.data_ptr(), dAv.data_ptr(), L=L, device_ptrs=True, nnz=nnz)
     n0 = H.level_info(0)["n"]
@@ -239,15 +242,23 @@ def run_solve(args, L, api, torch, dist, rank, world, local, dev, barrier):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     wall, e2e = float(tt[0]), float(tt[1])
     cyc = wall / (args.steps * reps)
+    streams = 1 if partitioned else world
+    import ctypes
+    cc, cb = ctypes.c_int64(), ctypes.c_int64()
+    L.amgb_comm_stats(ctypes.byref(cc), ctypes.byref(cb))
     if rank == 0:
         peak, peak_src = load_peaks()
         ach = bytes_cycle / cyc / 1e9
-        line = {"metric": "amg_vcycles_per_s", "value": world / cyc, "unit": "cycles/s", "n_gpus": world, "steps": args.steps,
+        world_ = world
+        world = streams
+        line = {"metric": "amg_vcycles_per_s", "value": world / cyc, "unit": "cycles/s", "n_gpus": world_, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": cyc * reps * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "scaling": "strong" if partitioned else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "%s_%d^3_vcycle" % (args.workload, args.n), "rows": rows, "levels": H.nlevels,
                            "cycles_per_step": reps, "l2": "hierarchy_exceeds_l2" if bytes_cycle > 126e6 else "fits_l2",
-                           "parallelism": "independent_solve_streams_x%d" % world},
+                           "parallelism": ("row_partitioned_vcycle_x%d" % world_) if partitioned else "independent_solve_streams_x%d" % world_},
+                "comm": {"exchanges_since_setup": int(cc.value), "bytes_received_per_rank": int(cb.value),
+                         "transport": "nccl grouped broadcast (all-gather of the row blocks of the result vectors)"},
                 "ms_per_cycle": cyc * 1e3, "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": world / e2e, "unit": "cycles/s", "h2d_bytes_per_step": 8 * n0, "d2h_bytes_per_step": 8 * n0},
                 "roofline": {"bound": "hbm", "kernel": "V-cycle (SpMV with W', W, AfP, Af and the vector updates of every level)",
@@ -344,7 +355,7 @@ def main():
         return meta, hs
 
     if args.metric == "solve":
-        run_solve(args, L, api, torch, dist, rank, world, local, (dAi, dAj, dAv, nnz, rows), barrier)
+        run_solve(args, L, api, torch, dist, rank, world, local, (dAi, dAj, dAv, nnz, rows), barrier, partitioned=partitioned)
         if world > 1:
             if partitioned:
                 api.comm_finalize(L)

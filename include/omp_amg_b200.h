@@ -80,6 +80,10 @@ int amgb_timing(const amgb_hier *h, double t[16]);
  * SpGEMM rows (mxm, amg_setup.c:1894) and the local solves of the coarse columns (interp,
  * amg_setup.c:2053) are partitioned over the ranks and the blocks are exchanged through NCCL
  * (NVLink), so that every rank ends with the same hierarchy, bit-identical to one GPU's.
+ * amgb_solve / crs_amg_solve on several ranks (same b on every rank) row-partition the
+ * matrix-vector products of the large levels of the V-cycle (amg.c:114; the reference applies its
+ * distributed matrices the same way, with gs halo exchanges amg.c:85-112) and exchange the blocks
+ * of the result vectors; the solution is bit-identical to one GPU's on every rank.
  * Rank 0 obtains an id (amgb_comm_unique_id), the host program hands it to the other ranks
  * (MPI_Bcast / torch.distributed), then every rank calls amgb_comm_init on its own device.
  * amgb_comm_init_host installs a host transport instead and exists only in the host-emulation
@@ -92,6 +96,9 @@ int amgb_comm_init_host(int rank, int size, amgb_allgatherv_fn fn, void *user);
 int amgb_comm_finalize(void);
 int amgb_comm_rank(void);
 int amgb_comm_size(void);
+/* exchanges issued and bytes received by this rank since the last amgb_setup (setup stages and
+ * the row-partitioned V-cycles after it; amgb_setup resets the counters) */
+int amgb_comm_stats(int64_t *calls, int64_t *bytes);
 
 /* ---- device memory ----
  * Temporaries come from a caching allocator inside the library; amgb_release_memory() hands the

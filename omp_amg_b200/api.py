@@ -86,6 +86,7 @@ def _declare(L):
     L.amgb_comm_unique_id.argtypes = [C.c_char_p]
     L.amgb_comm_init.argtypes = [C.c_int, C.c_int, C.c_char_p]
     L.amgb_comm_init_host.argtypes = [C.c_int, C.c_int, ALLGATHERV_FN, vp]
+    L.amgb_comm_stats.argtypes = [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     return L
 
 

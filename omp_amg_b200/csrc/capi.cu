@@ -390,6 +390,16 @@ int amgb_comm_finalize(void) {
 }
 int amgb_comm_rank(void) { return comm_rank(); }
 int amgb_comm_size(void) { return comm_size(); }
+int amgb_comm_stats(int64_t *calls, int64_t *bytes) {
+  API_BEGIN
+  i64 c = 0, b = 0;
+  double s = 0;
+  comm_stats_get(&c, &b, &s);
+  if (calls) *calls = c;
+  if (bytes) *bytes = b;
+  return 0;
+  API_END
+}
 
 int64_t amgb_launch_count(void) { return (int64_t)ctx().launches; }
 int64_t amgb_sync_count(void) { return (int64_t)ctx().syncs; }

@@ -133,7 +133,7 @@ void comm_init_host(int rank, int size, host_allgatherv_fn fn, void *user) {
 #endif
 }
 
-void comm_allgatherv(void *buf, const i64 *off, const char *what) {
+void comm_allgatherv(void *buf, const i64 *off, const char *what, bool timed) {
   const int P = g_comm.size;
   if (P <= 1) return;
   StageTimer st_(what);      // AMGB_STAGE_LOG: time waiting for + inside the exchange, per call site
@@ -146,9 +146,9 @@ void comm_allgatherv(void *buf, const i64 *off, const char *what) {
     cudaEvent_t a = nullptr, b = nullptr;
     ~Pair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
   } ev;
-  CUDA_CHECK(cudaEventCreate(&ev.a)); CUDA_CHECK(cudaEventCreate(&ev.b));
+  if (timed) { CUDA_CHECK(cudaEventCreate(&ev.a)); CUDA_CHECK(cudaEventCreate(&ev.b)); }
   cudaEvent_t e0 = ev.a, e1 = ev.b;
-  CUDA_CHECK(cudaEventRecord(e0, c.stream));
+  if (timed) CUDA_CHECK(cudaEventRecord(e0, c.stream));
   nccl_check(g_nccl.GroupStart(), "ncclGroupStart");
   for (int r = 0; r < P; r++) {
     const i64 n = off[r + 1] - off[r];
@@ -157,9 +157,11 @@ void comm_allgatherv(void *buf, const i64 *off, const char *what) {
     nccl_check(g_nccl.Broadcast(seg, seg, (size_t)n, /*ncclChar*/ 0, r, g_comm.nccl, c.stream), "ncclBroadcast");
   }
   nccl_check(g_nccl.GroupEnd(), "ncclGroupEnd");
-  CUDA_CHECK(cudaEventRecord(e1, c.stream));
-  g_comm.ev.emplace_back(e0, e1);
-  ev.a = ev.b = nullptr;
+  if (timed) {
+    CUDA_CHECK(cudaEventRecord(e1, c.stream));
+    g_comm.ev.emplace_back(e0, e1);
+    ev.a = ev.b = nullptr;
+  }
 #else
   std::vector<long long> o(off, off + P + 1);
   if (g_comm.host_fn(buf, o.data(), P, g_comm.host_user) != 0) throw Error(-113, "host transport failed");

@@ -21,7 +21,8 @@ i64 comm_min_work();
 
 // rank r owns bytes [off[r], off[r+1]) of buf (off has size+1 host entries); after the call
 // every rank holds all segments
-void comm_allgatherv(void *buf, const i64 *off, const char *what = "comm.exchange");
+// timed = false: no timing events (the V-cycle's vector exchanges: thousands per solve phase)
+void comm_allgatherv(void *buf, const i64 *off, const char *what = "comm.exchange", bool timed = true);
 
 // rows [row_split(r), row_split(r+1)) of an n-row stage belong to rank r
 inline i64 row_split(i64 n, int r) { return n * r / comm_size(); }

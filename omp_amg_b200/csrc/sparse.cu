@@ -168,12 +168,14 @@ __global__ void __launch_bounds__(256) k_spmv_pipe(int rn, const int *ro, const 
 #define SPMV_CH 2048
 __global__ void __launch_bounds__(256) k_spmv_chain(const int *rows, const int *nrows, const int *ro, const int *col,
                                                     const double *vals, const double *x, double *z, double alpha,
-                                                    const double *y, double beta, bool plain, const double *post) {
+                                                    const double *y, double beta, bool plain, const double *post,
+                                                    int r0, int r1) {
   __shared__ double buf[2][SPMV_CH];
   const int t = threadIdx.x;
   const int n = *nrows;
   for (int q = blockIdx.x; q < n; q += gridDim.x) {
     const int i = rows[q];
+    if (i < r0 || i >= r1) continue;              // another rank's row block (block-uniform)
     const int beg = ro[i], end = ro[i + 1];
     const int nch = (end - beg + SPMV_CH - 1) / SPMV_CH;
     __syncthreads();
@@ -219,7 +221,10 @@ __global__ void __launch_bounds__(256) k_find_long_rows(int rn, const int *ro, i
 #endif
 
 static void spmv_vals_run(double *z, double alpha, const double *y, double beta, const Csr &M, const double *vals,
-                          const double *x, const double *post, const int *gen, int want);
+                          const double *x, const double *post, const int *gen, int want, int r0, int r1);
+void spmv_rows(double *z, double alpha, const double *y, double beta, const Csr &M, const double *x, int r0, int r1) {
+  if (r1 > r0) spmv_vals_run(z, alpha, y, beta, M, M.a.p, x, nullptr, nullptr, 0, r0, r1);
+}
 void spmv_vals(double *z, double alpha, const double *y, double beta, const Csr &M, const double *vals,
                const double *x, const double *post, const int *gen, int want) {
 #ifndef AMGB_EMU
@@ -230,7 +235,7 @@ void spmv_vals(double *z, double alpha, const double *y, double beta, const Csr 
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, c.stream);
-    spmv_vals_run(z, alpha, y, beta, M, vals, x, post, gen, want);
+    spmv_vals_run(z, alpha, y, beta, M, vals, x, post, gen, want, 0, M.rn);
     cudaEventRecord(e1, c.stream);
     cudaEventSynchronize(e1);
     float ms = 0;
@@ -241,12 +246,18 @@ void spmv_vals(double *z, double alpha, const double *y, double beta, const Csr 
     return;
   }
 #endif
-  spmv_vals_run(z, alpha, y, beta, M, vals, x, post, gen, want);
+  spmv_vals_run(z, alpha, y, beta, M, vals, x, post, gen, want, 0, M.rn);
 }
-static void spmv_vals_run(double *z, double alpha, const double *y, double beta, const Csr &M, const double *vals,
-                          const double *x, const double *post, const int *gen, int want) {
+// rows [r0, r1) only (the V-cycle's row blocks, solve.cu): the kernels see the block as a matrix
+// of its own -- row offsets, z, y, post and gen shifted by r0; col/vals are indexed absolutely
+static void spmv_vals_run(double *zf, double alpha, const double *yf, double beta, const Csr &M, const double *vals,
+                          const double *x, const double *postf, const int *genf, int want, int r0, int r1) {
   StageTimer st_("prim.spmv");
-  const int *ro = M.ro.p, *col = M.col.p;
+  const int *ro = M.ro.p + r0, *col = M.col.p;
+  double *z = zf + r0;
+  const double *y = yf ? yf + r0 : nullptr, *post = postf ? postf + r0 : nullptr;
+  const int *gen = genf ? genf + r0 : nullptr;
+  const int rn = r1 - r0;
   const bool plain = (alpha == 0. || y == nullptr);
   int longrow = 0x7fffffff;
 #ifndef AMGB_EMU
@@ -262,7 +273,7 @@ static void spmv_vals_run(double *z, double alpha, const double *y, double beta,
       const int cap = M.rn < 16384 ? M.rn : 16384;
       M.long_rows.alloc((i64)cap + 1);
       dev_memset(M.long_rows.p + cap, 0, sizeof(int));
-      k_find_long_rows<<<(M.rn + 255) / 256, 256, 0, c.stream>>>(M.rn, ro, LR, cap, M.long_rows.p, M.long_rows.p + cap);
+      k_find_long_rows<<<(M.rn + 255) / 256, 256, 0, c.stream>>>(M.rn, M.ro.p, LR, cap, M.long_rows.p, M.long_rows.p + cap);
       c.launches++; post_launch("find_long_rows");
       int cnt = 0;
       d2h(&cnt, M.long_rows.p + cap, sizeof(int));
@@ -278,27 +289,27 @@ static void spmv_vals_run(double *z, double alpha, const double *y, double beta,
   static double t1 = -1;       // rows up to this average length: one thread per row (AMGB_SPMV_T1)
   if (t1 < 0) { const char *e = getenv("AMGB_SPMV_T1"); t1 = e ? atof(e) : 24.0; }
   bool done = false;
-  if (M.rn > 0 && (double)M.nnz / (double)M.rn > t1) {
+  if (rn > 0 && (double)M.nnz / (double)M.rn > t1) {
     // AMGB_SPMV=row32 | pipe16 | auto (default: 16 lanes per row, 8 lanes x 4 entries for a few
     // thousand rows of a few thousand entries; measured per matrix in profiles/r2_spmv_variants_poisson7_128.txt)
     static int spmv_kind = -1;
     if (spmv_kind < 0) { const char *e = getenv("AMGB_SPMV"); spmv_kind = (e && !strcmp(e, "row32")) ? 0 : (e && !strcmp(e, "pipe16")) ? 1 : (e && !strcmp(e, "pipe16x2")) ? 3 : 2; }
     if ((double)M.nnz / (double)M.rn <= 64.0 && !test_small_bins())
-      k_spmv_tile<8><<<(M.rn + 31) / 32, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow, gen, want);
+      k_spmv_tile<8><<<(rn + 31) / 32, 256, 0, c.stream>>>(rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow, gen, want);
     else if (spmv_kind == 0)
-      k_spmv_row32<<<(M.rn + 7) / 8, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow, gen, want);
+      k_spmv_row32<<<(rn + 7) / 8, 256, 0, c.stream>>>(rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow, gen, want);
     else if (spmv_kind == 3 && !((double)M.nnz / (double)M.rn >= 2048.0 && M.rn >= 2048))
-      k_spmv_pipe<16, 2><<<(M.rn + 15) / 16, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow, gen, want);
+      k_spmv_pipe<16, 2><<<(rn + 15) / 16, 256, 0, c.stream>>>(rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow, gen, want);
     else if (spmv_kind == 1 || (spmv_kind == 2 && !((double)M.nnz / (double)M.rn >= 2048.0 && M.rn >= 2048) && !test_small_bins()))
-      k_spmv_pipe<16, 1><<<(M.rn + 15) / 16, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow, gen, want);
+      k_spmv_pipe<16, 1><<<(rn + 15) / 16, 256, 0, c.stream>>>(rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow, gen, want);
     else
-      k_spmv_pipe<8, 4><<<(M.rn + 31) / 32, 256, 0, c.stream>>>(M.rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow, gen, want);
+      k_spmv_pipe<8, 4><<<(rn + 31) / 32, 256, 0, c.stream>>>(rn, ro, col, vals, x, z, alpha, y, beta, plain, post, longrow, gen, want);
     c.launches++; post_launch("spmv_tile");
     done = true;
   }
   if (!done)
 #endif
-  parallel_for(M.rn, [=] DEV(i64 i) {
+  parallel_for(rn, [=] DEV(i64 i) {
     if (ro[i + 1] - ro[i] > longrow) return;
     if (gen && gen[i] != want) return;
     double t = 0;
@@ -312,7 +323,7 @@ static void spmv_vals_run(double *z, double alpha, const double *y, double beta,
   if (M.n_long > 0) {
     const int cap = M.rn < 16384 ? M.rn : 16384;
     const int grid = M.n_long < c.sm_count * 6 ? M.n_long : c.sm_count * 6;
-    k_spmv_chain<<<grid, 256, 0, c.stream>>>(M.long_rows.p, M.long_rows.p + cap, ro, col, vals, x, z, alpha, y, beta, plain, post);
+    k_spmv_chain<<<grid, 256, 0, c.stream>>>(M.long_rows.p, M.long_rows.p + cap, M.ro.p, col, vals, x, zf, alpha, yf, beta, plain, postf, r0, r1);
     c.launches++; post_launch("spmv_chain");
   }
 #endif

@@ -36,6 +36,9 @@ struct Csr {
 
 // apply_M (amg_tools.c:71): z = alpha*y + beta*(M x); y may be null (then z = beta*(M x))
 void spmv(double *z, double alpha, const double *y, double beta, const Csr &M, const double *x);
+// rows [r0, r1) of the same product only (z, y indexed by absolute row): the row blocks of the
+// partitioned V-cycle
+void spmv_rows(double *z, double alpha, const double *y, double beta, const Csr &M, const double *x, int r0, int r1);
 // values-only variant: same pattern as M, other value array
 void spmv_vals(double *z, double alpha, const double *y, double beta, const Csr &M, const double *vals,
                const double *x, const double *post = nullptr,    // post != null: z[i] = (...) * post[i]

@@ -55,9 +55,10 @@ def test_max_over_ranks_reduction_gloo_world2():
 
 
 # ---------------------------------------------------------------------------------------
-# Row-partitioned setup on 2 and 3 ranks (DESIGN.md row e).  The host-emulation build runs the same
-# partitioning code as the product (spgemm_partitioned, q_partition) with a gloo transport in
-# place of NCCL; every rank must end with the hierarchy one rank builds, bit for bit.
+# Row-partitioned setup and V-cycle on 2, 3 and 4 ranks (DESIGN.md row e).  The host-emulation build
+# runs the same partitioning code as the product (spgemm_partitioned, q_partition, spmv_dist) with a
+# gloo transport in place of NCCL; every rank must end with the hierarchy -- and the solution of a
+# V-cycle -- one rank builds, bit for bit.
 # ---------------------------------------------------------------------------------------
 def _dist_worker(rank, world, port, q, case):
     import numpy as np
@@ -71,13 +72,28 @@ def _dist_worker(rank, world, port, q, case):
         L = api.lib(EMU_SO)
         mat = {"poisson7_8": lambda: matrices.poisson7(8), "aniso_6": lambda: matrices.aniso7(6),
                "amgdmp": lambda: matrices.read_amgdmp(os.path.join(ROOT, "tests", "golden"))}[case]()
-        single = fetch(amg.amg_setup(*mat, L=L))             # before joining: one rank, no exchange
+        H1 = amg.amg_setup(*mat, L=L)                        # before joining: one rank, no exchange
+        single = fetch(H1)
+        n = single.levels[0]["A"][3][0]
+        b = np.random.default_rng(7).standard_normal(n)
+        x1 = H1.solve(b)
         api.comm_init_host_gloo(L)
         assert L.amgb_comm_size() == world and L.amgb_comm_rank() == rank
         H = amg.amg_setup(*mat, L=L)
         t = H.timing()
         got = fetch(H)
         bad = orc.compare(got, single)
+        # the V-cycle on the ranks together: row blocks of every matrix-vector product, the result
+        # vectors exchanged -- the same bits as one rank's cycle, on every rank
+        import ctypes
+        c0, c1, nb = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        L.amgb_comm_stats(ctypes.byref(c0), ctypes.byref(nb))
+        x = H.solve(b)
+        L.amgb_comm_stats(ctypes.byref(c1), ctypes.byref(nb))
+        if not np.array_equal(x, x1):
+            bad.append("partitioned V-cycle differs from the single-rank one by %g" % np.abs(x - x1).max())
+        if c1.value <= c0.value:
+            bad.append("the V-cycle exchanged nothing")
         api.comm_finalize(L)
         q.put((rank, bad[:3], int(t["comm_calls"]), int(t["comm_bytes"])))
     finally:
