@@ -11,12 +11,21 @@ namespace amgb {
 // [n r/P, n (r+1)/P) of the product with the single-GPU kernels and the blocks of the result vector
 // are exchanged in place (comm_allgatherv: NCCL over NVLink) -- so a cycle streams every matrix
 // once across the box instead of once per GPU.  Every row sum is formed by exactly one rank in the
-// single-GPU order, so the cycle is bit-identical to one GPU's.  Levels whose matrices are below
-// the work threshold (comm_min_work) and all vector updates stay replicated: a vector of a large
-// level is a few MB, an exchange costs more than the update.
+// single-GPU order, so the cycle is bit-identical to one GPU's.  Matrices below the work threshold
+// and all vector updates stay replicated: an exchange costs 15-30 us of NCCL latency, which a
+// row block must save first -- at ~3 TB/s per GPU that is a matrix of about 8 M entries
+// (AMGB_DIST_MIN_NNZ_SOLVE, default 2^23; AMGB_DIST_MIN_NNZ when that is set, as in the tests).
+static i64 solve_min_work() {
+  static i64 v = -1;
+  if (v < 0) {
+    const char *e = getenv("AMGB_DIST_MIN_NNZ_SOLVE"), *g = getenv("AMGB_DIST_MIN_NNZ");
+    v = e ? atoll(e) : g ? atoll(g) : (i64)1 << 23;
+  }
+  return v;
+}
 static void spmv_dist(double *z, double alpha, const double *y, double beta, const Csr &M, const double *x) {
   const int P = comm_size();
-  if (P <= 1 || M.nnz < comm_min_work() || M.rn < P) { spmv(z, alpha, y, beta, M, x); return; }
+  if (P <= 1 || M.nnz < solve_min_work() || M.rn < P) { spmv(z, alpha, y, beta, M, x); return; }
   const int r = comm_rank();
   spmv_rows(z, alpha, y, beta, M, x, (int)row_split(M.rn, r), (int)row_split(M.rn, r + 1));
   std::vector<i64> off((size_t)P + 1);
@@ -100,8 +109,14 @@ void vcycle_solve_graph(const Hierarchy &H, double *x, const double *b) {
   Context &c = ctx();
   // the first solve runs plainly: it allocates the per-level workspaces and warms the allocator's
   // cache, so that the capture below makes no driver call besides the launches
-  // several ranks: the exchanges are NCCL calls; the cycle runs uncaptured
-  if (!on || g.calls < 1 || comm_active()) { vcycle_solve(H, x, b); g.calls++; return; }
+  // several ranks with at least one partitioned product: the exchanges are NCCL calls; the cycle
+  // runs uncaptured
+  bool exchanges = false;
+  if (comm_active())
+    for (const Level &L : H.lv)
+      for (const Csr *M : {&L.Wt, &L.W, &L.AfP, &L.Af})
+        if (M->nnz >= solve_min_work() && M->rn >= comm_size()) exchanges = true;
+  if (!on || g.calls < 1 || exchanges) { vcycle_solve(H, x, b); g.calls++; return; }
   if (!g.exec || g.x != x || g.b != b) {
     if (g.exec) { cudaGraphExecDestroy((cudaGraphExec_t)g.exec); g.exec = nullptr; }
     const i64 l0 = c.launches;
