@@ -344,6 +344,7 @@ def main():
     def step_device():
         H = api.amg_setup(dAi.data_ptr(), dAj.data_ptr(), dAv.data_ptr(), L=L, device_ptrs=True, nnz=nnz)
         t = H.timing()
+        t["spmv_device_s"], t["spmv_bytes"], t["spmv_calls"] = H.spmv_stats()
         H.free()
         return t
 
@@ -362,6 +363,9 @@ def main():
             dist.destroy_process_group()
         return
 
+    # CUDA events around every long-row SpMV call of the timed steps (two events per call: the
+    # second roofline object; the SpGEMM kernels are timed the same way by default)
+    L.amgb_spmv_stats_enable(1)
     for _ in range(args.warmup):
         step_device()
     sampler = ClockSampler(local)
@@ -378,6 +382,7 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dev_s, wall = float(tt[0]), float(tt[1])
     per_step = dev_s / args.steps
+    L.amgb_spmv_stats_enable(0)
 
     # end to end through the host-buffer entry point
     step_e2e()
@@ -463,6 +468,22 @@ def main():
                          "algorithmic_bytes_per_call": sp_b / max(sp_n, 1), "calls": int(sp_n),
                          "share_of_step": sp_s / dev_s if dev_s else None},
         }
+        # the kernel family with the largest share of the step besides SpGEMM: the ordered-row-sum
+        # SpMV kernels on matrices with more than 24 entries per row (k_spmv_pipe / k_spmv_tile; the
+        # coarsening, find_support, Lanczos and PCG loops), same definition of the numbers
+        mv_s = sum(t["spmv_device_s"] for t in tims)
+        mv_b = sum(t["spmv_bytes"] for t in tims)
+        mv_n = sum(t["spmv_calls"] for t in tims)
+        if mv_s > 0:
+            mv_ach = mv_b / mv_s / 1e9
+            line["roofline_spmv"] = {"bound": "hbm", "kernel": "long-row SpMV family (k_spmv_pipe<16,1>, <8,4>, k_spmv_tile<8>, k_spmv_chain)",
+                                     "achieved": mv_ach, "peak": peak, "unit": "GB/s", "frac": mv_ach / peak if peak else None,
+                                     "peak_source": peak_src, "traffic": None,
+                                     "launch_seconds": mv_s / max(mv_n, 1), "algorithmic_bytes_per_call": mv_b / max(mv_n, 1),
+                                     "calls": int(mv_n), "share_of_step": mv_s / dev_s if dev_s else None,
+                                     "note": "12 B per entry + 12/20 B per row, matrix streamed once per call; the gather of x "
+                                             "moves a 32 B sector per entry through L2, which is what bounds these kernels at ~3 TB/s "
+                                             "(profiles/r2_spmv_stream_and_evict_first_experiments.txt)"}
         if sample is not None:
             ts, srows = time_cpu_port(args.workload, args.sample_n, 1)
             line["cpu_baseline"] = {

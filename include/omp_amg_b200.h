@@ -73,6 +73,12 @@ int amgb_solve_device(const amgb_hier *h, double *dx, const double *db);      /*
  * t[13]=exchanges of the row-partitioned stages  t[14]=bytes this rank received in them
  * t[15]=device seconds inside the exchanges */
 int amgb_timing(const amgb_hier *h, double t[16]);
+/* Opt-in statistics of the long-row SpMV kernels (matrices with more than 24 entries per row) of
+ * the setups that follow: out[0]=device seconds (CUDA events around every call), out[1]=their
+ * algorithmic bytes (12 B per entry -- 8 B when the vector is an implicit vector of ones -- plus
+ * 12 or 20 B per row), out[2]=calls.  Off by default (two events per call). */
+int amgb_spmv_stats_enable(int on);
+int amgb_spmv_stats(const amgb_hier *h, double out[3]);
 
 /* ---- several GPUs: one process per GPU, row-partitioned stages ----
  * The reference distributes the coarse problem over MPI ranks (struct comm, crs.h:14; the setup

@@ -56,6 +56,8 @@ def _declare(L):
     L.amgb_solve.argtypes = [vp, f64p, f64p]
     L.amgb_solve_device.argtypes = [vp, vp, vp]
     L.amgb_timing.argtypes = [vp, C.POINTER(C.c_double)]
+    L.amgb_spmv_stats_enable.argtypes = [C.c_int]
+    L.amgb_spmv_stats.argtypes = [vp, C.POINTER(C.c_double)]
     L.amgb_set_reduce_mode.argtypes = [C.c_int]
     L.amgb_release_memory.restype = None
     L.amgb_peak_device_bytes.restype = C.c_int64
@@ -297,6 +299,13 @@ class Hierarchy:
                 "spgemm_device_s", "spgemm_bytes", "spgemm_calls", "launches", "syncs", "device_total_s",
                 "comm_calls", "comm_bytes", "comm_device_s")
         return dict(zip(keys, list(t)))
+
+    def spmv_stats(self):
+        """(device seconds, algorithmic bytes, calls) of the long-row SpMV kernels of this setup
+        (zeros unless amgb_spmv_stats_enable(1) was called before it)."""
+        t = (C.c_double * 3)()
+        _check(self._L, self._L.amgb_spmv_stats(self._h, t))
+        return float(t[0]), int(t[1]), int(t[2])
 
     def free(self):
         if self._h:

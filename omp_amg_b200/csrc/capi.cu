@@ -360,6 +360,14 @@ int amgb_timing(const amgb_hier *h, double t[16]) {
   return 0;
 }
 
+// opt-in statistics of the long-row SpMV kernels during setups (bench.py's second roofline)
+int amgb_spmv_stats_enable(int on) { spmv_stats_enable(on != 0); return 0; }
+int amgb_spmv_stats(const amgb_hier *h, double out[3]) {
+  if (!h) return fail(-2, "null hierarchy");
+  out[0] = h->H.t.spmv; out[1] = (double)h->H.t.spmv_bytes; out[2] = (double)h->H.t.spmv_calls;
+  return 0;
+}
+
 // ---- ranks (one process per GPU) ----
 int amgb_comm_unique_id(uint8_t id[128]) {
   API_BEGIN

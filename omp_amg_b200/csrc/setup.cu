@@ -917,6 +917,7 @@ void setup(i64 nnz, const int *dAi, const int *dAj, const double *dAv, Hierarchy
   const double t_begin = now_s();
   double t0 = t_begin;
   spgemm_stats_reset();
+  spmv_stats_reset();
   comm_stats_reset();
 #ifndef AMGB_EMU
   cudaEvent_t ev0, ev1;
@@ -1056,6 +1057,8 @@ void setup(i64 nnz, const int *dAi, const int *dAj, const double *dAv, Hierarchy
   H.t.device_total = H.t.total;
 #endif
   spgemm_stats_get(&H.t.spgemm, &H.t.spgemm_bytes, &H.t.spgemm_calls);
+  spmv_stats_get(&H.t.spmv, &H.t.spmv_bytes, &H.t.spmv_calls);
+  spmv_stats_reset();
   comm_stats_get(&H.t.comm_calls, &H.t.comm_bytes, &H.t.comm);
   spgemm_cache_reset();
   stage_report();

@@ -28,6 +28,8 @@ struct StageTimes {    // host wall-clock with a stream sync at stage ends, seco
   double spgemm = 0;   // device time (CUDA events) inside the SpGEMM kernels
   i64 spgemm_bytes = 0;  // algorithmic bytes moved by those kernels
   i64 spgemm_calls = 0;
+  double spmv = 0;     // the same for the long-row SpMV kernels, when spmv_stats_enable(true) (sparse.cuh)
+  i64 spmv_bytes = 0, spmv_calls = 0;
   i64 comm_calls = 0, comm_bytes = 0;   // exchanges of the row-partitioned stages (comm.cuh)
   double comm = 0;                      // device seconds inside them
 };

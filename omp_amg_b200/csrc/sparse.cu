@@ -5,6 +5,35 @@
 
 namespace amgb {
 
+// ---- SpMV statistics (opt-in: spmv_stats_enable; bench.py's second roofline) ----
+// device time (CUDA events around every call's launches) and algorithmic bytes of the kernels
+// that apply a matrix with more than 24 entries per row (the k_spmv_pipe / k_spmv_tile family)
+namespace {
+struct SpmvStats {
+  bool on = false;
+  i64 bytes = 0, calls = 0;
+#ifndef AMGB_EMU
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+#endif
+};
+SpmvStats g_spmv_stats;
+}  // namespace
+void spmv_stats_enable(bool on) { g_spmv_stats.on = on; }
+void spmv_stats_reset() {
+#ifndef AMGB_EMU
+  for (auto &e : g_spmv_stats.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  g_spmv_stats.ev.clear();
+#endif
+  g_spmv_stats.bytes = 0; g_spmv_stats.calls = 0;
+}
+void spmv_stats_get(double *seconds, i64 *bytes, i64 *calls) {
+  double sec = 0;
+#ifndef AMGB_EMU
+  for (auto &e : g_spmv_stats.ev) { float ms = 0; if (cudaEventElapsedTime(&ms, e.first, e.second) == cudaSuccess) sec += ms * 1e-3; }
+#endif
+  *seconds = sec; *bytes = g_spmv_stats.bytes; *calls = g_spmv_stats.calls;
+}
+
 void fill(double *p, i64 n, double v) { parallel_for(n, [=] DEV(i64 i) { p[i] = v; }); }
 void fill_int(int *p, i64 n, int v) { parallel_for(n, [=] DEV(i64 i) { p[i] = v; }); }
 
@@ -289,6 +318,12 @@ static void spmv_vals_run(double *zf, double alpha, const double *yf, double bet
   static double t1 = -1;       // rows up to this average length: one thread per row (AMGB_SPMV_T1)
   if (t1 < 0) { const char *e = getenv("AMGB_SPMV_T1"); t1 = e ? atof(e) : 24.0; }
   bool done = false;
+  cudaEvent_t se0 = nullptr, se1 = nullptr;
+  const bool stat = g_spmv_stats.on && rn == M.rn && rn > 0 && (double)M.nnz / (double)M.rn > t1 && !gen;
+  if (stat) {
+    if (cudaEventCreate(&se0) == cudaSuccess && cudaEventCreate(&se1) == cudaSuccess) cudaEventRecord(se0, c.stream);
+    else { if (se0) cudaEventDestroy(se0); se0 = se1 = nullptr; }
+  }
   if (rn > 0 && (double)M.nnz / (double)M.rn > t1) {
     // AMGB_SPMV=row32 | pipe16 | auto (default: 16 lanes per row, 8 lanes x 4 entries for a few
     // thousand rows of a few thousand entries; measured per matrix in profiles/r2_spmv_variants_poisson7_128.txt)
@@ -325,6 +360,13 @@ static void spmv_vals_run(double *zf, double alpha, const double *yf, double bet
     const int grid = M.n_long < c.sm_count * 6 ? M.n_long : c.sm_count * 6;
     k_spmv_chain<<<grid, 256, 0, c.stream>>>(M.long_rows.p, M.long_rows.p + cap, M.ro.p, col, vals, x, zf, alpha, yf, beta, plain, postf, r0, r1);
     c.launches++; post_launch("spmv_chain");
+  }
+  if (se0 && se1) {
+    cudaEventRecord(se1, c.stream);
+    g_spmv_stats.ev.emplace_back(se0, se1);
+    // matrix once (values, and columns unless x is the implicit vector of ones), row offsets, z, and y when read
+    g_spmv_stats.bytes += (x ? 12 : 8) * M.nnz + (plain ? 12 : 20) * (i64)M.rn;
+    g_spmv_stats.calls++;
   }
 #endif
 }

@@ -67,6 +67,11 @@ int max_row_len(const Csr &A);
 
 void trace_csr(const char *tag, const Csr &A);
 
+// opt-in statistics of the long-row SpMV kernels (more than 24 entries per row): device time and
+// algorithmic bytes ((12 nnz, 8 without a gather) + 12 or 20 per row) since the last reset
+void spmv_stats_enable(bool on);
+void spmv_stats_reset();
+void spmv_stats_get(double *seconds, i64 *bytes, i64 *calls);
 // device time / algorithmic bytes of the SpGEMM kernels since the last reset (spgemm.cu)
 void spgemm_stats_reset();
 void spgemm_cache_reset();      // drops the cached transpose of the last large left operand
