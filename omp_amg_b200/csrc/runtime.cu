@@ -709,12 +709,14 @@ __global__ void __launch_bounds__(EPS_T) k_eps_chunk_stats(const double *a, cons
   if (R.kind != 0) continue;
   const i64 n = R.end;
   const int sex = R.gsex, ssign = R.gsign;
+  // an unusable hypothesis is a property of the record, the same for every thread (bad_sh is
+  // written by whichever thread meets a bad term later on and is only read after the barriers)
+  if (sex == 0 || sex == 0x7ff) { if (t == 0) R.bad = 1; continue; }
   if (t == 0) {
-    first_tie = EPS_C; bad_sh = (sex == 0 || sex == 0x7ff) ? 1 : 0; d0_sh = 0;
+    first_tie = EPS_C; bad_sh = 0; d0_sh = 0;
     lo_pre = lo_post = (1LL << 62); hi_pre = hi_post = -(1LL << 62);
   }
   __syncthreads();
-  if (bad_sh) { if (t == 0) R.bad = 1; continue; }
   const int se = sex - 1075;
   const i64 base = R.begin + (i64)t * EPS_E;
   long long fl[EPS_E];
