@@ -7,32 +7,10 @@
 namespace amgb {
 
 // Several ranks (one process per GPU, every rank holding the hierarchy and the same b): the
-// matrix-vector products of the large levels are ROW-PARTITIONED -- rank r forms rows
-// [n r/P, n (r+1)/P) of the product with the single-GPU kernels and the blocks of the result vector
-// are exchanged in place (comm_allgatherv: NCCL over NVLink) -- so a cycle streams every matrix
-// once across the box instead of once per GPU.  Every row sum is formed by exactly one rank in the
-// single-GPU order, so the cycle is bit-identical to one GPU's.  Matrices below the work threshold
-// and all vector updates stay replicated: an exchange costs 15-30 us of NCCL latency, which a
-// row block must save first -- at ~3 TB/s per GPU that is a matrix of about 8 M entries
-// (AMGB_DIST_MIN_NNZ_SOLVE, default 2^23; AMGB_DIST_MIN_NNZ when that is set, as in the tests).
-static i64 solve_min_work() {
-  static i64 v = -1;
-  if (v < 0) {
-    const char *e = getenv("AMGB_DIST_MIN_NNZ_SOLVE"), *g = getenv("AMGB_DIST_MIN_NNZ");
-    v = e ? atoll(e) : g ? atoll(g) : (i64)1 << 23;
-  }
-  return v;
-}
-static void spmv_dist(double *z, double alpha, const double *y, double beta, const Csr &M, const double *x) {
-  const int P = comm_size();
-  if (P <= 1 || M.nnz < solve_min_work() || M.rn < P) { spmv(z, alpha, y, beta, M, x); return; }
-  const int r = comm_rank();
-  spmv_rows(z, alpha, y, beta, M, x, (int)row_split(M.rn, r), (int)row_split(M.rn, r + 1));
-  std::vector<i64> off((size_t)P + 1);
-  for (int q = 0; q <= P; q++) off[(size_t)q] = (i64)sizeof(double) * row_split(M.rn, q);
-  comm_allgatherv(z, off.data(), "comm.vcycle", false);
-}
-
+// matrix-vector products of the large levels are row-partitioned (sparse.cu: spmv_vals inside a
+// SpmvPartitionScope) -- a cycle streams every large matrix once across the box instead of once
+// per GPU, and is bit-identical to one GPU's.  The vector updates and the small levels stay
+// replicated: a vector of a large level is a few MB, an exchange costs more than the update.
 void vcycle_level(const Hierarchy &H, int l, double *x, const double *b) {
   const Level &L = H.lv[(size_t)l];
   if (l == (int)H.lv.size() - 1) {
@@ -53,12 +31,12 @@ void vcycle_level(const Hierarchy &H, int l, double *x, const double *b) {
   double *bfp = bf.p, *bcp = bc.p, *xcp = xc.p, *xfp = xf.p, *tp = t.p;
   parallel_for(n, [=] DEV(i64 i) { if (Cf[i] != 0.) bcp[cpos[i]] = b[i]; else bfp[fpos[i]] = b[i]; });
   // b_{l+1} += W^t b_l
-  spmv_dist(tp, 0, nullptr, 1, L.Wt, bfp);
+  spmv(tp, 0, nullptr, 1, L.Wt, bfp);
   parallel_for(nc, [=] DEV(i64 i) { bcp[i] = 1 * bcp[i] + 1 * tp[i]; });
   vcycle_level(H, l + 1, xcp, bcp);
   // x_l = W x_{l+1};  b_l -= AfP x_{l+1}
-  spmv_dist(xfp, 0, bfp, 1, L.W, xcp);
-  spmv_dist(bfp, 1, bfp, -1, L.AfP, xcp);
+  spmv(xfp, 0, bfp, 1, L.W, xcp);
+  spmv(bfp, 1, bfp, -1, L.AfP, xcp);
   const double *d = L.D.p;
   double *c = c1.p, *co = c2.p, *rp = r.p;
   const unsigned m = (unsigned)L.m;
@@ -67,14 +45,14 @@ void vcycle_level(const Hierarchy &H, int l, double *x, const double *b) {
   if (m > 1) {
     alpha = L.rho / 2; alpha *= alpha;
     gamma = 2 * alpha / (1 - 2 * alpha); beta = 1 + gamma;
-    spmv_dist(rp, 1, bfp, -1, L.Af, c);
+    spmv(rp, 1, bfp, -1, L.Af, c);
     { double *s = c; c = co; co = s; }
     { double *cc = c, *cco = co; const double bt = beta;
       parallel_for(nf, [=] DEV(i64 i) { cc[i] = bt * (cco[i] + d[i] * rp[i]); }); }
   }
   for (unsigned ci = 3; ci <= m; ci++) {
     gamma = alpha * beta; gamma = gamma / (1 - gamma); beta = 1 + gamma;
-    spmv_dist(rp, 1, bfp, -1, L.Af, c);
+    spmv(rp, 1, bfp, -1, L.Af, c);
     { double *s = c; c = co; co = s; }
     { double *cc = c, *cco = co; const double bt = beta, gm = gamma;
       parallel_for(nf, [=] DEV(i64 i) { cc[i] = bt * (cco[i] + d[i] * rp[i]) - gm * cc[i]; }); }
@@ -87,6 +65,7 @@ void vcycle_level(const Hierarchy &H, int l, double *x, const double *b) {
 }
 
 void vcycle_solve(const Hierarchy &H, double *x, const double *b) {
+  SpmvPartitionScope partition_;
   const int n = H.n0;
   vcycle_level(H, 0, x, b);
   (void)n;
@@ -112,10 +91,12 @@ void vcycle_solve_graph(const Hierarchy &H, double *x, const double *b) {
   // several ranks with at least one partitioned product: the exchanges are NCCL calls; the cycle
   // runs uncaptured
   bool exchanges = false;
-  if (comm_active())
+  if (comm_active()) {
+    SpmvPartitionScope partition_;
     for (const Level &L : H.lv)
       for (const Csr *M : {&L.Wt, &L.W, &L.AfP, &L.Af})
-        if (M->nnz >= solve_min_work() && M->rn >= comm_size()) exchanges = true;
+        if (spmv_is_partitioned(*M)) exchanges = true;
+  }
   if (!on || g.calls < 1 || exchanges) { vcycle_solve(H, x, b); g.calls++; return; }
   if (!g.exec || g.x != x || g.b != b) {
     if (g.exec) { cudaGraphExecDestroy((cudaGraphExec_t)g.exec); g.exec = nullptr; }

@@ -254,8 +254,44 @@ static void spmv_vals_run(double *z, double alpha, const double *y, double beta,
 void spmv_rows(double *z, double alpha, const double *y, double beta, const Csr &M, const double *x, int r0, int r1) {
   if (r1 > r0) spmv_vals_run(z, alpha, y, beta, M, M.a.p, x, nullptr, nullptr, 0, r0, r1);
 }
+// Several ranks: a product with a large matrix is ROW-PARTITIONED -- rank r forms rows
+// [n r/P, n (r+1)/P) with the single-GPU kernels and the blocks of z are exchanged in place -- when
+// the caller's phase asks for it (spmv_partition: always inside the V-cycle, solve.cu; inside the
+// setup loops only with AMGB_DIST_SPMV=1).  Every row sum is formed by exactly
+// one rank in the single-GPU order, so z is bit-identical on every rank.  An exchange costs
+// 15-30 us of NCCL latency, which a row block must save first: at ~3 TB/s per GPU that is a matrix
+// of about 8 M entries (AMGB_DIST_MIN_NNZ_SOLVE, default 2^23; AMGB_DIST_MIN_NNZ when only that
+// is set, as in the tests).
+static int g_spmv_partition = -1;      // -1: env not read yet; bit 0 = setup default, bit 1 = forced on by a scope
+i64 spmv_partition_min_nnz() {
+  static i64 v = -1;
+  if (v < 0) {
+    const char *e = getenv("AMGB_DIST_MIN_NNZ_SOLVE"), *g = getenv("AMGB_DIST_MIN_NNZ");
+    v = e ? atoll(e) : g ? atoll(g) : (i64)1 << 23;
+  }
+  return v;
+}
+static int spmv_partition_state() {
+  if (g_spmv_partition < 0) { const char *e = getenv("AMGB_DIST_SPMV"); g_spmv_partition = (e && *e == '1') ? 1 : 0; }
+  return g_spmv_partition;
+}
+SpmvPartitionScope::SpmvPartitionScope() { prev = spmv_partition_state(); g_spmv_partition = prev | 2; }
+SpmvPartitionScope::~SpmvPartitionScope() { g_spmv_partition = prev; }
+bool spmv_is_partitioned(const Csr &M) {
+  return comm_active() && spmv_partition_state() != 0 && M.rn >= comm_size() && M.nnz >= spmv_partition_min_nnz();
+}
+
 void spmv_vals(double *z, double alpha, const double *y, double beta, const Csr &M, const double *vals,
                const double *x, const double *post, const int *gen, int want) {
+  if (!gen && spmv_is_partitioned(M)) {
+    const int P = comm_size(), r = comm_rank();
+    const int r0 = (int)row_split(M.rn, r), r1 = (int)row_split(M.rn, r + 1);
+    if (r1 > r0) spmv_vals_run(z, alpha, y, beta, M, vals, x, post, nullptr, 0, r0, r1);
+    std::vector<i64> off((size_t)P + 1);
+    for (int q = 0; q <= P; q++) off[(size_t)q] = (i64)sizeof(double) * row_split(M.rn, q);
+    comm_allgatherv(z, off.data(), "comm.spmv", false);
+    return;
+  }
 #ifndef AMGB_EMU
   static int logit = -1;
   if (logit < 0) { const char *e = getenv("AMGB_SPMV_LOG"); logit = (e && *e && *e != '0') ? 1 : 0; }

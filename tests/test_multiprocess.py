@@ -60,11 +60,12 @@ def test_max_over_ranks_reduction_gloo_world2():
 # gloo transport in place of NCCL; every rank must end with the hierarchy -- and the solution of a
 # V-cycle -- one rank builds, bit for bit.
 # ---------------------------------------------------------------------------------------
-def _dist_worker(rank, world, port, q, case):
+def _dist_worker(rank, world, port, q, case, dist_spmv="0"):
     import numpy as np
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
-                      AMGB_DIST_MIN_NNZ="0")     # partition every product, however small
+                      AMGB_DIST_MIN_NNZ="0",     # partition every product, however small
+                      AMGB_DIST_SPMV=dist_spmv)  # "1": also the matrix-vector products of the setup loops
     from util import EMU_SO, api, amg, fetch, orc
     from omp_amg_b200 import matrices
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -100,15 +101,17 @@ def _dist_worker(rank, world, port, q, case):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case,world,port", [("poisson7_8", 2, 29641), ("aniso_6", 3, 29642), ("amgdmp", 2, 29643),
-                                             ("amgdmp", 4, 29644)])     # 49 rows over 4 ranks: blocks of 1-4 rows on the coarse levels
-def test_row_partitioned_setup_matches_single_rank(case, world, port):
+@pytest.mark.parametrize("case,world,port,dist_spmv",
+                         [("poisson7_8", 2, 29641, "0"), ("aniso_6", 3, 29642, "0"), ("amgdmp", 2, 29643, "0"),
+                          ("amgdmp", 4, 29644, "0"),     # 49 rows over 4 ranks: blocks of 1-4 rows on the coarse levels
+                          ("poisson7_8", 3, 29646, "1"), ("amgdmp", 2, 29647, "1")])   # setup SpMVs partitioned too
+def test_row_partitioned_setup_matches_single_rank(case, world, port, dist_spmv):
     import torch.multiprocessing as mp
     subprocess.run(["make", "-j4", "-C", os.path.join(ROOT, "omp_amg_b200", "csrc"), "emu"], check=True,
                    stdout=subprocess.DEVNULL)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    ps = [ctx.Process(target=_dist_worker, args=(r, world, port, q, case)) for r in range(world)]
+    ps = [ctx.Process(target=_dist_worker, args=(r, world, port, q, case, dist_spmv)) for r in range(world)]
     for p in ps:
         p.start()
     out = sorted(q.get(timeout=600) for _ in ps)
