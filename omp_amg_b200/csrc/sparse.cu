@@ -255,24 +255,26 @@ void spmv_rows(double *z, double alpha, const double *y, double beta, const Csr 
   if (r1 > r0) spmv_vals_run(z, alpha, y, beta, M, M.a.p, x, nullptr, nullptr, 0, r0, r1);
 }
 // Several ranks: a product with a large matrix is ROW-PARTITIONED -- rank r forms rows
-// [n r/P, n (r+1)/P) with the single-GPU kernels and the blocks of z are exchanged in place -- when
-// the caller's phase asks for it (spmv_partition: always inside the V-cycle, solve.cu; inside the
-// setup loops only with AMGB_DIST_SPMV=1).  Every row sum is formed by exactly
-// one rank in the single-GPU order, so z is bit-identical on every rank.  An exchange costs
-// 15-30 us of NCCL latency, which a row block must save first: at ~3 TB/s per GPU that is a matrix
-// of about 8 M entries (AMGB_DIST_MIN_NNZ_SOLVE, default 2^23; AMGB_DIST_MIN_NNZ when only that
-// is set, as in the tests).
+// [n r/P, n (r+1)/P) with the single-GPU kernels and the blocks of z are exchanged in place
+// (comm_allgatherv).  Every row sum is formed by exactly one rank in the single-GPU order, so z is
+// bit-identical on every rank.  An exchange costs 15-35 us of NCCL latency, which a row block
+// must save first.  Measured on 2 B200, one 128^3 setup (2.38 s with replicated products): 2.33 s
+// with every matrix of 2^23 entries or more partitioned (5 300 more exchanges), 2.28 s from
+// 20 M entries on (1 900 more) -- hence the default threshold (AMGB_DIST_MIN_NNZ_SOLVE;
+// AMGB_DIST_MIN_NNZ when only that is set, as in the tests).  AMGB_DIST_SPMV=0 keeps the
+// products of the setup loops replicated; inside the V-cycle (SpmvPartitionScope, solve.cu) the
+// partition is always on.
 static int g_spmv_partition = -1;      // -1: env not read yet; bit 0 = setup default, bit 1 = forced on by a scope
 i64 spmv_partition_min_nnz() {
   static i64 v = -1;
   if (v < 0) {
     const char *e = getenv("AMGB_DIST_MIN_NNZ_SOLVE"), *g = getenv("AMGB_DIST_MIN_NNZ");
-    v = e ? atoll(e) : g ? atoll(g) : (i64)1 << 23;
+    v = e ? atoll(e) : g ? atoll(g) : (i64)20000000;
   }
   return v;
 }
 static int spmv_partition_state() {
-  if (g_spmv_partition < 0) { const char *e = getenv("AMGB_DIST_SPMV"); g_spmv_partition = (e && *e == '1') ? 1 : 0; }
+  if (g_spmv_partition < 0) { const char *e = getenv("AMGB_DIST_SPMV"); g_spmv_partition = (e && *e == '0') ? 0 : 1; }
   return g_spmv_partition;
 }
 SpmvPartitionScope::SpmvPartitionScope() { prev = spmv_partition_state(); g_spmv_partition = prev | 2; }

@@ -39,8 +39,8 @@ void spmv(double *z, double alpha, const double *y, double beta, const Csr &M, c
 // rows [r0, r1) of the same product only (z, y indexed by absolute row): the row blocks of the
 // partitioned V-cycle
 void spmv_rows(double *z, double alpha, const double *y, double beta, const Csr &M, const double *x, int r0, int r1);
-// row-partitioned products over several ranks (see sparse.cu): on inside a scope of this type (the
-// V-cycle), elsewhere only with AMGB_DIST_SPMV=1
+// row-partitioned products over several ranks (see sparse.cu): always on inside a scope of this
+// type (the V-cycle), elsewhere unless AMGB_DIST_SPMV=0
 struct SpmvPartitionScope { int prev; SpmvPartitionScope(); ~SpmvPartitionScope(); };
 bool spmv_is_partitioned(const Csr &M);
 // values-only variant: same pattern as M, other value array

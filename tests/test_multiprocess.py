@@ -65,7 +65,7 @@ def _dist_worker(rank, world, port, q, case, dist_spmv="0"):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       AMGB_DIST_MIN_NNZ="0",     # partition every product, however small
-                      AMGB_DIST_SPMV=dist_spmv)  # "1": also the matrix-vector products of the setup loops
+                      AMGB_DIST_SPMV=dist_spmv)  # "1" (the default): also the matrix-vector products of the setup loops
     from util import EMU_SO, api, amg, fetch, orc
     from omp_amg_b200 import matrices
     dist.init_process_group("gloo", rank=rank, world_size=world)
