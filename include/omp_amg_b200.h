@@ -102,6 +102,14 @@ int amgb_comm_init_host(int rank, int size, amgb_allgatherv_fn fn, void *user);
 int amgb_comm_finalize(void);
 int amgb_comm_rank(void);
 int amgb_comm_size(void);
+/* Partitioned STORAGE for the solve phase.  After a setup on several ranks every rank holds the
+ * whole hierarchy; this call (collective, every rank) keeps, of every matrix the V-cycle applies
+ * row-partitioned (W', W, AfP, Af of the large levels, amg.c:125-152), only this rank's row block
+ * and releases the rest -- the layout the reference's crs_data has after amg_setup_mats
+ * (amg.c:295-377: every rank stores its rows).  amgb_solve / crs_amg_solve keep working,
+ * bit-identically; the accessors of those matrices, amgb_export and amgb_hierarchy_hash then
+ * return -120.  released_bytes: device bytes this rank released.  One rank: no-op. */
+int amgb_partition_solve_storage(amgb_hier *h, int64_t *released_bytes);
 /* exchanges issued and bytes received by this rank since the last amgb_setup (setup stages and
  * the row-partitioned V-cycles after it; amgb_setup resets the counters) */
 int amgb_comm_stats(int64_t *calls, int64_t *bytes);

@@ -89,6 +89,7 @@ def _declare(L):
     L.amgb_comm_init.argtypes = [C.c_int, C.c_int, C.c_char_p]
     L.amgb_comm_init_host.argtypes = [C.c_int, C.c_int, ALLGATHERV_FN, vp]
     L.amgb_comm_stats.argtypes = [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.amgb_partition_solve_storage.argtypes = [vp, C.POINTER(C.c_int64)]
     return L
 
 
@@ -299,6 +300,14 @@ class Hierarchy:
                 "spgemm_device_s", "spgemm_bytes", "spgemm_calls", "launches", "syncs", "device_total_s",
                 "comm_calls", "comm_bytes", "comm_device_s")
         return dict(zip(keys, list(t)))
+
+    def partition_solve_storage(self):
+        """Several ranks (collective): keep only this rank's row blocks of the matrices the V-cycle
+        applies row-partitioned, release the rest; returns the device bytes released.  The hierarchy
+        then serves ``solve`` only."""
+        f = C.c_int64()
+        _check(self._L, self._L.amgb_partition_solve_storage(self._h, C.byref(f)))
+        return int(f.value)
 
     def spmv_stats(self):
         """(device seconds, algorithmic bytes, calls) of the long-row SpMV kernels of this setup

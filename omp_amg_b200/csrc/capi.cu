@@ -148,6 +148,7 @@ int amgb_get_csr(const amgb_hier *h, int l, int which, int32_t *rn, int32_t *cn,
   API_BEGIN
   const Csr *M = pick(h, l, which);
   if (!M) return fail(-2, "no such matrix");
+  if (M->partial) return fail(-120, "the storage of this matrix is partitioned for the solve phase (amgb_partition_solve_storage)");
   if (rn) *rn = M->rn;
   if (cn) *cn = M->cn;
   if (nnz) *nnz = M->nnz;
@@ -212,6 +213,7 @@ extern "C" int amgb_hierarchy_hash(const amgb_hier *h, uint64_t *out) {
   API_BEGIN
   if (!h || !out) return fail(-2, "null argument");
   const Hierarchy &H = h->H;
+  if (H.solve_only) return fail(-120, "the hierarchy's storage is partitioned for the solve phase (amgb_partition_solve_storage)");
   const int nl = (int)H.lv.size();
   unsigned long long x = 0xCBF29CE484222325ULL;
   fnv_word(x, (unsigned long long)nl); fnv_word(x, (unsigned long long)H.nullspace);
@@ -276,6 +278,7 @@ int save_mats(std::vector<int> &len, int n, int nl, const std::vector<int> &lvl,
 
 int amgb_export(const amgb_hier *h, const char *dir) {
   API_BEGIN
+  if (h && h->H.solve_only) return fail(-120, "the hierarchy's storage is partitioned for the solve phase (amgb_partition_solve_storage)");
   if (!h) return fail(-2, "null hierarchy");
   const Hierarchy &H = h->H;
   const int nl = (int)H.lv.size(), n = H.lv[0].n;
@@ -358,6 +361,17 @@ int amgb_timing(const amgb_hier *h, double t[16]) {
   t[9] = (double)s.spgemm_calls; t[10] = (double)h->H.launches; t[11] = (double)h->H.syncs;
   t[12] = s.device_total; t[13] = (double)s.comm_calls; t[14] = (double)s.comm_bytes; t[15] = s.comm;
   return 0;
+}
+
+// Several ranks: keep only this rank's row blocks of the matrices the V-cycle applies row-
+// partitioned, release the rest (collective; the hierarchy becomes solve-only)
+int amgb_partition_solve_storage(amgb_hier *h, int64_t *released_bytes) {
+  API_BEGIN
+  if (!h) return fail(-2, "null hierarchy");
+  const i64 f = partition_solve_storage(h->H);
+  if (released_bytes) *released_bytes = f;
+  return 0;
+  API_END
 }
 
 // opt-in statistics of the long-row SpMV kernels during setups (bench.py's second roofline)

@@ -55,6 +55,10 @@ struct Hierarchy {
   int n0 = 0;
   StageTimes t;
   i64 launches = 0, syncs = 0;
+  // amgb_partition_solve_storage: the matrices of the V-cycle hold only this rank's row blocks;
+  // the hierarchy then serves amgb_solve / crs_amg_solve only (accessors, export and the
+  // fingerprint refuse)
+  bool solve_only = false;
   mutable Buf<double> mean_scratch;     // device scalar of the mean projection
   // crs_solve's storage order (amg.c:438-446: unknowns sorted by the level at which they become
   // F, ascending inside a level): position of every top-level unknown, and the vector in that
@@ -76,6 +80,10 @@ void setup(i64 nnz, const int *dAi, const int *dAj, const double *dAv, Hierarchy
 void vcycle_solve(const Hierarchy &H, double *x, const double *b);
 // the same through a CUDA graph captured on the second call with the same vectors (AMGB_SOLVE_GRAPH=0: never)
 void vcycle_solve_graph(const Hierarchy &H, double *x, const double *b);
+// Several ranks: every rank keeps only its row blocks of the matrices the V-cycle applies row-
+// partitioned (Wt, W, AfP, Af of the large levels) and releases the rest; returns the bytes this
+// rank released.  Collective; the hierarchy becomes solve-only.
+i64 partition_solve_storage(Hierarchy &H);
 // x -= mean(x) (amg.c:181-184): the sum runs over crs_solve's level-sorted storage order and
 // stays on the device (no host round trip)
 void project_mean(const Hierarchy &H, double *x);

@@ -64,6 +64,21 @@ void vcycle_level(const Hierarchy &H, int l, double *x, const double *b) {
     }); }
 }
 
+i64 partition_solve_storage(Hierarchy &H) {
+  if (!comm_active()) return 0;
+  SpmvPartitionScope partition_;
+  const int r = comm_rank();
+  i64 freed = 0;
+  for (Level &L : H.lv)
+    for (Csr *M : {&L.Wt, &L.W, &L.AfP, &L.Af})
+      if (M->rn > 0 && spmv_is_partitioned(*M)) {
+        freed += csr_keep_row_block(*M, (int)row_split(M->rn, r), (int)row_split(M->rn, r + 1));
+        H.solve_only = true;
+      }
+  if (H.solve_only) dev_release_cache();       // hand the released blocks back to the driver
+  return freed;
+}
+
 void vcycle_solve(const Hierarchy &H, double *x, const double *b) {
   SpmvPartitionScope partition_;
   const int n = H.n0;

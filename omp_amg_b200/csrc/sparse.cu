@@ -198,14 +198,14 @@ __global__ void __launch_bounds__(256) k_spmv_pipe(int rn, const int *ro, const 
 __global__ void __launch_bounds__(256) k_spmv_chain(const int *rows, const int *nrows, const int *ro, const int *col,
                                                     const double *vals, const double *x, double *z, double alpha,
                                                     const double *y, double beta, bool plain, const double *post,
-                                                    int r0, int r1) {
+                                                    int r0, int r1, int shift) {
   __shared__ double buf[2][SPMV_CH];
   const int t = threadIdx.x;
   const int n = *nrows;
   for (int q = blockIdx.x; q < n; q += gridDim.x) {
     const int i = rows[q];
     if (i < r0 || i >= r1) continue;              // another rank's row block (block-uniform)
-    const int beg = ro[i], end = ro[i + 1];
+    const int beg = ro[i - shift], end = ro[i - shift + 1];    // ro starts at row `shift` (Csr::partial)
     const int nch = (end - beg + SPMV_CH - 1) / SPMV_CH;
     __syncthreads();
     for (int j = beg + t; j < end && j < beg + SPMV_CH; j += 256) buf[0][j - beg] = x ? vals[j] * x[col[j]] : vals[j] * 1.0;
@@ -242,10 +242,11 @@ __global__ void __launch_bounds__(256) k_spmv_chain(const int *rows, const int *
     }
   }
 }
-__global__ void __launch_bounds__(256) k_find_long_rows(int rn, const int *ro, int longrow, int cap, int *rows, int *count) {
+__global__ void __launch_bounds__(256) k_find_long_rows(int rn, const int *ro, int longrow, int cap, int *rows, int *count,
+                                                        int shift) {       // ro describes rows shift .. shift + rn
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= rn) return;
-  if (ro[i + 1] - ro[i] > longrow) { const int p = atomicAdd(count, 1); if (p < cap) rows[p] = i; }
+  if (ro[i + 1] - ro[i] > longrow) { const int p = atomicAdd(count, 1); if (p < cap) rows[p] = i + shift; }
 }
 #endif
 
@@ -294,6 +295,7 @@ void spmv_vals(double *z, double alpha, const double *y, double beta, const Csr 
     comm_allgatherv(z, off.data(), "comm.spmv", false);
     return;
   }
+  if (M.partial) throw Error(-120, "matrix storage is partitioned for the solve phase: the product needs the ranks it was partitioned over");
 #ifndef AMGB_EMU
   static int logit = -1;
   if (logit < 0) { const char *e = getenv("AMGB_SPMV_LOG"); logit = (e && *e && *e != '0') ? 1 : 0; }
@@ -320,7 +322,11 @@ void spmv_vals(double *z, double alpha, const double *y, double beta, const Csr 
 static void spmv_vals_run(double *zf, double alpha, const double *yf, double beta, const Csr &M, const double *vals,
                           const double *x, const double *postf, const int *genf, int want, int r0, int r1) {
   StageTimer st_("prim.spmv");
-  const int *ro = M.ro.p + r0, *col = M.col.p;
+  // a matrix whose storage is partitioned holds rows [row_lo, row_lo + own_rows) only
+  const int shift = M.partial ? M.row_lo : 0;
+  if (M.partial && (r0 < M.row_lo || r1 > M.row_lo + M.own_rows))
+    throw Error(-120, "matrix storage is partitioned for the solve phase: rows outside this rank's block were asked for");
+  const int *ro = M.ro.p + (r0 - shift), *col = M.col.p;
   double *z = zf + r0;
   const double *y = yf ? yf + r0 : nullptr, *post = postf ? postf + r0 : nullptr;
   const int *gen = genf ? genf + r0 : nullptr;
@@ -340,7 +346,8 @@ static void spmv_vals_run(double *zf, double alpha, const double *yf, double bet
       const int cap = M.rn < 16384 ? M.rn : 16384;
       M.long_rows.alloc((i64)cap + 1);
       dev_memset(M.long_rows.p + cap, 0, sizeof(int));
-      k_find_long_rows<<<(M.rn + 255) / 256, 256, 0, c.stream>>>(M.rn, M.ro.p, LR, cap, M.long_rows.p, M.long_rows.p + cap);
+      const int have = M.partial ? M.own_rows : M.rn;       // rows whose offsets are stored
+      if (have > 0) k_find_long_rows<<<(have + 255) / 256, 256, 0, c.stream>>>(have, M.ro.p, LR, cap, M.long_rows.p, M.long_rows.p + cap, shift);
       c.launches++; post_launch("find_long_rows");
       int cnt = 0;
       d2h(&cnt, M.long_rows.p + cap, sizeof(int));
@@ -396,7 +403,7 @@ static void spmv_vals_run(double *zf, double alpha, const double *yf, double bet
   if (M.n_long > 0) {
     const int cap = M.rn < 16384 ? M.rn : 16384;
     const int grid = M.n_long < c.sm_count * 6 ? M.n_long : c.sm_count * 6;
-    k_spmv_chain<<<grid, 256, 0, c.stream>>>(M.long_rows.p, M.long_rows.p + cap, M.ro.p, col, vals, x, zf, alpha, yf, beta, plain, postf, r0, r1);
+    k_spmv_chain<<<grid, 256, 0, c.stream>>>(M.long_rows.p, M.long_rows.p + cap, M.ro.p, col, vals, x, zf, alpha, yf, beta, plain, postf, r0, r1, shift);
     c.launches++; post_launch("spmv_chain");
   }
   if (se0 && se1) {
@@ -410,6 +417,29 @@ static void spmv_vals_run(double *zf, double alpha, const double *yf, double bet
 }
 void spmv(double *z, double alpha, const double *y, double beta, const Csr &M, const double *x) {
   spmv_vals(z, alpha, y, beta, M, M.a.p, x);
+}
+
+// Solve-phase storage partition: keep rows [r0, r1) of M (row offsets rebased to 0, the entries of
+// the block), release the rest.  rn/cn/nnz keep describing the whole matrix.
+i64 csr_keep_row_block(Csr &M, int r0, int r1) {
+  if (M.partial) return 0;
+  if (r0 < 0 || r1 > M.rn || r0 > r1) throw Error(-2, "csr_keep_row_block: bad row range");
+  const i64 before = (i64)sizeof(int) * (M.rn + 1) + (i64)(sizeof(int) + sizeof(double)) * M.nnz;
+  const int b = M.ro.get(r0), e = M.ro.get(r1);
+  const int own = r1 - r0;
+  Buf<int> ro2((i64)own + 1), col2((i64)(e - b));
+  Buf<double> a2((i64)(e - b));
+  { const int *ro = M.ro.p; int *o = ro2.p; parallel_for((i64)own + 1, [=] DEV(i64 i) { o[i] = ro[r0 + i] - b; }); }
+  if (e > b) {
+    d2d(col2.p, M.col.p + b, sizeof(int) * (size_t)(e - b));
+    d2d(a2.p, M.a.p + b, sizeof(double) * (size_t)(e - b));
+  }
+  stream_sync();                       // the old buffers are released next
+  M.ro = std::move(ro2); M.col = std::move(col2); M.a = std::move(a2);
+  M.partial = true; M.row_lo = r0; M.own_rows = own; M.own_nnz = e - b;
+  M.n_long = -1; M.long_rows.release();
+  const i64 after = (i64)sizeof(int) * (own + 1) + (i64)(sizeof(int) + sizeof(double)) * (e - b);
+  return before - after;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -22,6 +22,13 @@ struct Csr {
   // matrix and handled by a block each (sparse.cu: k_spmv_chain); -1 = not looked for yet
   mutable int n_long = -1;
   mutable Buf<int> long_rows;
+  // Solve-phase storage partition (csr_keep_row_block): only rows [row_lo, row_lo + own_rows) are
+  // stored -- ro has own_rows + 1 entries starting at 0, col/a the own_nnz entries of the block --
+  // while rn, cn and nnz keep describing the whole matrix (kernel selection and thresholds must
+  // not depend on the partition).  Such a matrix only serves row-partitioned products.
+  bool partial = false;
+  int row_lo = 0, own_rows = 0;
+  i64 own_nnz = 0;
   Csr() {}
   Csr(int rn_, int cn_, i64 nnz_) : rn(rn_), cn(cn_), nnz(nnz_), ro(rn_ + 1), col(nnz_), a(nnz_), uid(next_uid()) {}
   Csr(Csr &&) = default;
@@ -30,6 +37,7 @@ struct Csr {
     Csr B;
     B.rn = rn; B.cn = cn; B.nnz = nnz; B.uid = next_uid();
     B.ro = ro.clone(); B.col = col.clone(); B.a = a.clone();
+    B.partial = partial; B.row_lo = row_lo; B.own_rows = own_rows; B.own_nnz = own_nnz;
     return B;
   }
 };
@@ -39,6 +47,8 @@ void spmv(double *z, double alpha, const double *y, double beta, const Csr &M, c
 // rows [r0, r1) of the same product only (z, y indexed by absolute row): the row blocks of the
 // partitioned V-cycle
 void spmv_rows(double *z, double alpha, const double *y, double beta, const Csr &M, const double *x, int r0, int r1);
+// keeps rows [r0, r1) of M and releases the rest (see Csr::partial); returns the bytes released
+i64 csr_keep_row_block(Csr &M, int r0, int r1);
 // row-partitioned products over several ranks (see sparse.cu): always on inside a scope of this
 // type (the V-cycle), elsewhere unless AMGB_DIST_SPMV=0
 struct SpmvPartitionScope { int prev; SpmvPartitionScope(); ~SpmvPartitionScope(); };

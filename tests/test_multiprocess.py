@@ -95,6 +95,27 @@ def _dist_worker(rank, world, port, q, case, dist_spmv="0"):
             bad.append("partitioned V-cycle differs from the single-rank one by %g" % np.abs(x - x1).max())
         if c1.value <= c0.value:
             bad.append("the V-cycle exchanged nothing")
+        # partitioned STORAGE for the solve phase: every rank keeps its row blocks of W', W, AfP, Af
+        # and releases the rest; the cycle must not change by a bit, and the hierarchy is solve-only
+        freed = H.partition_solve_storage()
+        if freed <= 0:
+            bad.append("partition_solve_storage released nothing")
+        x2 = H.solve(b)
+        if not np.array_equal(x2, x1):
+            bad.append("V-cycle on partitioned storage differs by %g" % np.abs(x2 - x1).max())
+        x3, x3ref = H.solve(2.5 * b), H1.solve(2.5 * b)      # H1: whole storage (collective as well)
+        if not np.array_equal(x3, x3ref):
+            bad.append("second V-cycle on partitioned storage differs by %g" % np.abs(x3 - x3ref).max())
+        try:
+            H.csr(0, api.W)
+            bad.append("accessor of a partitioned matrix did not refuse")
+        except amg.AmgError:
+            pass
+        try:
+            H.hash()
+            bad.append("fingerprint of a solve-only hierarchy did not refuse")
+        except amg.AmgError:
+            pass
         api.comm_finalize(L)
         q.put((rank, bad[:3], int(t["comm_calls"]), int(t["comm_bytes"])))
     finally:

@@ -67,6 +67,13 @@ def main():
             for _ in range(10):
                 H.solve(b)
             tvp = (time.time() - t0) / 10
+        # partitioned storage for the solve phase: the same cycle from this rank's row blocks only
+        freed = H.partition_solve_storage()
+        x2 = H.solve(b)
+        if not np.array_equal(x2, x1):
+            bad.append("V-cycle on partitioned storage differs from one GPU's by %g" % np.abs(x2 - x1).max())
+        print("rank %d %-16s solve-phase storage partitioned: %.1f MB released on this rank, V-cycle %s"
+              % (rank, c, freed / 1e6, "IDENTICAL" if np.array_equal(x2, x1) else "DIFFERS"), flush=True)
         H.free()
         flag = torch.tensor([1 if bad else 0], device="cuda")
         dist.all_reduce(flag)
