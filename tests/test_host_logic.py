@@ -391,3 +391,18 @@ def test_bench_reference_arm_reports_an_unscaled_measurement():
     assert d["config"]["same_config_as_gpu_arm"] is False
     assert d["value"] == d["cpu_baseline"]["value"] == d["e2e"]["value"] and d["cpu_baseline"]["cores"] == 1
     assert abs(d["ms_per_step"] - 1e3 * d["value"]) < 1e-6
+
+
+def test_single_rank_partition_calls_are_no_ops(emu):
+    """One rank: amgb_partition_solve_storage releases nothing and leaves the hierarchy whole
+    (accessors and fingerprint keep working); the opt-in SpMV statistics are zero unless enabled."""
+    H = amg.amg_setup(*M.poisson7(6), L=emu)
+    h0 = H.hash()
+    assert H.partition_solve_storage() == 0
+    assert H.hash() == h0
+    ro, col, a, shape = H.csr(0, api.W)
+    assert len(col) == ro[-1]
+    assert H.spmv_stats() == (0.0, 0, 0)
+    cc, cb = ctypes.c_int64(-1), ctypes.c_int64(-1)
+    assert emu.amgb_comm_stats(ctypes.byref(cc), ctypes.byref(cb)) == 0
+    assert cc.value == 0 and cb.value == 0
