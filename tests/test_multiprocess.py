@@ -125,7 +125,8 @@ def _dist_worker(rank, world, port, q, case, dist_spmv="0"):
 @pytest.mark.parametrize("case,world,port,dist_spmv",
                          [("poisson7_8", 2, 29641, "0"), ("aniso_6", 3, 29642, "0"), ("amgdmp", 2, 29643, "0"),
                           ("amgdmp", 4, 29644, "0"),     # 49 rows over 4 ranks: blocks of 1-4 rows on the coarse levels
-                          ("poisson7_8", 3, 29646, "1"), ("amgdmp", 2, 29647, "1")])   # setup SpMVs partitioned too
+                          ("poisson7_8", 3, 29646, "1"), ("amgdmp", 2, 29647, "1"),    # setup SpMVs partitioned too
+                          ("poisson7_8", 8, 29648, "1")])                             # the rank count of one B200 box
 def test_row_partitioned_setup_matches_single_rank(case, world, port, dist_spmv):
     import torch.multiprocessing as mp
     subprocess.run(["make", "-j4", "-C", os.path.join(ROOT, "omp_amg_b200", "csrc"), "emu"], check=True,
